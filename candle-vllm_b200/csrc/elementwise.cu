@@ -1,0 +1,270 @@
+// elementwise.cu -- the small ops between the big kernels of a decoder layer (K15, K21) and the
+// fused rope + q-cast + cache-write used by the decode engine.
+//
+// Reference semantics: candle_nn::ops::rms_norm (layers/qrmsnorm.rs:28-31), FusedRope::apply_inplace
+// (layers/rotary_emb.rs:52-69, interleaved = rope_i for GGUF llama quantized_llama.rs:313-318),
+// silu(w1 x) * (w3 x) (quantized_llama.rs:32-37), to_dtype casts (layers/attention.rs:971-975),
+// tok_embeddings lookup (quantized_llama.rs:449), argmax sampling (pipeline.rs:2338).
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- rms_norm: one CTA per row, row cached in registers (n <= 8 * 1024 with 256 threads x 4 x float4...)
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, TOut* __restrict__ out, int n, float eps) {
+    const int row = blockIdx.x;
+    const float* xr = x + (int64_t)row * n;
+    __shared__ float red[8];
+    float ss = 0.f;
+    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
+        if (i + 3 < n) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + i);
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        } else {
+            for (int j = i; j < n; ++j) ss += xr[j] * xr[j];
+        }
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += (i < (int)(blockDim.x >> 5)) ? red[i] : 0.f;
+    const float sc = rsqrtf(tot / (float)n + eps);
+    TOut* o = out + (int64_t)row * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = from_f32<TOut>(xr[i] * sc * w[i]);
+}
+
+// ---- RoPE in place on f32 q,k --------------------------------------------------------------
+__global__ void fused_rope_f32_kernel(float* __restrict__ q, float* __restrict__ k,
+                                      const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                      const int64_t* __restrict__ positions, int num_heads, int num_kv_heads,
+                                      int head_dim, int interleaved) {
+    const int t = blockIdx.x;
+    const int half = head_dim >> 1;
+    const int64_t pos = positions[t];
+    const int total = (num_heads + num_kv_heads) * half;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int h = i / half, j = i % half;
+        float* p = h < num_heads ? q + ((int64_t)t * num_heads + h) * head_dim
+                                 : k + ((int64_t)t * num_kv_heads + (h - num_heads)) * head_dim;
+        const float c = cos_t[pos * half + j], s = sin_t[pos * half + j];
+        const int i0 = interleaved ? 2 * j : j, i1 = interleaved ? 2 * j + 1 : j + half;
+        const float a = p[i0], b = p[i1];
+        p[i0] = a * c - b * s;
+        p[i1] = a * s + b * c;
+    }
+}
+
+// ---- fused: rope(q,k) + q -> 16-bit + k,v -> cache (flash layout) ----------------------------
+// qkv f32 [T, (h + 2 kvh) * hd] is the packed output of the fused QKV projection.
+template <typename T16, bool kFp8>
+__global__ void __launch_bounds__(256)
+rope_and_cache_kernel(const float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
+                      const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                      const int64_t* __restrict__ positions, const int64_t* __restrict__ slot_mapping,
+                      int num_heads, int num_kv_heads, int head_dim, int interleaved) {
+    const int t = blockIdx.x;
+    const int half = head_dim >> 1;
+    const int64_t pos = positions[t];
+    const int64_t slot = slot_mapping[t];
+    const int row = (num_heads + 2 * num_kv_heads) * head_dim;
+    const float* src = qkv + (int64_t)t * row;
+    const int nrot = (num_heads + num_kv_heads) * half;
+    const int kvn = num_kv_heads * head_dim;
+    for (int i = threadIdx.x; i < nrot; i += blockDim.x) {
+        const int h = i / half, j = i % half;
+        const float c = cos_t[pos * half + j], s = sin_t[pos * half + j];
+        const int i0 = interleaved ? 2 * j : j, i1 = interleaved ? 2 * j + 1 : j + half;
+        const float a = src[h * head_dim + i0], b = src[h * head_dim + i1];
+        const float r0 = a * c - b * s, r1 = a * s + b * c;
+        if (h < num_heads) {
+            T16* o = q_out + ((int64_t)t * num_heads + h) * head_dim;
+            o[i0] = from_f32<T16>(r0);
+            o[i1] = from_f32<T16>(r1);
+        } else if (slot >= 0) {
+            const int64_t base = slot * kvn + (int64_t)(h - num_heads) * head_dim;
+            // reference: k -> model dtype first (attention.rs:971-975), then the cache write casts again
+            const float k0 = to_f32(from_f32<T16>(r0)), k1 = to_f32(from_f32<T16>(r1));
+            if constexpr (kFp8) {
+                static_cast<uint8_t*>(kc_)[base + i0] = f32_to_e4m3(k0);
+                static_cast<uint8_t*>(kc_)[base + i1] = f32_to_e4m3(k1);
+            } else {
+                static_cast<T16*>(kc_)[base + i0] = from_f32<T16>(r0);
+                static_cast<T16*>(kc_)[base + i1] = from_f32<T16>(r1);
+            }
+        }
+    }
+    if (slot >= 0) {
+        const float* v = src + (num_heads + num_kv_heads) * head_dim;
+        for (int i = threadIdx.x; i < kvn; i += blockDim.x) {
+            if constexpr (kFp8) static_cast<uint8_t*>(vc_)[slot * kvn + i] = f32_to_e4m3(to_f32(from_f32<T16>(v[i])));
+            else static_cast<T16*>(vc_)[slot * kvn + i] = from_f32<T16>(v[i]);
+        }
+    }
+}
+
+template <typename TOut>
+__global__ void silu_mul_kernel(const float* __restrict__ g, const float* __restrict__ u, TOut* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = g[i];
+        out[i] = from_f32<TOut>(a / (1.f + __expf(-a)) * u[i]);
+    }
+}
+
+__global__ void add_f32_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += y[i];
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d[i] = from_f32<TD>(to_f32(s[i]));
+}
+
+__global__ void embedding_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
+                                     float* __restrict__ out, int dim) {
+    const int t = blockIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(table + ids[t] * (int64_t)dim);
+    float4* dst = reinterpret_cast<float4*>(out + (int64_t)t * dim);
+    for (int i = threadIdx.x; i < dim / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// argmax per row (first maximal index, like candle's argmax); one CTA per row.
+__global__ void __launch_bounds__(1024)
+argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int n) {
+    const int row = blockIdx.x;
+    const float* xr = x + (int64_t)row * n;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = xr[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    __shared__ float sv[32];
+    __shared__ int si[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) out[row] = bi == 0x7fffffff ? 0 : bi;
+    }
+}
+
+static inline int ew_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int32_t n, float eps,
+              int32_t out_dtype, int64_t stream) {
+    if (rows == 0) return;
+    B200_REQUIRE(x && weight && out && rows > 0 && n > 0, kErrBadArg, "rms_norm: bad arguments");
+    B200_REQUIRE(((uintptr_t)x & 15) == 0 && n % 4 == 0, kErrBadArg, "rms_norm: x must be 16-byte aligned, n %% 4 == 0");
+    if (out_dtype == B200_F32) rms_norm_kernel<float><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (float*)out, n, eps);
+    else if (out_dtype == B200_F16) rms_norm_kernel<__half><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);
+    else if (out_dtype == B200_BF16) rms_norm_kernel<__nv_bfloat16><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__nv_bfloat16*)out, n, eps);
+    else { set_error(kErrUnsupported, "rms_norm: out dtype %d", out_dtype); return; }
+    count_launch();
+    check_launch("rms_norm");
+}
+
+void fused_rope_f32(float* q, float* k, const float* cos_t, const float* sin_t, const int64_t* positions,
+                    int32_t num_tokens, int32_t num_heads, int32_t num_kv_heads, int32_t head_dim,
+                    int32_t interleaved, int64_t stream) {
+    if (num_tokens == 0) return;
+    B200_REQUIRE(q && k && cos_t && sin_t && positions && head_dim % 2 == 0, kErrBadArg, "fused_rope: bad arguments");
+    fused_rope_f32_kernel<<<num_tokens, 256, 0, as_stream(stream)>>>(q, k, cos_t, sin_t, positions, num_heads, num_kv_heads, head_dim, interleaved);
+    count_launch();
+    check_launch("fused_rope");
+}
+
+void rope_and_cache(const float* qkv, void* q_out, void* key_cache, void* value_cache,
+                    const float* cos_t, const float* sin_t, const int64_t* positions,
+                    const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
+                    int32_t num_kv_heads, int32_t head_dim, int32_t block_size, int32_t interleaved,
+                    int32_t dtype, int32_t cache_dtype, int64_t stream) {
+    (void)block_size;
+    if (num_tokens == 0) return;
+    B200_REQUIRE(qkv && q_out && key_cache && value_cache && cos_t && sin_t && positions && slot_mapping, kErrBadArg, "rope_and_cache: null pointer");
+    const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
+    B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "rope_and_cache: cache dtype %d vs dtype %d", cache_dtype, dtype);
+    cudaStream_t st = as_stream(stream);
+#define LAUNCH(T16, F8) rope_and_cache_kernel<T16, F8><<<num_tokens, 256, 0, st>>>(qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved)
+    if (dtype == B200_BF16) { if (fp8) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
+    else if (dtype == B200_F16) { if (fp8) LAUNCH(__half, true); else LAUNCH(__half, false); }
+    else { set_error(kErrUnsupported, "rope_and_cache: dtype %d", dtype); return; }
+#undef LAUNCH
+    count_launch();
+    check_launch("rope_and_cache");
+}
+
+void silu_mul(const float* gate, const float* up, void* out, int64_t numel, int32_t out_dtype, int64_t stream) {
+    if (numel == 0) return;
+    B200_REQUIRE(gate && up && out && numel > 0, kErrBadArg, "silu_mul: bad arguments");
+    if (out_dtype == B200_F32) silu_mul_kernel<float><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(gate, up, (float*)out, numel);
+    else if (out_dtype == B200_F16) silu_mul_kernel<__half><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(gate, up, (__half*)out, numel);
+    else { set_error(kErrUnsupported, "silu_mul: out dtype %d", out_dtype); return; }
+    count_launch();
+    check_launch("silu_mul");
+}
+
+void add_f32(float* x, const float* y, int64_t numel, int64_t stream) {
+    if (numel == 0) return;
+    B200_REQUIRE(x && y && numel > 0, kErrBadArg, "add_f32: bad arguments");
+    add_f32_kernel<<<ew_grid(numel), 256, 0, as_stream(stream)>>>(x, y, numel);
+    count_launch();
+    check_launch("add_f32");
+}
+
+void cast(const void* src, void* dst, int64_t numel, int32_t sd, int32_t dd, int64_t stream) {
+    if (numel == 0) return;
+    B200_REQUIRE(src && dst && numel > 0, kErrBadArg, "cast: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const int g = ew_grid(numel);
+#define C(SD, ST, DD, DT) if (sd == SD && dd == DD) { cast_kernel<ST, DT><<<g, 256, 0, st>>>((const ST*)src, (DT*)dst, numel); count_launch(); check_launch("cast"); return; }
+    C(B200_F32, float, B200_F16, __half) C(B200_F32, float, B200_BF16, __nv_bfloat16) C(B200_F32, float, B200_F32, float)
+    C(B200_F16, __half, B200_F32, float) C(B200_BF16, __nv_bfloat16, B200_F32, float)
+    C(B200_BF16, __nv_bfloat16, B200_F16, __half) C(B200_F16, __half, B200_BF16, __nv_bfloat16)
+#undef C
+    set_error(kErrUnsupported, "cast: %d -> %d unsupported", sd, dd);
+}
+
+void embedding_f32(const float* table, const int64_t* ids, float* out, int32_t num_tokens, int32_t dim, int64_t stream) {
+    if (num_tokens == 0) return;
+    B200_REQUIRE(table && ids && out && dim % 4 == 0, kErrBadArg, "embedding: bad arguments");
+    embedding_f32_kernel<<<num_tokens, 256, 0, as_stream(stream)>>>(table, ids, out, dim);
+    count_launch();
+    check_launch("embedding");
+}
+
+void argmax_f32(const float* logits, int32_t* out, int32_t rows, int32_t n, int64_t stream) {
+    if (rows == 0) return;
+    B200_REQUIRE(logits && out && n > 0, kErrBadArg, "argmax: bad arguments");
+    argmax_f32_kernel<<<rows, 1024, 0, as_stream(stream)>>>(logits, out, n);
+    count_launch();
+    check_launch("argmax");
+}
+
+}  // extern "C"

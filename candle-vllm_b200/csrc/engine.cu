@@ -1,0 +1,353 @@
+// engine.cu -- host-side decode engine: GGUF-LLaMA forward for one decode step over the paged KV
+// cache, captured once per batch size into a CUDA graph and replayed.
+//
+// Mirrors the reference's host code for this path:
+//   GGUFLLaMa::forward_inner   /root/reference/src/openai/models/quantized_llama.rs:424-506
+//   QuantizedAttention::forward /root/reference/src/openai/models/layers/attention.rs:910-1011
+//   Mlp::forward               /root/reference/src/openai/models/quantized_llama.rs:32-44
+//   GraphCapturer::capture/replay /root/reference/src/backend/graph.rs:471-661, :685-803
+//     (static input buffers, metadata copied in, one cuGraphLaunch, stream sync, narrow output)
+//   prepare_decode metadata    /root/reference/src/openai/pipelines/inputs.rs:376-454
+//
+// Dtype flow (same cast points as the reference): f32 residual stream; QMatMul activations are
+// fp16 (include/b200_backend.h); q,k,v -> bf16 before the cache write / attention; attention output
+// rounded to bf16, handed to wo as fp16 (exact: bf16 subset of fp16 range here); logits f32.
+// The residual adds are fused into the wo / w2 GEMM epilogues (accumulate into x).
+#include <cmath>
+#include <map>
+#include <vector>
+
+#include "attention.cuh"
+#include "qmatmul.cuh"
+
+using namespace b200;
+
+extern "C" long long b200_total_kernel_launches(void);
+namespace b200 { void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st); }
+
+struct b200_llama {
+    b200_llama_config cfg;
+    std::vector<b200_llama_layer> layers;
+    const float* tok_embeddings = nullptr;
+    const float* norm = nullptr;
+    const void* output_w = nullptr;
+    int output_type = 0;
+    std::vector<void*> kc, vc;
+    int64_t num_blocks = 0;
+    void* comm = nullptr;
+
+    // local (tensor-parallel shard) sizes
+    int heads_l, kv_l, ffn_l, vocab_l, qkv_row;
+
+    // static device buffers (graph.rs: static input buffers sized for max batch)
+    int64_t* d_tokens = nullptr; int64_t* d_positions = nullptr; int64_t* d_slots = nullptr;
+    uint32_t* d_ctx = nullptr; uint32_t* d_tables = nullptr;
+    float* x = nullptr; __half* xn = nullptr; float* qkv = nullptr; __nv_bfloat16* q16 = nullptr;
+    __half* attn16 = nullptr; float* gate = nullptr; float* up = nullptr; __half* act16 = nullptr;
+    float* partial = nullptr; float* logits = nullptr; int32_t* next_tokens = nullptr;
+    float* cos_t = nullptr; float* sin_t = nullptr;
+    void* attn_ws = nullptr; size_t attn_ws_bytes = 0;
+
+    // pinned staging for the host metadata (one slab)
+    char* h_stage = nullptr; size_t stage_bytes = 0;
+    int32_t* h_next = nullptr;
+
+    std::map<int, cudaGraphExec_t> graphs;       // batch size -> captured step
+    std::map<int, int> launches_per_step;
+    int64_t launches = 0;
+    bool ok = false;
+};
+
+namespace {
+
+template <typename T>
+bool dmalloc(T*& p, size_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, n * sizeof(T) + 256) != cudaSuccess) { set_error(kErrCuda, "engine: cudaMalloc(%zu) failed", n * sizeof(T)); return false; }
+    cudaMemset(q, 0, n * sizeof(T) + 256);
+    p = static_cast<T*>(q);
+    return true;
+}
+
+// next-step metadata on the device (fixed block tables): tokens <- argmax, pos += 1, ctx += 1,
+// slot = table[pos / bs] * bs + pos % bs   (inputs.rs:410-423)
+__global__ void advance_metadata_kernel(int64_t* tokens, const int32_t* next_tokens, int64_t* positions,
+                                        int64_t* slots, uint32_t* ctx, const uint32_t* tables,
+                                        int num_seqs, int max_blocks, int block_size, int feed_tokens) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_seqs) return;
+    if (feed_tokens) tokens[b] = next_tokens[b];
+    const int64_t pos = positions[b] + 1;
+    positions[b] = pos;
+    ctx[b] += 1;
+    slots[b] = (int64_t)tables[(int64_t)b * max_blocks + pos / block_size] * block_size + pos % block_size;
+}
+
+__global__ void zero_f32_kernel(float* p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+// One decode forward on `st` for B sequences.  Returns number of kernel launches issued.
+int forward(b200_llama* m, int B, cudaStream_t st) {
+    const b200_llama_config& c = m->cfg;
+    const int64_t s = reinterpret_cast<int64_t>(st);
+    const int H = c.hidden, hd = c.head_dim;
+    const int qd = m->heads_l * hd, kd = m->kv_l * hd;
+    const long long n0 = b200_total_kernel_launches();
+    embedding_f32(m->tok_embeddings, m->d_tokens, m->x, B, H, s);
+    for (int l = 0; l < c.num_layers; ++l) {
+        const b200_llama_layer& w = m->layers[l];
+        rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16, s);
+        qmatmul_dispatch(m->xn, w.wq, m->qkv, m->qkv_row, B, qd, H, w.tq, 0, st);
+        qmatmul_dispatch(m->xn, w.wk, m->qkv + qd, m->qkv_row, B, kd, H, w.tk, 0, st);
+        qmatmul_dispatch(m->xn, w.wv, m->qkv + qd + kd, m->qkv_row, B, kd, H, w.tv, 0, st);
+        rope_and_cache(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
+                       m->heads_l, m->kv_l, hd, c.block_size, /*interleaved=*/1, B200_BF16, c.kv_dtype, s);
+        paged_attention_decode(m->attn16, m->q16, m->kc[l], m->vc[l], m->d_tables, m->d_ctx, B, m->heads_l, m->kv_l, hd,
+                               c.block_size, c.max_blocks_per_seq, m->num_blocks, 1.0f / sqrtf((float)hd), 0.f, 0,
+                               B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16, m->attn_ws, m->attn_ws_bytes, s);
+        if (c.tp_world == 1) {
+            qmatmul_dispatch(m->attn16, w.wo, m->x, H, B, H, qd, w.to, 1, st);          // x += wo(attn)
+        } else {
+            // row-parallel: partial sums -> all-reduce -> residual add (distributed.rs:696-710)
+            zero_f32_kernel<<<64, 256, 0, st>>>(m->partial, (int64_t)B * H); count_launch();
+            qmatmul_dispatch(m->attn16, w.wo, m->partial, H, B, H, qd, w.to, 1, st);
+            tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);   // tp.cu (NCCL)
+            add_f32(m->x, m->partial, (int64_t)B * H, s);
+        }
+        rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16, s);
+        qmatmul_dispatch(m->xn, w.w1, m->gate, m->ffn_l, B, m->ffn_l, H, w.t1, 0, st);
+        qmatmul_dispatch(m->xn, w.w3, m->up, m->ffn_l, B, m->ffn_l, H, w.t3, 0, st);
+        silu_mul(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, B200_F16, s);
+        if (c.tp_world == 1) {
+            qmatmul_dispatch(m->act16, w.w2, m->x, H, B, H, m->ffn_l, w.t2, 1, st);     // x += w2(act)
+        } else {
+            zero_f32_kernel<<<64, 256, 0, st>>>(m->partial, (int64_t)B * H); count_launch();
+            qmatmul_dispatch(m->act16, w.w2, m->partial, H, B, H, m->ffn_l, w.t2, 1, st);
+            tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);
+            add_f32(m->x, m->partial, (int64_t)B * H, s);
+        }
+    }
+    rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, B200_F16, s);
+    qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
+    argmax_f32(m->logits, m->next_tokens, B, m->vocab_l, s);
+    return (int)(b200_total_kernel_launches() - n0);
+}
+
+bool ready(b200_llama* m) {
+    if (!m || !m->ok) { set_error(kErrBadArg, "engine: model not initialised"); return false; }
+    if (!m->tok_embeddings || !m->norm || !m->output_w) { set_error(kErrBadArg, "engine: globals not set"); return false; }
+    if ((int)m->kc.size() != m->cfg.num_layers) { set_error(kErrBadArg, "engine: kv cache not set"); return false; }
+    for (auto& l : m->layers) if (!l.wq) { set_error(kErrBadArg, "engine: layer weights not set"); return false; }
+    if (m->cfg.tp_world > 1 && !m->comm) { set_error(kErrBadArg, "engine: tp_world > 1 but no communicator"); return false; }
+    return true;
+}
+
+// launch the step: graph replay when enabled (capture on first use), eager otherwise
+void run_step(b200_llama* m, int B, cudaStream_t st) {
+    if (!m->cfg.use_graph || st == nullptr) {
+        m->launches += forward(m, B, st);
+        return;
+    }
+    auto it = m->graphs.find(B);
+    if (it == m->graphs.end()) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            set_error(kErrCuda, "engine: begin capture failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return;
+        }
+        const int n = forward(m, B, st);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (e != cudaSuccess || !g) { set_error(kErrCuda, "engine: end capture failed: %s", cudaGetErrorString(e)); return; }
+        cudaGraphExec_t ex = nullptr;
+        e = cudaGraphInstantiate(&ex, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { set_error(kErrCuda, "engine: graph instantiate failed: %s", cudaGetErrorString(e)); return; }
+        m->graphs[B] = ex;
+        m->launches_per_step[B] = n;
+        it = m->graphs.find(B);
+    }
+    cudaError_t e = cudaGraphLaunch(it->second, st);
+    if (e != cudaSuccess) { set_error(kErrCuda, "engine: graph launch failed: %s", cudaGetErrorString(e)); return; }
+    m->launches += m->launches_per_step[B];
+}
+
+}  // namespace
+
+extern "C" {
+
+b200_llama* b200_llama_create(const b200_llama_config* cfg) {
+    if (!cfg) { set_error(kErrBadArg, "b200_llama_create: null config"); return nullptr; }
+    const b200_llama_config& c = *cfg;
+    if (c.hidden <= 0 || c.num_layers <= 0 || c.num_heads <= 0 || c.num_kv_heads <= 0 || c.head_dim <= 0 || c.ffn <= 0 ||
+        c.vocab <= 0 || c.block_size <= 0 || c.max_num_seqs <= 0 || c.max_blocks_per_seq <= 0 || c.max_pos <= 0 ||
+        c.tp_world <= 0 || c.tp_rank < 0 || c.tp_rank >= c.tp_world) {
+        set_error(kErrBadArg, "b200_llama_create: bad config");
+        return nullptr;
+    }
+    if (c.num_heads % c.tp_world || c.ffn % c.tp_world || c.vocab % c.tp_world) {
+        set_error(kErrBadArg, "b200_llama_create: heads/ffn/vocab not divisible by tp_world=%d", c.tp_world);
+        return nullptr;
+    }
+    if (b200_device_cc() < 100) { set_error(kErrNoDevice, "b200_llama_create: no sm_100 device (cc=%d)", b200_device_cc()); return nullptr; }
+    b200_llama* m = new b200_llama();
+    m->cfg = c;
+    m->layers.resize(c.num_layers);
+    for (auto& l : m->layers) l = b200_llama_layer{};
+    m->heads_l = c.num_heads / c.tp_world;
+    // kv_head_shard (/root/reference/src/openai/distributed.rs:725-765): split, or replicate when kvh < world
+    m->kv_l = c.num_kv_heads >= c.tp_world ? c.num_kv_heads / c.tp_world : 1;
+    m->ffn_l = c.ffn / c.tp_world;
+    m->vocab_l = c.vocab / c.tp_world;
+    m->qkv_row = (m->heads_l + 2 * m->kv_l) * c.head_dim;
+    const size_t B = c.max_num_seqs;
+    bool ok = dmalloc(m->d_tokens, B) && dmalloc(m->d_positions, B) && dmalloc(m->d_slots, B) && dmalloc(m->d_ctx, B) &&
+              dmalloc(m->d_tables, B * c.max_blocks_per_seq) && dmalloc(m->x, B * c.hidden) && dmalloc(m->xn, B * c.hidden) &&
+              dmalloc(m->qkv, B * m->qkv_row) && dmalloc(m->q16, B * m->heads_l * c.head_dim) &&
+              dmalloc(m->attn16, B * m->heads_l * c.head_dim) && dmalloc(m->gate, B * m->ffn_l) && dmalloc(m->up, B * m->ffn_l) &&
+              dmalloc(m->act16, B * m->ffn_l) && dmalloc(m->partial, B * c.hidden) && dmalloc(m->logits, B * m->vocab_l) &&
+              dmalloc(m->next_tokens, B);
+    m->attn_ws_bytes = paged_attention_decode_workspace_bytes((int)B, m->heads_l, c.head_dim, c.max_blocks_per_seq, c.block_size);
+    char* ws = nullptr;
+    ok = ok && dmalloc(ws, m->attn_ws_bytes);
+    m->attn_ws = ws;
+    // RoPE tables: calculate_default_inv_freq (/root/reference/src/openai/models/layers/rotary_emb.rs:14-19,31-36)
+    const int half = c.head_dim / 2;
+    std::vector<float> hc((size_t)c.max_pos * half), hs((size_t)c.max_pos * half);
+    for (int i = 0; i < half; ++i) {
+        const float inv = 1.0f / (float)std::pow((double)c.rope_theta, (double)(2 * i) / (double)c.head_dim);
+        for (int p = 0; p < c.max_pos; ++p) {
+            const float ang = (float)p * inv;
+            hc[(size_t)p * half + i] = cosf(ang);
+            hs[(size_t)p * half + i] = sinf(ang);
+        }
+    }
+    ok = ok && dmalloc(m->cos_t, hc.size()) && dmalloc(m->sin_t, hs.size());
+    if (ok) {
+        cudaMemcpy(m->cos_t, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m->sin_t, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
+    }
+    m->stage_bytes = B * (8 + 8 + 8 + 4) + B * c.max_blocks_per_seq * 4 + 64;
+    ok = ok && cudaMallocHost((void**)&m->h_stage, m->stage_bytes) == cudaSuccess &&
+         cudaMallocHost((void**)&m->h_next, B * 4) == cudaSuccess;
+    if (!ok) {
+        if (!b200_last_error()) set_error(kErrCuda, "b200_llama_create: allocation failed");
+        b200_llama_destroy(m);
+        return nullptr;
+    }
+    m->ok = true;
+    return m;
+}
+
+void b200_llama_destroy(b200_llama* m) {
+    if (!m) return;
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    void* ptrs[] = {m->d_tokens, m->d_positions, m->d_slots, m->d_ctx, m->d_tables, m->x, m->xn, m->qkv, m->q16, m->attn16,
+                    m->gate, m->up, m->act16, m->partial, m->logits, m->next_tokens, m->cos_t, m->sin_t, m->attn_ws};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->h_next) cudaFreeHost(m->h_next);
+    delete m;
+}
+
+void b200_llama_set_layer(b200_llama* m, int32_t layer, const b200_llama_layer* w) {
+    B200_REQUIRE(m && w && layer >= 0 && layer < m->cfg.num_layers, kErrBadArg, "b200_llama_set_layer: bad arguments");
+    B200_REQUIRE(w->attn_norm && w->ffn_norm && w->wq && w->wk && w->wv && w->wo && w->w1 && w->w2 && w->w3, kErrBadArg,
+                 "b200_llama_set_layer: null weight in layer %d", layer);
+    m->layers[layer] = *w;
+}
+
+void b200_llama_set_globals(b200_llama* m, const float* tok_embeddings, const float* norm, const void* output_w, int32_t output_type) {
+    B200_REQUIRE(m && tok_embeddings && norm && output_w, kErrBadArg, "b200_llama_set_globals: null pointer");
+    m->tok_embeddings = tok_embeddings; m->norm = norm; m->output_w = output_w; m->output_type = output_type;
+}
+
+void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const* value_caches, int64_t num_blocks) {
+    B200_REQUIRE(m && key_caches && value_caches && num_blocks > 0, kErrBadArg, "b200_llama_set_kv_cache: bad arguments");
+    m->kc.assign(key_caches, key_caches + m->cfg.num_layers);
+    m->vc.assign(value_caches, value_caches + m->cfg.num_layers);
+    m->num_blocks = num_blocks;
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);    // pointers are baked into captured graphs
+    m->graphs.clear();
+}
+
+void b200_llama_set_comm(b200_llama* m, void* nccl_comm) {
+    B200_REQUIRE(m, kErrBadArg, "b200_llama_set_comm: null model");
+    m->comm = nccl_comm;
+}
+
+void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* positions,
+                       const int64_t* slot_mapping, const uint32_t* context_lens,
+                       const uint32_t* block_tables, int32_t table_width, int32_t num_seqs,
+                       int32_t* next_tokens_host, float* logits_host, int64_t stream) {
+    if (!ready(m)) return;
+    const b200_llama_config& c = m->cfg;
+    B200_REQUIRE(tokens && positions && slot_mapping && context_lens && block_tables, kErrBadArg, "b200_llama_decode: null metadata");
+    B200_REQUIRE(num_seqs > 0 && num_seqs <= c.max_num_seqs, kErrBadArg, "b200_llama_decode: num_seqs %d out of (0, %d]", num_seqs, c.max_num_seqs);
+    B200_REQUIRE(table_width > 0 && table_width <= c.max_blocks_per_seq, kErrBadArg,
+                 "b200_llama_decode: block table width %d out of (0, %d]", table_width, c.max_blocks_per_seq);
+    cudaStream_t st = as_stream(stream);
+    const int B = num_seqs, W = c.max_blocks_per_seq;
+    // stage into pinned memory; block tables are re-padded with zeros to the static width (graph.rs:732-738)
+    char* p = m->h_stage;
+    int64_t* h_tok = (int64_t*)p; p += 8 * B;
+    int64_t* h_pos = (int64_t*)p; p += 8 * B;
+    int64_t* h_slot = (int64_t*)p; p += 8 * B;
+    uint32_t* h_ctx = (uint32_t*)p; p += 4 * B;
+    uint32_t* h_tab = (uint32_t*)p;
+    for (int b = 0; b < B; ++b) {
+        B200_REQUIRE(tokens[b] < (uint32_t)c.vocab, kErrBadArg, "b200_llama_decode: token id %u >= vocab", tokens[b]);
+        B200_REQUIRE(positions[b] >= 0 && positions[b] < c.max_pos, kErrBadArg, "b200_llama_decode: position out of range");
+        h_tok[b] = tokens[b]; h_pos[b] = positions[b]; h_slot[b] = slot_mapping[b]; h_ctx[b] = context_lens[b];
+        for (int j = 0; j < W; ++j) h_tab[(size_t)b * W + j] = j < table_width ? block_tables[(size_t)b * table_width + j] : 0u;
+    }
+    cudaMemcpyAsync(m->d_tokens, h_tok, 8 * B, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(m->d_positions, h_pos, 8 * B, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(m->d_slots, h_slot, 8 * B, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(m->d_ctx, h_ctx, 4 * B, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(m->d_tables, h_tab, (size_t)4 * B * W, cudaMemcpyHostToDevice, st);
+    run_step(m, B, st);
+    if (logits_host) cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->vocab_l * 4, cudaMemcpyDeviceToHost, st);
+    if (next_tokens_host) {
+        cudaMemcpyAsync(m->h_next, m->next_tokens, 4 * B, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);                 // graph.rs:297-301
+        if (e != cudaSuccess) { set_error(kErrCuda, "b200_llama_decode: %s", cudaGetErrorString(e)); return; }
+        for (int b = 0; b < B; ++b) next_tokens_host[b] = m->h_next[b];
+    } else if (logits_host) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error(kErrCuda, "b200_llama_decode: %s", cudaGetErrorString(e)); return; }
+    }
+}
+
+void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance, int64_t stream) {
+    if (!ready(m)) return;
+    B200_REQUIRE(num_seqs > 0 && num_seqs <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_decode_resident: bad num_seqs");
+    cudaStream_t st = as_stream(stream);
+    if (advance) {
+        advance_metadata_kernel<<<ceil_div(num_seqs, 128), 128, 0, st>>>(m->d_tokens, m->next_tokens, m->d_positions, m->d_slots,
+                                                                        m->d_ctx, m->d_tables, num_seqs, m->cfg.max_blocks_per_seq,
+                                                                        m->cfg.block_size, 1);
+        m->launches += 1;
+    }
+    run_step(m, num_seqs, st);
+}
+
+void b200_llama_read_next_tokens(b200_llama* m, int32_t* host, int32_t n, int64_t stream) {
+    B200_REQUIRE(m && host && n > 0 && n <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_read_next_tokens: bad arguments");
+    cudaMemcpyAsync(host, m->next_tokens, (size_t)n * 4, cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+    if (e != cudaSuccess) set_error(kErrCuda, "b200_llama_read_next_tokens: %s", cudaGetErrorString(e));
+}
+
+void b200_llama_read_logits(b200_llama* m, float* host, int32_t n, int64_t stream) {
+    B200_REQUIRE(m && host && n > 0 && n <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_read_logits: bad arguments");
+    cudaMemcpyAsync(host, m->logits, (size_t)n * m->vocab_l * 4, cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+    if (e != cudaSuccess) set_error(kErrCuda, "b200_llama_read_logits: %s", cudaGetErrorString(e));
+}
+
+const float* b200_llama_logits(b200_llama* m) { return m ? m->logits : nullptr; }
+const int32_t* b200_llama_next_tokens(b200_llama* m) { return m ? m->next_tokens : nullptr; }
+int64_t b200_llama_kernel_launches(b200_llama* m) { return m ? m->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// qmatmul_generic.cu -- shape-generic quantised mat-mul and dequantise for GGML Q4_K / Q6_K / Q8_0.
+//
+// y[m,n] = x[m,k] . dequant(W[n,k])^T.  One warp per weight row, lanes over k (8 consecutive
+// weights per lane per 256-wide super-block), 8 activation rows per pass, fp32 accumulate.  This is
+// the catch-all / bring-up path (odd shapes, large m); the tcgen05 kernel in qmatmul_tc.cu is the
+// decode hot path.  Activations are rounded to fp16 first so both paths share one numerical
+// contract (see include/b200_backend.h).
+//
+// Reference call sites: QMatMul::forward /root/reference/src/openai/models/linear.rs:765-806;
+// QTensor::dequantize linear.rs:808-842.
+#include "qmatmul.cuh"
+
+namespace b200 {
+
+template <int kType> struct QType;
+template <> struct QType<B200_GGML_Q4_K> { using Block = block_q4_K; static constexpr int kElems = 256;
+    static __device__ __forceinline__ float w(const Block* b, int i) { return q4k_weight(b, i); } };
+template <> struct QType<B200_GGML_Q6_K> { using Block = block_q6_K; static constexpr int kElems = 256;
+    static __device__ __forceinline__ float w(const Block* b, int i) { return q6k_weight(b, i); } };
+template <> struct QType<B200_GGML_Q8_0> { using Block = block_q8_0; static constexpr int kElems = 32;
+    static __device__ __forceinline__ float w(const Block* b, int i) { return q8_0_weight(b, i); } };
+
+constexpr int kRowsPerCta = 8;   // warps
+constexpr int kMTile = 8;
+
+template <int kType, typename TX>
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+qmatmul_generic_kernel(const TX* __restrict__ x, const void* __restrict__ w_, float* __restrict__ y,
+                       int64_t ldy, int m, int n, int k, int accumulate) {
+    using Q = QType<kType>;
+    using Block = typename Q::Block;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kRowsPerCta + warp;
+    if (row >= n) return;
+    const int m0 = blockIdx.y * kMTile;
+    const int blocks_per_row = k / Q::kElems;
+    const Block* wrow = static_cast<const Block*>(w_) + (int64_t)row * blocks_per_row;
+    float acc[kMTile];
+#pragma unroll
+    for (int i = 0; i < kMTile; ++i) acc[i] = 0.f;
+    for (int k0 = lane * 8; k0 < k; k0 += 256) {
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kk = k0 + j;
+            wv[j] = Q::w(wrow + kk / Q::kElems, kk % Q::kElems);
+        }
+#pragma unroll
+        for (int i = 0; i < kMTile; ++i) {
+            if (m0 + i < m) {
+                const TX* xr = x + (int64_t)(m0 + i) * k + k0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i] += to_f32(from_f32<__half>(to_f32(xr[j]))) * wv[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMTile; ++i) {
+        const float s = warp_sum(acc[i]);
+        if (lane == 0 && m0 + i < m) {
+            float* o = y + (int64_t)(m0 + i) * ldy + row;
+            if (accumulate) atomicAdd(o, s); else *o = s;
+        }
+    }
+}
+
+template <int kType>
+__global__ void dequantize_kernel(const void* __restrict__ w_, float* __restrict__ out, int64_t total) {
+    using Q = QType<kType>;
+    const typename Q::Block* w = static_cast<const typename Q::Block*>(w_);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = Q::w(w + i / Q::kElems, (int)(i % Q::kElems));
+}
+
+template <int kType>
+static void launch(const void* x, bool f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int acc, cudaStream_t st) {
+    dim3 grid(ceil_div(n, kRowsPerCta), ceil_div(m, kMTile));
+    if (f16) qmatmul_generic_kernel<kType, __half><<<grid, kRowsPerCta * 32, 0, st>>>((const __half*)x, w, y, ldy, m, n, k, acc);
+    else qmatmul_generic_kernel<kType, float><<<grid, kRowsPerCta * 32, 0, st>>>((const float*)x, w, y, ldy, m, n, k, acc);
+    count_launch();
+}
+
+void qmatmul_generic(const void* x, bool x_is_f16, const void* w, float* y, int64_t ldy, int m, int n, int k,
+                     int ggml_type, int accumulate, cudaStream_t st) {
+    switch (ggml_type) {
+        case B200_GGML_Q4_K: launch<B200_GGML_Q4_K>(x, x_is_f16, w, y, ldy, m, n, k, accumulate, st); break;
+        case B200_GGML_Q6_K: launch<B200_GGML_Q6_K>(x, x_is_f16, w, y, ldy, m, n, k, accumulate, st); break;
+        case B200_GGML_Q8_0: launch<B200_GGML_Q8_0>(x, x_is_f16, w, y, ldy, m, n, k, accumulate, st); break;
+        default: set_error(kErrUnsupported, "qmatmul: ggml type %d unsupported", ggml_type); return;
+    }
+    check_launch("qmatmul_generic");
+}
+
+void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k,
+                      int ggml_type, int accumulate, cudaStream_t st) {
+    if (qmatmul_tc_supported(m, n, k, ggml_type)) qmatmul_tc(x_f16, w, y, ldy, m, n, k, ggml_type, accumulate, st);
+    else qmatmul_generic(x_f16, true, w, y, ldy, m, n, k, ggml_type, accumulate, st);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static bool qmm_check(const char* who, const void* x, const void* w, const float* y, int m, int n, int k, int t) {
+    if (!x || !w || !y) { set_error(kErrBadArg, "%s: null pointer", who); return false; }
+    if (m <= 0 || n <= 0 || k <= 0) { set_error(kErrBadArg, "%s: bad sizes m=%d n=%d k=%d", who, m, n, k); return false; }
+    const int be = t == B200_GGML_Q8_0 ? 32 : 256;
+    if (t != B200_GGML_Q4_K && t != B200_GGML_Q6_K && t != B200_GGML_Q8_0) { set_error(kErrUnsupported, "%s: ggml type %d unsupported", who, t); return false; }
+    if (k % be) { set_error(kErrBadArg, "%s: k=%d not a multiple of the block size %d", who, k, be); return false; }
+    return true;
+}
+
+extern "C" {
+
+size_t qmatmul_workspace_bytes(int32_t m, int32_t n, int32_t k) {
+    (void)n;
+    return (size_t)(m > 0 ? m : 0) * (size_t)(k > 0 ? k : 0) * 2 + 256;    // fp16 copy of the activations
+}
+
+void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32_t n, int32_t k,
+                    int32_t ggml_type, int32_t accumulate, int64_t stream) {
+    if (m == 0 || n == 0) return;
+    if (!qmm_check("qmatmul_f16act", x_f16, w, y, m, n, k, ggml_type)) return;
+    qmatmul_dispatch(x_f16, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));
+}
+
+void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, int32_t k,
+                 int32_t ggml_type, int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t stream) {
+    if (m == 0 || n == 0) return;
+    if (!qmm_check("qmatmul_f32", x, w, y, m, n, k, ggml_type)) return;
+    if (qmatmul_tc_supported(m, n, k, ggml_type)) {
+        B200_REQUIRE(workspace && workspace_bytes >= qmatmul_workspace_bytes(m, n, k), kErrBadArg,
+                     "qmatmul_f32: workspace too small (%zu < %zu)", workspace_bytes, qmatmul_workspace_bytes(m, n, k));
+        cast(x, workspace, (int64_t)m * k, B200_F32, B200_F16, stream);
+        qmatmul_tc(workspace, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));
+    } else {
+        qmatmul_generic(x, false, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));
+    }
+}
+
+void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggml_type, int64_t stream) {
+    if (n == 0 || k == 0) return;
+    B200_REQUIRE(w && out && n > 0 && k > 0, kErrBadArg, "dequantize: bad arguments");
+    const int64_t total = n * k;
+    int64_t g = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    cudaStream_t st = as_stream(stream);
+    switch (ggml_type) {
+        case B200_GGML_Q4_K: dequantize_kernel<B200_GGML_Q4_K><<<(int)g, 256, 0, st>>>(w, out, total); break;
+        case B200_GGML_Q6_K: dequantize_kernel<B200_GGML_Q6_K><<<(int)g, 256, 0, st>>>(w, out, total); break;
+        case B200_GGML_Q8_0: dequantize_kernel<B200_GGML_Q8_0><<<(int)g, 256, 0, st>>>(w, out, total); break;
+        default: set_error(kErrUnsupported, "dequantize: ggml type %d unsupported", ggml_type); return;
+    }
+    count_launch();
+    check_launch("dequantize");
+}
+
+}  // extern "C"

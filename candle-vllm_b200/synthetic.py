@@ -1,0 +1,114 @@
+"""Synthetic GGUF-LLaMA weights and KV state: no model files, no network.
+
+Weights are random but VALID GGML blocks generated on the device with a seeded torch generator:
+Q4_K: 12 scale bytes + 128 nibble bytes uniform, d ~ U(0.5,2)*2^-14, dmin ~ 7.5*U(0.5,2)*2^-14
+(zero-mean weights of std ~0.02, so activations stay O(1) through 32 layers); Q6_K: 208 bytes
+uniform, d ~ U(0.5,2)*2^-16.  Norm weights ~ U(0.5,1.5), embeddings N(0,1).
+Tensor-parallel shards follow the reference: column split dim 0, row split dim 1 by raw blocks
+(/root/reference/src/openai/models/layers/quantized_var_builder.rs:234-269).
+"""
+from __future__ import annotations
+
+import torch
+
+from .backend import GgmlType, QTensor
+from .llama import LlamaConfig
+
+
+def _f16_bytes(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.float16).view(torch.uint8).reshape(*x.shape, 2)
+
+
+def random_q4k(gen, n: int, k: int, device) -> torch.Tensor:
+    nb = n * (k // 256)
+    blocks = torch.randint(0, 256, (nb, 144), dtype=torch.uint8, device=device, generator=gen)
+    d = (torch.rand(nb, device=device, generator=gen) * 1.5 + 0.5) * 2.0 ** -14
+    dmin = (torch.rand(nb, device=device, generator=gen) * 1.5 + 0.5) * 7.5 * 2.0 ** -14
+    blocks[:, 0:2] = _f16_bytes(d)
+    blocks[:, 2:4] = _f16_bytes(dmin)
+    return blocks.reshape(-1)
+
+
+def random_q6k(gen, n: int, k: int, device) -> torch.Tensor:
+    nb = n * (k // 256)
+    blocks = torch.randint(0, 256, (nb, 210), dtype=torch.uint8, device=device, generator=gen)
+    d = (torch.rand(nb, device=device, generator=gen) * 1.5 + 0.5) * 2.0 ** -16
+    blocks[:, 208:210] = _f16_bytes(d)
+    return blocks.reshape(-1)
+
+
+def random_qtensor(gen, ggml_type: int, n: int, k: int, device) -> QTensor:
+    fn = {GgmlType.Q4_K: random_q4k, GgmlType.Q6_K: random_q6k}[ggml_type]
+    return QTensor(fn(gen, n, k, device), ggml_type, (n, k))
+
+
+def shard_rows(w: QTensor, rank: int, world: int) -> QTensor:
+    """column-parallel: split dim 0 (distributed.rs:767-811)."""
+    n, k = w.shape
+    be, bb = GgmlType.BLOCK[w.ggml_type]
+    rows = w.data.reshape(n, (k // be) * bb)
+    nl = n // world
+    return QTensor(rows[rank * nl:(rank + 1) * nl].contiguous().reshape(-1), w.ggml_type, (nl, k))
+
+
+def shard_cols(w: QTensor, rank: int, world: int) -> QTensor:
+    """row-parallel: split dim 1 along whole blocks (raw-byte shard, quantized_var_builder.rs:234-269)."""
+    n, k = w.shape
+    be, bb = GgmlType.BLOCK[w.ggml_type]
+    nbk = k // be
+    if nbk % world:
+        raise ValueError(f"k={k}: {nbk} blocks per row not divisible by world {world}")
+    blocks = w.data.reshape(n, nbk, bb)
+    bl = nbk // world
+    return QTensor(blocks[:, rank * bl:(rank + 1) * bl].contiguous().reshape(-1), w.ggml_type, (n, k // world))
+
+
+def make_weights(cfg: LlamaConfig, device="cuda", seed: int = 0, tp_rank: int = 0, tp_world: int = 1,
+                 linear_type: int = GgmlType.Q4_K, output_type: int = GgmlType.Q6_K) -> dict:
+    """Full (unsharded) tensors are drawn from the seeded stream on every rank, then sharded, so all
+    ranks agree on the global model (embedding + norms replicated)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    H, hd = cfg.hidden, cfg.head_dim
+    qd, kd = cfg.num_heads * hd, cfg.num_kv_heads * hd
+    col = (lambda w: shard_rows(w, tp_rank, tp_world)) if tp_world > 1 else (lambda w: w)
+    row = (lambda w: shard_cols(w, tp_rank, tp_world)) if tp_world > 1 else (lambda w: w)
+    if tp_world > 1 and cfg.num_kv_heads < tp_world:
+        raise ValueError("kv-head replication (kvh < world) not wired in the synthetic generator")
+    w = dict(tok_embeddings=torch.randn((cfg.vocab, H), device=device, generator=gen, dtype=torch.float32),
+             norm=torch.rand(H, device=device, generator=gen) + 0.5, layers=[])
+    for _ in range(cfg.num_layers):
+        w["layers"].append(dict(
+            attn_norm=torch.rand(H, device=device, generator=gen) + 0.5,
+            ffn_norm=torch.rand(H, device=device, generator=gen) + 0.5,
+            wq=col(random_qtensor(gen, linear_type, qd, H, device)),
+            wk=col(random_qtensor(gen, linear_type, kd, H, device)),
+            wv=col(random_qtensor(gen, linear_type, kd, H, device)),
+            wo=row(random_qtensor(gen, linear_type, H, qd, device)),
+            w1=col(random_qtensor(gen, linear_type, cfg.ffn, H, device)),
+            w2=row(random_qtensor(gen, linear_type, H, cfg.ffn, device)),
+            w3=col(random_qtensor(gen, linear_type, cfg.ffn, H, device)),
+        ))
+    w["output"] = col(random_qtensor(gen, output_type, cfg.vocab, H, device))
+    return w
+
+
+def fill_kv_cache(kv_cache, seed: int = 1) -> None:
+    """KV contents N(0,1) in the cache dtype (bf16, or e4m3 bits for u8 caches)."""
+    gen = torch.Generator(device=kv_cache[0][0].device)
+    gen.manual_seed(seed)
+    for k, v in kv_cache:
+        for t in (k, v):
+            if t.dtype == torch.uint8:
+                r = torch.randn(t.shape, device=t.device, generator=gen, dtype=torch.float32)
+                t.copy_(r.to(torch.float8_e4m3fn).view(torch.uint8))
+            else:
+                t.normal_(0.0, 1.0, generator=gen)
+
+
+def random_block_tables(num_seqs: int, blocks_per_seq: int, num_blocks: int, seed: int = 2):
+    """Random permutation of physical blocks (non-contiguous pages), seeded; list of lists."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(num_blocks)[: num_seqs * blocks_per_seq]
+    return perm.reshape(num_seqs, blocks_per_seq).tolist()

@@ -1,0 +1,217 @@
+/*
+ * b200_backend.h -- C ABI of libb200backend.so: the B200-native (sm_100a) batched-decode backend
+ * that drops in behind candle-vllm's `src/backend` / attention-rs FFI surface.
+ *
+ * Conventions (identical to the reference's `attention_rs::kernels::ffi`):
+ *   - extern "C", plain pointers and sizes, `int64_t stream` = the caller's CUstream
+ *     (`*dev.cu_stream() as i64`, /root/reference/src/backend/cache.rs:135, gptq.rs:130);
+ *   - every entry point is stream-ordered, allocation-free, host-sync-free and therefore
+ *     CUDA-graph capture safe (/root/reference/src/backend/graph.rs:271-274); scratch memory is
+ *     a caller-provided `workspace` whose size comes from the matching `*_workspace_bytes`;
+ *   - functions return void like the reference's; argument errors (the reference validates on the
+ *     Rust side and `bail!`s, cache.rs:26-39, gptq.rs:232-238) are recorded per thread and read
+ *     with b200_last_error(); device errors stay sticky CUDA errors, as in the reference;
+ *   - outputs are caller-allocated, possibly uninitialised (gptq.rs:66), inputs may be views.
+ *
+ * There is no CPU fallback: on a machine without an sm_100 GPU every launch fails loudly
+ * (b200_last_error() != 0 / CUDA error), it never computes on the host.
+ */
+#ifndef B200_BACKEND_H_
+#define B200_BACKEND_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library / error state ------------------------------------------------------------- */
+int         b200_abi_version(void);
+/* 0 = ok.  Last argument/launch error recorded on THIS thread; reading clears it. */
+int         b200_last_error(void);
+const char* b200_last_error_message(void);
+/* SM count / compute capability of the current device (0 if no usable device). */
+int         b200_device_sm_count(void);
+int         b200_device_cc(void);
+
+/* data-type tags used by the entry points below */
+enum { B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2, B200_U8 = 3, B200_FP8_E4M3 = 4 };
+/* GGML tensor types (values = ggml_type, as stored in GGUF files) */
+enum { B200_GGML_Q8_0 = 8, B200_GGML_Q4_K = 12, B200_GGML_Q6_K = 14 };
+/* KV layouts (/root/reference/src/scheduler/cache_engine.rs:298-341) */
+enum { B200_KV_FLASH = 0 /* K,V [nb, bs, kvh, hd] */,
+       B200_KV_PAGED = 1 /* K [nb, kvh, hd/x, bs, x], V [nb, kvh, hd, bs], x = 16/elem */ };
+
+/* ---- K4: copy_blocks -- replaces attention_rs::kernels::ffi::copy_blocks_{bf16,f16,f32} ----
+ * Call site: /root/reference/src/backend/cache.rs:127-162.  The first three arguments are HOST
+ * pointers (Vec::as_mut_ptr, cache.rs:112-114): u64 device addresses of each layer's K / V cache,
+ * and i64 (src,dst) block pairs.  For every layer, K and V: dst block <- src block,
+ * numel_per_block elements each.  copy_blocks_u8 adds the arm the reference lacks for FP8 KV
+ * (cache.rs:95-97 bails). */
+void copy_blocks_bf16(void* key_cache_ptrs, void* value_cache_ptrs, const void* block_mapping,
+                      int32_t num_layers, int32_t num_pairs, int32_t numel_per_block, int64_t stream);
+void copy_blocks_f16 (void* key_cache_ptrs, void* value_cache_ptrs, const void* block_mapping,
+                      int32_t num_layers, int32_t num_pairs, int32_t numel_per_block, int64_t stream);
+void copy_blocks_f32 (void* key_cache_ptrs, void* value_cache_ptrs, const void* block_mapping,
+                      int32_t num_layers, int32_t num_pairs, int32_t numel_per_block, int64_t stream);
+void copy_blocks_u8  (void* key_cache_ptrs, void* value_cache_ptrs, const void* block_mapping,
+                      int32_t num_layers, int32_t num_pairs, int32_t numel_per_block, int64_t stream);
+
+/* ---- K5: swap_blocks -- replaces attention_rs::cache::swap_blocks(src, dst, &HashMap) -------
+ * Call site: /root/reference/src/scheduler/cache_engine.rs:527-535 (swap_in :345-363, swap_out
+ * :365-385).  dst[dst_block] <- src[src_block], bytes_per_block each.  `mapping` is a HOST array
+ * of i64 (src,dst) pairs.  One of src/dst may be host memory (pinned or pageable); the copy kind
+ * is inferred (cudaMemcpyDefault).  Adjacent pairs are coalesced into single copies. */
+void swap_blocks(const void* src, void* dst, const int64_t* mapping, int32_t num_pairs,
+                 int64_t bytes_per_block, int64_t stream);
+
+/* ---- K3: reshape_and_cache -- the cache write inside PagedAttention::forward ----------------
+ * Call sites: /root/reference/src/openai/models/layers/attention.rs:707-718, :983-994; slot math
+ * /root/reference/src/openai/pipelines/inputs.rs:180-194, :410-423.
+ * key/value: [num_tokens, num_kv_heads, head_dim] of `in_dtype` (B200_F32/F16/BF16), row strides
+ * in elements.  slot_mapping i64[num_tokens]: flat slot = block*block_size + offset; negative
+ * (pad, -1) = skip.  cache_dtype: same 16-bit type as the model dtype, or B200_FP8_E4M3 (stored as
+ * U8, saturating RNE cast, scale 1.0 -- the reference passes no scale).  layout: B200_KV_*. */
+void reshape_and_cache(const void* key, const void* value, void* key_cache, void* value_cache,
+                       const int64_t* slot_mapping, int32_t num_tokens, int32_t num_kv_heads,
+                       int32_t head_dim, int32_t block_size, int64_t key_stride, int64_t value_stride,
+                       int32_t in_dtype, int32_t cache_dtype, int32_t layout, int64_t stream);
+
+/* ---- K1: paged attention, decode -- PagedAttention::forward with is_prefill = false ---------
+ * Call sites as above; metadata contract /root/reference/src/openai/pipelines/inputs.rs:552-568.
+ * q, out: [num_seqs, num_heads, head_dim] of `dtype` (B200_BF16 / B200_F16), contiguous.
+ * block_tables u32 [num_seqs, max_blocks_per_seq] (0-padded), context_lens u32 [num_seqs]
+ * INCLUDING the token being decoded.  The kernel reads only device-side context_lens (never a
+ * host max_context_len), so a graph captured with padded tables replays correctly (graph.rs:604).
+ * softcap <= 0: none.  sliding_window <= 0: none.  out_dtype: `dtype`, or B200_F16 to hand the
+ * result straight to a quantised GEMM (values are rounded to `dtype` first).
+ * workspace: >= paged_attention_decode_workspace_bytes(...) bytes of device memory. */
+size_t paged_attention_decode_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_dim,
+                                              int32_t max_blocks_per_seq, int32_t block_size);
+void paged_attention_decode(void* out, const void* q, const void* key_cache, const void* value_cache,
+                            const uint32_t* block_tables, const uint32_t* context_lens,
+                            int32_t num_seqs, int32_t num_heads, int32_t num_kv_heads, int32_t head_dim,
+                            int32_t block_size, int32_t max_blocks_per_seq, int64_t num_blocks,
+                            float scale, float softcap, int32_t sliding_window,
+                            int32_t dtype, int32_t cache_dtype, int32_t layout, int32_t out_dtype,
+                            void* workspace, size_t workspace_bytes, int64_t stream);
+
+/* ---- K2: paged attention, (chunked) prefill -- is_prefill = true ----------------------------
+ * Metadata /root/reference/src/openai/pipelines/inputs.rs:133-148, :351-367.  Varlen causal
+ * attention; ALL keys/values (cached prefix + this chunk) are read from the paged cache, which the
+ * caller has already written with reshape_and_cache.  Sequence i owns q rows
+ * cu_seqlens_q[i]..cu_seqlens_q[i+1] = the last q_len positions of its k_len context. */
+void paged_attention_prefill(void* out, const void* q, const void* key_cache, const void* value_cache,
+                             const uint32_t* block_tables, const uint32_t* cu_seqlens_q,
+                             const uint32_t* cu_seqlens_k, int32_t num_seqs, int32_t total_q,
+                             int32_t max_seqlen_q, int32_t num_heads, int32_t num_kv_heads,
+                             int32_t head_dim, int32_t block_size, int32_t max_blocks_per_seq,
+                             float scale, float softcap, int32_t sliding_window,
+                             int32_t dtype, int32_t cache_dtype, int32_t layout, int64_t stream);
+
+/* ---- K6: QMatMul::forward on GGUF tensors -- replaces candle QMatMul (quantized.cu) ---------
+ * Call sites: /root/reference/src/openai/models/linear.rs:765-806,
+ * /root/reference/src/openai/models/quantized_llama.rs:33-37, layers/attention.rs:920-922,1004.
+ * y[m,n] (f32) = x[m,k] (f32) . dequant(W[n,k])^T.  W = GGML blocks, row-major over n, verbatim
+ * GGUF bytes (k % 256 == 0 for K-quants, % 32 for Q8_0).  Activations are rounded to fp16
+ * (saturating) and products accumulate in fp32 on the tensor cores; the reference quantises
+ * activations to 8 bit (Q8_1 / Q8_K), which is coarser.
+ * accumulate != 0: y += result (used for the residual add; implies fp32 atomics). */
+size_t qmatmul_workspace_bytes(int32_t m, int32_t n, int32_t k);
+void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, int32_t k,
+                 int32_t ggml_type, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                 int64_t stream);
+/* same with activations already in fp16 [m,k] (what the fused decode layer feeds) */
+void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32_t n, int32_t k,
+                    int32_t ggml_type, int32_t accumulate, int64_t stream);
+/* QTensor::dequantize: W -> f32 [n,k] (linear.rs:808-842 forward_via_dequant) */
+void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggml_type, int64_t stream);
+
+/* ---- K15 / K21: the elementwise ops between the big ones ------------------------------------
+ * rms_norm: candle_nn::ops::rms_norm (layers/qrmsnorm.rs:28-31).  out_dtype F32 or F16. */
+void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int32_t n, float eps,
+              int32_t out_dtype, int64_t stream);
+/* FusedRope::apply_inplace (layers/rotary_emb.rs:52-69): q [T,h,hd], k [T,kvh,hd] f32 in place,
+ * cos/sin f32 [max_pos, hd/2], positions i64[T]; interleaved != 0 => rope_i (GGUF llama). */
+void fused_rope_f32(float* q, float* k, const float* cos_t, const float* sin_t, const int64_t* positions,
+                    int32_t num_tokens, int32_t num_heads, int32_t num_kv_heads, int32_t head_dim,
+                    int32_t interleaved, int64_t stream);
+/* silu(gate)*up (quantized_llama.rs:32-37); out_dtype F32 or F16 */
+void silu_mul(const float* gate, const float* up, void* out, int64_t numel, int32_t out_dtype, int64_t stream);
+void add_f32(float* x, const float* y, int64_t numel, int64_t stream);                 /* x += y */
+void cast(const void* src, void* dst, int64_t numel, int32_t src_dtype, int32_t dst_dtype, int64_t stream);
+void embedding_f32(const float* table, const int64_t* ids, float* out, int32_t num_tokens, int32_t dim, int64_t stream);
+void argmax_f32(const float* logits, int32_t* out, int32_t rows, int32_t n, int64_t stream);
+
+/* ---- fused decode layer pieces used by the engine (also exported for tests) ------------------
+ * rope (interleaved or NeoX) on q,k + cast q -> dtype + reshape_and_cache of k,v, from the packed
+ * f32 [T, (h + 2*kvh)*hd] output of the fused QKV projection. */
+void rope_and_cache(const float* qkv, void* q_out, void* key_cache, void* value_cache,
+                    const float* cos_t, const float* sin_t, const int64_t* positions,
+                    const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
+                    int32_t num_kv_heads, int32_t head_dim, int32_t block_size, int32_t interleaved,
+                    int32_t dtype, int32_t cache_dtype, int64_t stream);
+
+/* ---- decode engine: GGUFLLaMa::forward_inner for one decode step ------------------------------
+ * Mirrors /root/reference/src/openai/models/quantized_llama.rs:424-506 (+ attention.rs:910-1011,
+ * Mlp::forward :32-44) with the reference's CUDA-graph replay protocol (backend/graph.rs:685-803):
+ * static device buffers, metadata copied in, one graph launch per step. */
+typedef struct {
+    int32_t hidden, num_layers, num_heads, num_kv_heads, head_dim, ffn, vocab;
+    int32_t block_size, max_num_seqs, max_blocks_per_seq, max_pos;
+    float   rms_eps, rope_theta;
+    int32_t kv_dtype;          /* B200_BF16 or B200_FP8_E4M3 */
+    int32_t tp_rank, tp_world; /* tensor-parallel shard (heads, kv heads, ffn, vocab split) */
+    int32_t use_graph;
+} b200_llama_config;
+
+typedef struct {
+    const float* attn_norm; const float* ffn_norm;          /* f32 [hidden] */
+    const void *wq, *wk, *wv, *wo, *w1, *w2, *w3;           /* GGML blocks (device) */
+    int32_t tq, tk, tv, to, t1, t2, t3;                     /* ggml types */
+} b200_llama_layer;
+
+typedef struct b200_llama b200_llama;
+
+b200_llama* b200_llama_create(const b200_llama_config* cfg);
+void        b200_llama_destroy(b200_llama* m);
+/* all pointers are device pointers owned by the caller and must outlive the model */
+void b200_llama_set_layer(b200_llama* m, int32_t layer, const b200_llama_layer* w);
+void b200_llama_set_globals(b200_llama* m, const float* tok_embeddings /*f32 [vocab,hidden]*/,
+                            const float* norm, const void* output_w, int32_t output_type);
+/* KV caches: flash layout, one K and one V device pointer per layer (cache_engine.rs:122-294) */
+void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const* value_caches,
+                             int64_t num_blocks);
+/* tensor-parallel all-reduce hook: an NCCL communicator (ncclComm_t) created by the host */
+void b200_llama_set_comm(b200_llama* m, void* nccl_comm);
+/* One decode step from HOST metadata (what prepare_decode builds, inputs.rs:376-454):
+ * tokens u32[B], positions i64[B], slot_mapping i64[B], context_lens u32[B],
+ * block_tables u32[B, table_width].  Copies them into the static device buffers (async, pinned
+ * staging), replays the graph, and (if next_tokens_host != NULL) returns greedy argmax token ids
+ * after synchronising the stream, like GraphCapturer::replay (graph.rs:297-301).
+ * logits_host (optional): f32 [B, vocab] copied back. */
+void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* positions,
+                       const int64_t* slot_mapping, const uint32_t* context_lens,
+                       const uint32_t* block_tables, int32_t table_width, int32_t num_seqs,
+                       int32_t* next_tokens_host, float* logits_host, int64_t stream);
+/* Device-resident variant: metadata already in the static buffers; advance positions/slots on the
+ * device (fixed block tables) and replay.  Used for the HBM-resident `value` measurement. */
+void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance, int64_t stream);
+const float* b200_llama_logits(b200_llama* m);        /* device f32 [max_num_seqs, vocab_local] */
+const int32_t* b200_llama_next_tokens(b200_llama* m); /* device i32 [max_num_seqs] */
+int64_t b200_llama_kernel_launches(b200_llama* m);    /* kernels launched by this model so far */
+/* copy the last step's greedy tokens (i32[n]) / logits (f32 [n, vocab_local]) to the host; syncs the stream */
+void b200_llama_read_next_tokens(b200_llama* m, int32_t* host, int32_t n, int64_t stream);
+void b200_llama_read_logits(b200_llama* m, float* host, int32_t n, int64_t stream);
+
+/* library-wide count of kernels launched by this library (evidence for bench.py's gpu_launches) */
+long long b200_total_kernel_launches(void);
+/* NCCL all-reduce(sum) in place on f32, on the caller's communicator (tensor-parallel residual path,
+ * /root/reference/src/openai/distributed.rs:547-654) */
+void b200_allreduce_f32(void* nccl_comm, float* buf, int64_t n, int64_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_BACKEND_H_ */

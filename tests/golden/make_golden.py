@@ -1,0 +1,58 @@
+"""Generates the committed golden vectors under tests/golden/ (run in the authoring container).
+
+  ggml_dequant.npz : random GGML blocks (Q4_K, Q6_K, Q8_0) + their dequantisation by the `gguf`
+                     Python package (gguf.quants.dequantize -- llama.cpp's own independent numpy
+                     implementation of the GGUF block formats, v0.19) + Q8_0 quantisation of a
+                     random vector by gguf.quants.quantize.  Pins oracle/ggml_quants.py.
+  slot_mapping.json: known answers for the slot / block-table arithmetic restated from
+                     /root/reference/src/openai/pipelines/inputs.rs:12-22, :410-430 (hand-computed
+                     from the formulae; the reference holds no test vectors for them).
+The reference itself (Rust, kernels in un-vendored deps) cannot be executed here, so no vectors
+come from running it.
+"""
+import json
+import os
+
+import numpy as np
+from gguf import GGMLQuantizationType as T
+from gguf import quants
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    rng = np.random.default_rng(20260922)
+    out = {}
+    for name, t, bb in (("q4k", T.Q4_K, 144), ("q6k", T.Q6_K, 210), ("q8_0", T.Q8_0, 34)):
+        nb = 24
+        blocks = rng.integers(0, 256, (nb, bb), dtype=np.uint8)
+        # keep the f16 scale fields finite and moderate
+        if name == "q4k":
+            blocks[:, 0:2] = (rng.uniform(0.5, 2, nb) * 2.0 ** -10).astype(np.float16).view(np.uint8).reshape(nb, 2)
+            blocks[:, 2:4] = (rng.uniform(0.5, 2, nb) * 2.0 ** -8).astype(np.float16).view(np.uint8).reshape(nb, 2)
+        elif name == "q6k":
+            blocks[:, 208:210] = (rng.uniform(0.5, 2, nb) * 2.0 ** -12).astype(np.float16).view(np.uint8).reshape(nb, 2)
+        else:
+            blocks[:, 0:2] = (rng.uniform(0.5, 2, nb) * 2.0 ** -6).astype(np.float16).view(np.uint8).reshape(nb, 2)
+        out[f"{name}_blocks"] = blocks
+        out[f"{name}_deq"] = quants.dequantize(blocks, t).astype(np.float32)
+    x = rng.standard_normal((4, 64)).astype(np.float32)
+    out["q8_0_x"] = x
+    out["q8_0_quant"] = quants.quantize(x, T.Q8_0)
+    np.savez_compressed(os.path.join(HERE, "ggml_dequant.npz"), **out)
+
+    cases = [
+        # (seq_len incl. decoded token, block_size, table) -> position, slot, used blocks
+        dict(seq_len=1, block_size=64, table=[7], position=0, slot=448, used=1),
+        dict(seq_len=64, block_size=64, table=[7], position=63, slot=511, used=1),
+        dict(seq_len=65, block_size=64, table=[7, 3], position=64, slot=192, used=2),
+        dict(seq_len=4097, block_size=64, table=list(range(100, 165)), position=4096, slot=164 * 64, used=65),
+        dict(seq_len=130, block_size=16, table=[5, 9, 2, 11, 4, 8, 1, 0, 3], position=129, slot=3 * 16 + 1, used=9),
+        dict(seq_len=17, block_size=16, table=[5, 9, 2], position=16, slot=9 * 16, used=2),
+    ]
+    with open(os.path.join(HERE, "slot_mapping.json"), "w") as f:
+        json.dump(cases, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
