@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: decode tokens/s, Llama-3-8B Q4_K (GGUF), batch 32, ctx 4096 -> 5120,
+paged KV (bf16), on N B200s (tensor parallel = N), synthetic weights / KV / block tables.
+
+One "step" = one decode step of the whole batch through the hot path (32 decoder layers of
+quantised GEMMs + paged attention + lm_head + greedy argmax).  Prints ONE JSON line (see the
+driver contract):  value = tokens/s with all inputs resident in HBM (CUDA-graph replay, metadata
+advanced on the device); e2e = the same through the public host API (prepare_decode on the host,
+H2D metadata copies, D2H token read-back inside the timed region); roofline = the paged-attention
+decode kernel (HBM-bound) measured live with CUDA events; cpu_baseline = the C port of the
+reference's CPU/GGML arithmetic (oracle/cpu_ref.c) on a bounded sample.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU; TP = N)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "decode tokens/s Llama-3-8B Q4_K batch=32"
+UNIT = "tokens/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--ctx", type=int, default=4096, help="context length at the first decode step")
+    ap.add_argument("--max-ctx", type=int, default=5120)
+    ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers => number is INVALID")
+    ap.add_argument("--kv", default="bf16", choices=["bf16", "fp8"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: C port of the reference's CPU/GGML path (oracle/cpu_ref.c) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_setup(batch: int, ctx: int):
+    """Times ONE decoder layer (Q4_K x Q8_K integer-dot GEMMs + f32 paged attention over a bf16
+    cache) for `batch` sequences at context `ctx`, plus a row slice of the Q6_K lm_head, and scales to
+    the full model: t_step = 32 * t_layer + t_head * (vocab / rows).  Returns (tokens/s, info)."""
+    import ctypes as C
+    from oracle import cpu_ref
+    from oracle import attention as OA
+    lib = cpu_ref.lib()
+    rng = np.random.default_rng(0)
+    H, heads, kvh, hd, F, V, bs = 4096, 32, 8, 128, 14336, 128256, 64
+    nblk = -(-(ctx + 1) // bs)
+
+    def q4k(n, k):
+        b = rng.integers(0, 256, (n * (k // 256), 144), dtype=np.uint8)
+        b[:, 0:2] = (rng.uniform(0.5, 2, len(b)) * 2.0 ** -14).astype(np.float16).view(np.uint8).reshape(-1, 2)
+        b[:, 2:4] = (rng.uniform(0.5, 2, len(b)) * 7.5 * 2.0 ** -14).astype(np.float16).view(np.uint8).reshape(-1, 2)
+        return b.reshape(-1)
+
+    ws = dict(wq=q4k(heads * hd, H), wk=q4k(kvh * hd, H), wv=q4k(kvh * hd, H), wo=q4k(H, heads * hd),
+              w1=q4k(F, H), w2=q4k(H, F), w3=q4k(F, H))
+    norms = dict(attn_norm=rng.uniform(0.5, 1.5, H).astype(np.float32), ffn_norm=rng.uniform(0.5, 1.5, H).astype(np.float32))
+    nb = batch * nblk
+    kc = rng.integers(0, 2 ** 16, (nb, bs, kvh, hd), dtype=np.uint16) & 0xBFFF     # finite bf16 bit patterns
+    vc = rng.integers(0, 2 ** 16, (nb, bs, kvh, hd), dtype=np.uint16) & 0xBFFF
+    kc = (kc & 0x807F) | 0x3F00; vc = (vc & 0x807F) | 0x3F00                         # |x| in [0.5, 1)
+    bt = rng.permutation(nb).reshape(batch, nblk).astype(np.uint32)
+    ctx_lens = np.full(batch, ctx + 1, np.uint32)
+    pos = np.full(batch, ctx, np.int64)
+    slots = (bt[:, ctx // bs].astype(np.int64) * bs + ctx % bs)
+    cos, sin = OA.rope_tables(hd, ctx + 8, 500000.0)
+    cfg = cpu_ref.RefCfg(H, heads, kvh, hd, F, bs, nblk, 1e-5)
+    layer = cpu_ref.RefLayer(*[a.ctypes.data for a in (norms["attn_norm"], norms["ffn_norm"], ws["wq"], ws["wk"], ws["wv"],
+                                                       ws["wo"], ws["w1"], ws["w2"], ws["w3"])])
+    x = rng.standard_normal((batch, H)).astype(np.float32)
+    lib.ref_layer_scratch_floats.restype = C.c_size_t
+    scratch = np.empty(lib.ref_layer_scratch_floats(C.byref(cfg), batch), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def one_layer():
+        t0 = time.perf_counter()
+        rc = lib.ref_llama_layer_decode(C.byref(cfg), C.byref(layer), p(x), batch, p(pos), p(slots), p(bt), p(ctx_lens),
+                                        p(kc), p(vc), p(cos), p(sin), p(scratch))
+        assert rc == 0
+        return time.perf_counter() - t0
+
+    rows = 8192
+    w6 = rng.integers(0, 256, (rows * (H // 256), 210), dtype=np.uint8)
+    w6[:, 208:210] = (rng.uniform(0.5, 2, len(w6)) * 2.0 ** -16).astype(np.float16).view(np.uint8).reshape(-1, 2)
+    w6 = w6.reshape(-1)
+    xh = rng.standard_normal((batch, H)).astype(np.float32)
+
+    keep = (ws, norms, kc, vc, bt, ctx_lens, pos, slots, cos, sin, x, scratch, layer, cfg)   # raw pointers inside
+
+    def step():
+        """one bounded sample -> seconds for a FULL decode step (scaled)"""
+        assert keep
+        t_layer = one_layer()
+        t0 = time.perf_counter()
+        cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)
+        t_head = time.perf_counter() - t0
+        return 32 * t_layer + t_head * (V / rows), t_layer, t_head
+
+    info = dict(cores=cpu_ref.num_threads(), kind="port",
+                sample=f"per step: 1 of 32 decoder layers (batch {batch}, ctx {ctx}, Q4_K x Q8_K int dot + f32 paged "
+                       f"attention) + {rows}/{V} Q6_K lm_head rows, scaled to the full model")
+    return step, info
+
+
+def cpu_decode_sample(batch: int, ctx: int, budget_s: float):
+    step, info = cpu_sample_setup(batch, ctx)
+    best = None
+    t_start = time.perf_counter()
+    n = 0
+    while n < 3 and (n == 0 or (time.perf_counter() - t_start) * (n + 1) / n < budget_s):
+        t_step, t_layer, t_head = step()
+        best = t_step if best is None else min(best, t_step)
+        n += 1
+    info = dict(info)
+    info["sample"] += f"; best of {n}: {best:.2f} s/step"
+    return batch / best, best, info
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (C port; the Rust reference cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, info = cpu_sample_setup(args.batch, args.ctx)
+    vals, t_begin = [], time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        t_step, _, _ = step()
+        if i >= args.warmup or (time.perf_counter() - t_begin) > 60:
+            vals.append((args.batch / t_step, t_step))
+        if vals and (time.perf_counter() - t_begin) > 150:       # keep the whole run within a few minutes
+            break
+    tps = statistics.mean(v[0] for v in vals)
+    ms = statistics.mean(v[1] for v in vals) * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "q4_k weights x q8_k activations (int8 dot), f32 attention", "data": "synthetic",
+            "config": {"workload": f"Llama-3-8B Q4_K decode, batch {args.batch}, ctx {args.ctx}, block_size 64, bf16 paged KV",
+                       "note": "CPU arm runs on host cores only; each step is a bounded sample scaled to the full model"},
+            "cpu_baseline": {"value": tps, "unit": UNIT, **info},
+            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import candle_vllm_b200 as pkg
+    from candle_vllm_b200 import synthetic
+    from candle_vllm_b200.distributed import Comm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    comm = Comm(rank, world) if world > 1 else None
+
+    B, bs = args.batch, 64
+    K, W = args.steps, args.warmup
+    args.max_ctx = max(args.max_ctx, args.ctx + 2 * (K + W) + 8)      # room for resident + e2e steps
+    blocks_per_seq = -(-args.max_ctx // bs)
+    cfg = pkg.LlamaConfig(num_layers=args.layers, max_num_seqs=B, max_blocks_per_seq=blocks_per_seq, max_pos=args.max_ctx + 64,
+                          block_size=bs)
+    kv_dtype = pkg.DType.FP8_E4M3 if args.kv == "fp8" else pkg.DType.BF16
+    weights = synthetic.make_weights(cfg, dev, seed=0, tp_rank=rank, tp_world=world)
+    num_blocks = B * blocks_per_seq + 16
+    eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim,
+                          pkg.CacheConfig(bs, num_blocks, kvcache_dtype="fp8" if args.kv == "fp8" else "auto"),
+                          device=dev, num_shards=world)
+    synthetic.fill_kv_cache(eng.gpu_cache, seed=1 + rank)
+    tables = synthetic.random_block_tables(B, blocks_per_seq, num_blocks, seed=2)
+    model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, tp_rank=rank, tp_world=world,
+                          nccl_comm=comm.handle.value if comm else None)
+    stream = model.stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident: metadata advanced on the device, graph replay only ----------------
+    lens = [args.ctx + 1] * B          # context INCLUDING the token being decoded
+    toks = [int(t) for t in np.random.default_rng(3).integers(0, cfg.vocab, B)]
+    prep = pkg.prepare_decode(lens, toks, tables, bs)
+    model.decode(prep)                                     # loads the static buffers, captures the graph
+    for _ in range(W):
+        model.decode_resident(B, advance=True)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = model.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(K):
+            model.decode_resident(B, advance=True)
+        e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = model.kernel_launches() - l0
+    ms_step = ms_total / K
+    value = B / (ms_step * 1e-3)
+    ctx_first, ctx_last = args.ctx + 1 + W + 1, args.ctx + 1 + W + K
+
+    # ---- (2) end to end through the host API -------------------------------------------------------
+    cur = ctx_last + 1
+    nxt = model.read_next_tokens(B)
+    h2d = B * (8 + 8 + 8 + 4) + B * blocks_per_seq * 4
+    d2h = B * 4
+    for _ in range(min(W, 3)):
+        prep = pkg.prepare_decode([cur] * B, [int(t) for t in nxt], tables, bs)
+        nxt, _ = model.decode(prep); cur += 1
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(K):
+        prep = pkg.prepare_decode([cur] * B, [int(t) for t in nxt], tables, bs)     # host: block tables, slots
+        nxt, _ = model.decode(prep); cur += 1                                       # H2D + replay + D2H + sync
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / K
+    e2e = B / (e2e_ms * 1e-3)
+
+    # ---- (3) roofline of the dominant kernel: paged-attention decode, timed alone per layer ---------
+    roof = attention_roofline(pkg, model, cfg, eng, B, cur, tables, world, stream, dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roof.update(peak=hbm_peak, peak_source="MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s",
+                frac=roof["achieved"] / hbm_peak)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 activations x q4_k/q6_k weights (fp32 accumulate), bf16 attention", "data": "synthetic",
+            "config": {"workload": f"Llama-3-8B Q4_K (lm_head Q6_K) decode, batch {B}, ctx {ctx_first}->{ctx_last} of 4096->5120, "
+                                   f"block_size {bs}, {args.kv} paged KV, random non-contiguous block tables",
+                       "parallelism": f"tp{world}", "global_batch": B, "layers": cfg.num_layers,
+                       "l2_policy": "inputs larger than L2 (KV 17+ GB and weights 4.4 GB streamed per step; 126 MB L2)"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "prepare_decode (host) + GGUFLLaMa.decode -> b200_llama_decode (C ABI, host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+    if cfg.num_layers != 32:
+        line["invalid"] = "debug run with fewer layers"
+    if not args.no_cpu_baseline:
+        tps, t_step, info = cpu_decode_sample(B, args.ctx, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": tps, "unit": UNIT, **info}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev):
+    """Times PagedAttention decode alone (all layers round-robin, so every launch streams a different
+    layer's KV: 0.5+ GB per launch >> 126 MB L2) with CUDA events on the launching stream."""
+    import torch
+    heads_l = cfg.num_heads // world
+    kv_l = max(cfg.num_kv_heads // world, 1)
+    attn = pkg.PagedAttention(heads_l, cfg.head_dim, cfg.head_dim ** -0.5, kv_l, fp8_kvcache=eng.dtype == torch.uint8)
+    prep = pkg.prepare_decode([ctx] * B, [0] * B, tables, cfg.block_size)
+    bt = np.zeros((B, cfg.max_blocks_per_seq), np.int32); bt[:, :prep["block_tables"].shape[1]] = prep["block_tables"]
+    with torch.cuda.stream(stream):
+        meta = pkg.InputMetadata(False, torch.zeros(0, dtype=torch.int64, device=dev), torch.from_numpy(bt).to(dev),
+                                 torch.from_numpy(prep["context_lens"]).to(dev))
+        q = torch.randn((B, heads_l, cfg.head_dim), device=dev, dtype=torch.float32).to(torch.bfloat16)
+        for l in range(min(3, cfg.num_layers)):
+            attn.forward(q, None, None, None, eng.gpu_cache[l][0], eng.gpu_cache[l][1], meta, out_dtype=torch.float16)
+        reps = max(cfg.num_layers, 32)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream.synchronize()
+        e0.record(stream)
+        for i in range(reps):
+            k, v = eng.gpu_cache[i % cfg.num_layers]
+            attn.forward(q, None, None, None, k, v, meta, out_dtype=torch.float16)
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    esz = eng.gpu_cache[0][0].element_size()
+    kv_bytes = B * ctx * 2 * kv_l * cfg.head_dim * esz
+    io_bytes = 2 * B * heads_l * cfg.head_dim * 2
+    alg = kv_bytes + io_bytes
+    return {"kernel": "paged_attention_decode (one layer: split-KV kernel + merge)", "bound": "hbm",
+            "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
+            "ms_per_launch": ms, "ctx": ctx, "traffic": None}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,7 +1,479 @@
-// attention_decode.cu -- placeholder until the TMA-staged split-KV kernel lands (next commit).
+// attention_decode.cu -- paged-attention decode for B200: TMA-staged KV pages, split-KV persistent
+// CTAs, tensor-core QK^T / PV with warp-level online softmax, plus the split merge.
+//
+// Why this shape (DESIGN.md "paged attention decode"): the op is HBM-bound -- per layer it streams
+// B * ctx * 2 * kvh * 128 * 2 B of KV (537-671 MB at B=32, ctx 4-5k) against ~4 flop/B of math.
+// So the kernel is organised around keeping >= 190 KB of KV reads in flight per SM:
+//   * KV cache = 4-D tensor [num_blocks, 64, kvh, 128] (flash layout,
+//     /root/reference/src/scheduler/cache_engine.rs:326-340); one TMA box {64 dims, 1 head, 64 tokens,
+//     1 block} lands a page-half (8 KB) in shared memory with the 128-byte swizzle, 4 boxes per page
+//     (K lo/hi, V lo/hi), completion on an mbarrier (cp.async.bulk.tensor -> UTMALDG).
+//   * work item = (sequence, kv head, chunk of <= 8 pages); items are enumerated from the DEVICE-side
+//     context_lens (graph-replay safe, graph.rs:604) with the kv head fastest so concurrently running
+//     CTAs touch the same DRAM pages; a persistent grid of one CTA per SM walks them round-robin.
+//   * 1 producer warp (block-table gather + TMA issue) feeds a 6-stage ring; 4 consumer warps take
+//     pages round-robin: S = Q K^T with mma.sync m16n8k16 (the GQA group's <= 8 query heads are the
+//     M rows, K read with ldmatrix from the swizzled tile), online softmax in registers (exp2, fp32),
+//     O += P V with ldmatrix.trans on V.  Tensor cores are needed only to keep the issue slots free:
+//     the arithmetic (16 flop/B padded) is two orders below the tensor peak.
+//   * per item the 4 warps' (m, l, O) are combined through shared memory and written as an fp32
+//     partial; a tiny merge kernel folds the chunks of each (sequence, head) and rounds to bf16.
+//
+// Semantics: softmax(q k^T * scale) v over the block table, GQA by head grouping
+// (NaiveAttention::forward /root/reference/src/openai/models/mod.rs:1268-1307; call sites
+// layers/attention.rs:707-718, :983-994; metadata pipelines/inputs.rs:552-568).
+#include <cuda.h>
+
+#include <type_traits>
+
 #include "attention.cuh"
+
 namespace b200 {
-bool paged_attention_decode_tma_supported(const DecodeArgs&, float, int, int, int) { return false; }
-size_t paged_attention_decode_tma_workspace(int, int, int, int, int) { return 256; }
-void paged_attention_decode_tma(const DecodeArgs&, cudaStream_t) {}
+
+namespace {
+
+constexpr int kHeadDim = 128;
+constexpr int kPage = 64;                     // tokens per KV block (main.rs:364-366 default)
+constexpr int kStages = 6;
+constexpr int kConsumerWarps = 4;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kMaxChunkPages = 8;
+constexpr int kHalfTileBytes = kPage * 64 * 2;            // 64 tokens x 64 dims x 2 B = 8 KB
+constexpr int kStageBytes = 4 * kHalfTileBytes;           // K lo, K hi, V lo, V hi = 32 KB
+constexpr int kORow = 136;                                // padded fp32 row (bank-conflict-free float2 stores)
+constexpr int kMaxSeqs = 1024;
+
+struct SmemLayout {
+    // stages first (1024-byte aligned for the 128B swizzle)
+    static constexpr int kStagesOff = 0;
+    static constexpr int kScratchO = kStages * kStageBytes;                         // [4][8][kORow] f32
+    static constexpr int kScratchML = kScratchO + kConsumerWarps * 8 * kORow * 4;   // [4][8][2] f32
+    static constexpr int kBars = kScratchML + kConsumerWarps * 8 * 2 * 4;           // full[kStages], empty[kStages]
+    static constexpr int kPrefix = kBars + 2 * kStages * 8;                         // int[kMaxSeqs + 1]
+    static constexpr int kTotal = kPrefix + (kMaxSeqs + 1) * 4;
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    } else {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+struct DecodeParams {
+    const void* q;                    // [B, H, 128] T
+    const uint32_t* block_tables;     // [B, max_blocks]
+    const uint32_t* context_lens;     // [B]
+    float* part_o;                    // [B*kvh*max_chunks][group][128]
+    float* part_ml;                   // [B*kvh*max_chunks][group][2]  (m in log2 domain, l)
+    int num_seqs, num_heads, num_kv_heads, max_blocks, chunk_pages, max_chunks;
+    float scale_log2;                 // scale * log2(e)
+};
+
+// =================================================================================================
+template <typename T, int kGroup>
+__global__ void __launch_bounds__(kThreads, 1)
+paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
+                         const DecodeParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base + SmemLayout::kBars;
+    int* prefix = reinterpret_cast<int*>(smem + SmemLayout::kPrefix);
+    auto full_bar = [&](int s) { return bars + s * 8; };
+    auto empty_bar = [&](int s) { return bars + (kStages + s) * 8; };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // chunk prefix over sequences from the device-side context lengths
+    const int chunk_tokens = p.chunk_pages * kPage;
+    for (int b = threadIdx.x; b < p.num_seqs; b += kThreads) {
+        const int ctx = (int)p.context_lens[b];
+        prefix[b + 1] = (ctx + chunk_tokens - 1) / chunk_tokens;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        prefix[0] = 0;
+        for (int b = 0; b < p.num_seqs; ++b) prefix[b + 1] += prefix[b];
+    }
+    __syncthreads();
+    const int total_items = prefix[p.num_seqs] * p.num_kv_heads;
+
+    // item -> (seq, kv head, chunk, pages in chunk, valid tokens of the last page)
+    auto decode_item = [&](int item, int& b, int& h, int& c, int& npages, int& ctx) {
+        const int pair = item / p.num_kv_heads;
+        h = item - pair * p.num_kv_heads;
+        int lo = 0, hi = p.num_seqs;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= pair) lo = mid; else hi = mid; }
+        b = lo;
+        c = pair - prefix[b];
+        ctx = (int)p.context_lens[b];
+        const int pages_total = (ctx + kPage - 1) / kPage;
+        npages = min(p.chunk_pages, pages_total - c * p.chunk_pages);
+    };
+
+    if (warp == kConsumerWarps) {
+        // ===================================== PRODUCER ==========================================
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        int n = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            int b, h, c, npages, ctx;
+            decode_item(item, b, h, c, npages, ctx);
+            const uint32_t my_block = lane < npages ? p.block_tables[(int64_t)b * p.max_blocks + c * p.chunk_pages + lane] : 0u;
+            for (int j = 0; j < npages; ++j, ++n) {
+                const int blk = (int)__shfl_sync(0xffffffffu, my_block, j);
+                if (lane == 0) {
+                    const int s = n % kStages;
+                    mbar_wait(empty_bar(s), ((n / kStages) & 1) ^ 1);
+                    mbar_expect_tx(full_bar(s), kStageBytes);
+                    const uint32_t dst = smem_base + s * kStageBytes;
+                    tma_load_4d(dst, &kmap, full_bar(s), 0, h, 0, blk, policy);
+                    tma_load_4d(dst + kHalfTileBytes, &kmap, full_bar(s), 64, h, 0, blk, policy);
+                    tma_load_4d(dst + 2 * kHalfTileBytes, &vmap, full_bar(s), 0, h, 0, blk, policy);
+                    tma_load_4d(dst + 3 * kHalfTileBytes, &vmap, full_bar(s), 64, h, 0, blk, policy);
+                }
+            }
+        }
+        return;
+    }
+
+    // ========================================= CONSUMERS ==========================================
+    const int g = lane >> 2, t = lane & 3;
+    float* scr_o = reinterpret_cast<float*>(smem + SmemLayout::kScratchO);
+    float* scr_ml = reinterpret_cast<float*>(smem + SmemLayout::kScratchML);
+    const T* qbase = static_cast<const T*>(p.q);
+    int n_base = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int b, h, c, npages, ctx;
+        decode_item(item, b, h, c, npages, ctx);
+
+        // Q fragments: rows = the group's query heads (g < kGroup), zero padding otherwise
+        uint32_t qa[8][2];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            if (g < kGroup) {
+                const T* qr = qbase + ((int64_t)b * p.num_heads + h * kGroup + g) * kHeadDim + ks * 16 + 2 * t;
+                qa[ks][0] = *reinterpret_cast<const uint32_t*>(qr);
+                qa[ks][1] = *reinterpret_cast<const uint32_t*>(qr + 8);
+            } else { qa[ks][0] = qa[ks][1] = 0u; }
+        }
+        float o[16][4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;         // log2-domain running max, this thread's partial row sum
+
+        for (int j = warp; j < npages; j += kConsumerWarps) {
+            const int n = n_base + j;
+            const int s = n % kStages;
+            mbar_wait(full_bar(s), (n / kStages) & 1);
+            const uint32_t kt = smem_base + s * kStageBytes, vt = kt + 2 * kHalfTileBytes;
+            const int valid = min(kPage, ctx - (c * p.chunk_pages + j) * kPage);
+
+            // ---- S = Q K^T : 8 n-tiles (8 tokens each) x 8 k-steps --------------------------------
+            float sacc[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int row = nt * 8 + (lane & 7);
+#pragma unroll
+                for (int kp = 0; kp < 4; ++kp) {            // 32 dims (2 k-steps) per ldmatrix.x4
+                    const int chunk = kp * 4 + (lane >> 3);  // 16-byte chunk index 0..15 along the 128 dims
+                    const uint32_t addr = kt + (chunk >> 3) * kHalfTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+                    uint32_t kb[4];
+                    ldmatrix_x4(kb, addr);
+                    const uint32_t a0[4] = {qa[2 * kp][0], 0u, qa[2 * kp][1], 0u};
+                    const uint32_t a1[4] = {qa[2 * kp + 1][0], 0u, qa[2 * kp + 1][1], 0u};
+                    mma_16816<T>(sacc[nt], a0, kb[0], kb[1]);
+                    mma_16816<T>(sacc[nt], a1, kb[2], kb[3]);
+                }
+            }
+            // ---- mask + online softmax (rows g; rows g+8 are padding) -----------------------------
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int tok = nt * 8 + 2 * t;
+                sacc[nt][0] = tok < valid ? sacc[nt][0] * p.scale_log2 : -INFINITY;
+                sacc[nt][1] = tok + 1 < valid ? sacc[nt][1] * p.scale_log2 : -INFINITY;
+                mx = fmaxf(mx, fmaxf(sacc[nt][0], sacc[nt][1]));
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run, mx);            // finite: every page holds >= 1 valid token
+            const float corr = fast_exp2(m_run - m_new);
+            m_run = m_new;
+            l_run *= corr;
+            uint32_t pa[8];                                  // P as packed 16-bit pairs, per n-tile
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float p0 = fast_exp2(sacc[nt][0] - m_new), p1 = fast_exp2(sacc[nt][1] - m_new);
+                l_run += p0 + p1;
+                pa[nt] = pack2<T>(p0, p1);
+            }
+            if (corr != 1.f) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
+            }
+            // V rows past the context may hold non-finite garbage: 0 * NaN would poison O
+            if (valid < kPage) {
+                for (int r = valid + (lane >> 4); r < kPage; r += 2) {
+                    const int ch = lane & 15;
+                    *reinterpret_cast<int4*>(smem + (vt - smem_base) + (ch >> 3) * kHalfTileBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+                        make_int4(0, 0, 0, 0);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes vs the next TMA refill
+                __syncwarp();
+            }
+            // ---- O += P V : 4 k-steps (16 tokens) x 16 n-tiles (8 dims) ---------------------------
+#pragma unroll
+            for (int ktk = 0; ktk < 4; ++ktk) {
+                const uint32_t a[4] = {pa[2 * ktk], 0u, pa[2 * ktk + 1], 0u};
+                const int row = ktk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                for (int np = 0; np < 8; ++np) {            // two 8-dim n-tiles per ldmatrix.x4.trans
+                    const int chunk = np * 2 + (lane >> 4);
+                    const uint32_t addr = vt + (chunk >> 3) * kHalfTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+                    uint32_t vb[4];
+                    ldmatrix_x4_trans(vb, addr);
+                    mma_16816<T>(o[2 * np], a, vb[0], vb[1]);
+                    mma_16816<T>(o[2 * np + 1], a, vb[2], vb[3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar(s));
+        }
+        n_base += npages;
+
+        // ---- combine the 4 warps of this item, write the fp32 partial ------------------------------
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+        if (g < kGroup) {
+            float* orow = scr_o + (warp * 8 + g) * kORow;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(orow + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
+            if (t == 0) { scr_ml[(warp * 8 + g) * 2] = m_run; scr_ml[(warp * 8 + g) * 2 + 1] = l_run; }
+        }
+        named_bar_sync(1, kConsumerWarps * 32);
+        {
+            const int d = threadIdx.x;                      // 0..127 = output dim
+            const int64_t slot = ((int64_t)b * p.num_kv_heads + h) * p.max_chunks + c;
+#pragma unroll
+            for (int r = 0; r < kGroup; ++r) {
+                float M = -INFINITY;
+#pragma unroll
+                for (int w = 0; w < kConsumerWarps; ++w) M = fmaxf(M, scr_ml[(w * 8 + r) * 2]);
+                float acc = 0.f, L = 0.f;
+#pragma unroll
+                for (int w = 0; w < kConsumerWarps; ++w) {
+                    const float mw = scr_ml[(w * 8 + r) * 2];
+                    const float wgt = mw == -INFINITY ? 0.f : exp2f(mw - M);
+                    acc += wgt * scr_o[(w * 8 + r) * kORow + d];
+                    L += wgt * scr_ml[(w * 8 + r) * 2 + 1];
+                }
+                p.part_o[(slot * kGroup + r) * kHeadDim + d] = acc;
+                if (d == 0) { p.part_ml[(slot * kGroup + r) * 2] = M; p.part_ml[(slot * kGroup + r) * 2 + 1] = L; }
+            }
+        }
+        named_bar_sync(1, kConsumerWarps * 32);
+    }
+}
+
+// merge the chunk partials of one (sequence, head); one CTA of 128 threads (= dims) each
+template <typename T, typename TOut>
+__global__ void __launch_bounds__(kHeadDim)
+paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                        const uint32_t* __restrict__ context_lens, int num_heads, int num_kv_heads, int group,
+                        int chunk_tokens, int max_chunks) {
+    const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    const int h = head / group, r = head - h * group;
+    const int ctx = (int)context_lens[b];
+    const int nchunks = (ctx + chunk_tokens - 1) / chunk_tokens;
+    const int64_t base = ((int64_t)b * num_kv_heads + h) * max_chunks;
+    float M = -INFINITY;
+    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, part_ml[((base + c) * group + r) * 2]);
+    float acc = 0.f, L = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+        const float w = exp2f(part_ml[((base + c) * group + r) * 2] - M);
+        acc += w * part_o[((base + c) * group + r) * kHeadDim + d];
+        L += w * part_ml[((base + c) * group + r) * 2 + 1];
+    }
+    const float res = nchunks > 0 && L > 0.f ? acc / L : 0.f;
+    out[((int64_t)b * num_heads + head) * kHeadDim + d] = from_f32<TOut>(to_f32(from_f32<T>(res)));
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool make_kv_map(CUtensorMap* map, const void* cache, int64_t num_blocks, int kvh, int dtype) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error(kErrCuda, "paged_attention_decode: cuTensorMapEncodeTiled unavailable"); return false; }
+    const cuuint64_t dims[4] = {(cuuint64_t)kHeadDim, (cuuint64_t)kvh, (cuuint64_t)kPage, (cuuint64_t)num_blocks};
+    const cuuint64_t strides[3] = {(cuuint64_t)kHeadDim * 2, (cuuint64_t)kvh * kHeadDim * 2, (cuuint64_t)kPage * kvh * kHeadDim * 2};
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)kPage, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                           const_cast<void*>(cache), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error(kErrCuda, "paged_attention_decode: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+    return true;
+}
+
+int pick_chunk_pages(int num_seqs, int kvh, int max_blocks) {
+    int chunk = kMaxChunkPages;
+    const int64_t want = 4ll * sm_count();
+    while (chunk > 1 && (int64_t)num_seqs * kvh * ((max_blocks + chunk - 1) / chunk) < want) chunk >>= 1;
+    return chunk;
+}
+
+template <typename T, typename TOut, int kGroup>
+void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, cudaStream_t st) {
+    auto kern = paged_attn_decode_kernel<T, kGroup>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal);
+        attr_set = true;
+    }
+    const int64_t max_items = (int64_t)a.num_seqs * a.num_kv_heads * p.max_chunks;
+    const int grid = (int)(max_items < sm_count() ? max_items : sm_count());
+    kern<<<grid, kThreads, SmemLayout::kTotal, st>>>(kmap, vmap, p);
+    count_launch();
+    paged_attn_merge_kernel<T, TOut><<<dim3(a.num_heads, a.num_seqs), kHeadDim, 0, st>>>(
+        static_cast<TOut*>(a.out), p.part_o, p.part_ml, a.context_lens, a.num_heads, a.num_kv_heads, kGroup,
+        p.chunk_pages * kPage, p.max_chunks);
+    count_launch();
+}
+
+template <typename T, typename TOut>
+void launch_group(const DecodeArgs& a, const CUtensorMap& km, const CUtensorMap& vm, const DecodeParams& p, int group, cudaStream_t st) {
+    switch (group) {
+        case 1: launch<T, TOut, 1>(a, km, vm, p, st); break;
+        case 2: launch<T, TOut, 2>(a, km, vm, p, st); break;
+        case 4: launch<T, TOut, 4>(a, km, vm, p, st); break;
+        case 8: launch<T, TOut, 8>(a, km, vm, p, st); break;
+    }
+}
+
+}  // namespace
+
+bool paged_attention_decode_tma_supported(const DecodeArgs& a, float softcap, int window, int cache_dtype, int layout) {
+    const int group = a.num_heads / a.num_kv_heads;
+    return layout == B200_KV_FLASH && a.head_dim == kHeadDim && a.block_size == kPage && cache_dtype == a.dtype &&
+           (a.dtype == B200_BF16 || a.dtype == B200_F16) && softcap <= 0.f && window <= 0 &&
+           (group == 1 || group == 2 || group == 4 || group == 8) && a.num_seqs <= kMaxSeqs && a.num_blocks > 0 &&
+           ((uintptr_t)a.kc & 15) == 0 && ((uintptr_t)a.vc & 15) == 0 && ((uintptr_t)a.q & 3) == 0;
+}
+
+size_t paged_attention_decode_tma_workspace(int num_seqs, int num_heads, int head_dim, int max_blocks, int block_size) {
+    (void)block_size;
+    // worst case: 1-page chunks -> max_blocks partials per (sequence, head)
+    return (size_t)num_seqs * num_heads * (size_t)max_blocks * ((size_t)head_dim * 4 + 8) + 256;
+}
+
+void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
+    const int group = a.num_heads / a.num_kv_heads;
+    DecodeParams p;
+    p.q = a.q; p.block_tables = a.block_tables; p.context_lens = a.context_lens;
+    p.num_seqs = a.num_seqs; p.num_heads = a.num_heads; p.num_kv_heads = a.num_kv_heads; p.max_blocks = a.max_blocks;
+    p.chunk_pages = pick_chunk_pages(a.num_seqs, a.num_kv_heads, a.max_blocks);
+    p.max_chunks = (a.max_blocks + p.chunk_pages - 1) / p.chunk_pages;
+    p.scale_log2 = a.scale * 1.4426950408889634f;
+    const size_t n_part = (size_t)a.num_seqs * a.num_kv_heads * p.max_chunks * group;
+    const size_t need = n_part * (kHeadDim * 4 + 8) + 16;
+    if (!a.workspace || a.workspace_bytes < need) {
+        set_error(kErrBadArg, "paged_attention_decode: workspace too small (%zu < %zu bytes)", a.workspace_bytes, need);
+        return;
+    }
+    p.part_o = static_cast<float*>(a.workspace);
+    p.part_ml = p.part_o + n_part * kHeadDim;
+    CUtensorMap km, vm;
+    if (!make_kv_map(&km, a.kc, a.num_blocks, a.num_kv_heads, a.dtype) || !make_kv_map(&vm, a.vc, a.num_blocks, a.num_kv_heads, a.dtype)) return;
+    if (a.dtype == B200_BF16) {
+        if (a.out_dtype == B200_F16) launch_group<__nv_bfloat16, __half>(a, km, vm, p, group, st);
+        else launch_group<__nv_bfloat16, __nv_bfloat16>(a, km, vm, p, group, st);
+    } else {
+        launch_group<__half, __half>(a, km, vm, p, group, st);
+    }
+    check_launch("paged_attention_decode");
+}
+
 }  // namespace b200
