@@ -5,19 +5,23 @@
 // B * ctx * 2 * kvh * 128 * 2 B of KV (537-671 MB at B=32, ctx 4-5k) against ~4 flop/B of math.
 // So the kernel is organised around keeping >= 190 KB of KV reads in flight per SM:
 //   * KV cache = 4-D tensor [num_blocks, 64, kvh, 128] (flash layout,
-//     /root/reference/src/scheduler/cache_engine.rs:326-340); one TMA box {64 dims, 1 head, 64 tokens,
-//     1 block} lands a page-half (8 KB) in shared memory with the 128-byte swizzle, 4 boxes per page
+//     /root/reference/src/scheduler/cache_engine.rs:326-340); one TMA box {64 dims, 1 head, 32 tokens,
+//     1 block} lands a quarter page (4 KB) in shared memory with the 128-byte swizzle, 4 boxes per tile
 //     (K lo/hi, V lo/hi), completion on an mbarrier (cp.async.bulk.tensor -> UTMALDG).
 //   * work item = (sequence, kv head, chunk of <= 8 pages); items are enumerated from the DEVICE-side
 //     context_lens (graph-replay safe, graph.rs:604) with the kv head fastest so concurrently running
-//     CTAs touch the same DRAM pages; a persistent grid of one CTA per SM walks them round-robin.
-//   * 1 producer warp (block-table gather + TMA issue) feeds a 6-stage ring; 4 consumer warps take
-//     pages round-robin: S = Q K^T with mma.sync m16n8k16 (the GQA group's <= 8 query heads are the
-//     M rows, K read with ldmatrix from the swizzled tile), online softmax in registers (exp2, fp32),
-//     O += P V with ldmatrix.trans on V.  Tensor cores are needed only to keep the issue slots free:
-//     the arithmetic (16 flop/B padded) is two orders below the tensor peak.
-//   * per item the 4 warps' (m, l, O) are combined through shared memory and written as an fp32
-//     partial; a tiny merge kernel folds the chunks of each (sequence, head) and rounds to bf16.
+//     warps touch the same DRAM pages; a persistent grid of one CTA per SM pulls items from a global
+//     atomic queue (no tail imbalance).
+//   * every warp (6 per CTA) is an independent pipeline: it gathers the chunk's block ids from the block
+//     table, issues its own TMA loads two 32-token tiles ahead into a private 2-stage ring (16 KB per
+//     stage, 192 KB in flight per SM) and consumes them: S = Q K^T with mma.sync m16n8k16 (the GQA
+//     group's <= 8 query heads are the M rows, K read with ldmatrix from the swizzled tile), online
+//     softmax in registers (exp2, fp32), O += P V with ldmatrix.trans on V.  Tensor cores are needed
+//     only to keep the issue slots free: the arithmetic (16 flop/B padded) is far below the tensor peak.
+//     A warp only waits on mbarrier phases it armed itself, so there is no cross-warp phase aliasing
+//     and no CTA barrier in the steady state.
+//   * per item the warp writes an fp32 partial (m, l, O) straight from registers; a tiny merge kernel
+//     folds the chunks of each (sequence, head), rounds to bf16 and re-zeroes the queue head.
 //
 // Semantics: softmax(q k^T * scale) v over the block table, GQA by head grouping
 // (NaiveAttention::forward /root/reference/src/openai/models/mod.rs:1268-1307; call sites
@@ -34,22 +38,20 @@ namespace {
 
 constexpr int kHeadDim = 128;
 constexpr int kPage = 64;                     // tokens per KV block (main.rs:364-366 default)
-constexpr int kStages = 6;
-constexpr int kConsumerWarps = 4;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kTile = 32;                     // tokens per pipeline stage (half a page)
+constexpr int kWarps = 6;                     // independent warp pipelines per CTA
+constexpr int kStagesPerWarp = 2;
+constexpr int kThreads = kWarps * 32;
 constexpr int kMaxChunkPages = 8;
-constexpr int kHalfTileBytes = kPage * 64 * 2;            // 64 tokens x 64 dims x 2 B = 8 KB
-constexpr int kStageBytes = 4 * kHalfTileBytes;           // K lo, K hi, V lo, V hi = 32 KB
-constexpr int kORow = 136;                                // padded fp32 row (bank-conflict-free float2 stores)
+constexpr int kSubTileBytes = kTile * 64 * 2;             // 32 tokens x 64 dims x 2 B = 4 KB
+constexpr int kStageBytes = 4 * kSubTileBytes;            // K lo, K hi, V lo, V hi = 16 KB
 constexpr int kMaxSeqs = 1024;
 
 struct SmemLayout {
-    // stages first (1024-byte aligned for the 128B swizzle)
-    static constexpr int kStagesOff = 0;
-    static constexpr int kScratchO = kStages * kStageBytes;                         // [4][8][kORow] f32
-    static constexpr int kScratchML = kScratchO + kConsumerWarps * 8 * kORow * 4;   // [4][8][2] f32
-    static constexpr int kBars = kScratchML + kConsumerWarps * 8 * 2 * 4;           // full[kStages], empty[kStages]
-    static constexpr int kPrefix = kBars + 2 * kStages * 8;                         // int[kMaxSeqs + 1]
+    // stages first (1024-byte aligned for the 128B swizzle): [warp][stage][K lo | K hi | V lo | V hi]
+    static constexpr int kBars = kWarps * kStagesPerWarp * kStageBytes;             // full[kWarps][kStagesPerWarp]
+    static constexpr int kHdr = kBars + kWarps * kStagesPerWarp * 8;                // int[kWarps][4][8] item headers
+    static constexpr int kPrefix = kHdr + kWarps * 4 * 8 * 4;                       // int[kMaxSeqs + 1]
     static constexpr int kTotal = kPrefix + (kMaxSeqs + 1) * 4;
 };
 
@@ -129,11 +131,18 @@ struct DecodeParams {
     const uint32_t* context_lens;     // [B]
     float* part_o;                    // [B*kvh*max_chunks][group][128]
     float* part_ml;                   // [B*kvh*max_chunks][group][2]  (m in log2 domain, l)
+    unsigned int* counter;            // dynamic work queue head (zero on entry; the merge kernel re-zeroes it)
     int num_seqs, num_heads, num_kv_heads, max_blocks, chunk_pages, max_chunks;
     float scale_log2;                 // scale * log2(e)
 };
 
-// =================================================================================================
+// One work item = (sequence b, kv head h, chunk c of <= chunk_pages pages), owned by ONE warp.
+// Header words in shared memory: {valid, b, h, c, ctx, ntiles}.
+//
+// Every warp is an independent pipeline: it claims items from a global queue, gathers the chunk's block
+// ids from the block table, issues its own TMA loads two tiles ahead into a private 2-stage ring
+// (completion on an mbarrier) and consumes them with ldmatrix + mma.sync.  No CTA-wide barrier in the
+// steady state, and a warp only ever waits on a barrier phase it armed itself (no phase aliasing).
 template <typename T, int kGroup>
 __global__ void __launch_bounds__(kThreads, 1)
 paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
@@ -141,17 +150,17 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bars = smem_base + SmemLayout::kBars;
     int* prefix = reinterpret_cast<int*>(smem + SmemLayout::kPrefix);
-    auto full_bar = [&](int s) { return bars + s * 8; };
-    auto empty_bar = [&](int s) { return bars + (kStages + s) * 8; };
+    int* hdr = reinterpret_cast<int*>(smem + SmemLayout::kHdr) + warp * 32;          // [4][8]
+    const uint32_t my_stages = smem_base + warp * kStagesPerWarp * kStageBytes;
+    const uint32_t my_bars = smem_base + SmemLayout::kBars + warp * kStagesPerWarp * 8;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    if (lane == 0) {
+        for (int s = 0; s < kStagesPerWarp; ++s) mbar_init(my_bars + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // chunk prefix over sequences from the device-side context lengths
+    // chunk prefix over sequences from the DEVICE-side context lengths
     const int chunk_tokens = p.chunk_pages * kPage;
     for (int b = threadIdx.x; b < p.num_seqs; b += kThreads) {
         const int ctx = (int)p.context_lens[b];
@@ -165,54 +174,74 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     __syncthreads();
     const int total_items = prefix[p.num_seqs] * p.num_kv_heads;
 
-    // item -> (seq, kv head, chunk, pages in chunk, valid tokens of the last page)
-    auto decode_item = [&](int item, int& b, int& h, int& c, int& npages, int& ctx) {
-        const int pair = item / p.num_kv_heads;
-        h = item - pair * p.num_kv_heads;
+    // claim the next item of the global queue into header slot `slot`; returns the lane-distributed block ids
+    int n_claimed = 0;
+    auto claim = [&](bool& valid, int& h, int& ntiles) -> uint32_t {
+        unsigned int id = 0;
+        if (lane == 0) id = atomicAdd(p.counter, 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        int* hd = hdr + (n_claimed & 3) * 8;
+        ++n_claimed;
+        valid = id < (unsigned int)total_items;
+        h = 0; ntiles = 0;
+        if (!valid) {
+            if (lane == 0) hd[0] = 0;
+            return 0u;
+        }
+        const int pair = (int)id / p.num_kv_heads;
+        h = (int)id - pair * p.num_kv_heads;              // kv head fastest: neighbours share DRAM pages
         int lo = 0, hi = p.num_seqs;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= pair) lo = mid; else hi = mid; }
-        b = lo;
-        c = pair - prefix[b];
-        ctx = (int)p.context_lens[b];
-        const int pages_total = (ctx + kPage - 1) / kPage;
-        npages = min(p.chunk_pages, pages_total - c * p.chunk_pages);
+        const int c = pair - prefix[lo];
+        const int ctx = (int)p.context_lens[lo];
+        const int ntok = min(chunk_tokens, ctx - c * chunk_tokens);
+        ntiles = (ntok + kTile - 1) / kTile;
+        const int npages = (ntok + kPage - 1) / kPage;
+        if (lane == 0) { hd[0] = 1; hd[1] = lo; hd[2] = h; hd[3] = c; hd[4] = ctx; hd[5] = ntiles; }
+        return lane < npages ? p.block_tables[(int64_t)lo * p.max_blocks + c * p.chunk_pages + lane] : 0u;
     };
 
-    if (warp == kConsumerWarps) {
-        // ===================================== PRODUCER ==========================================
-        uint64_t policy;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        int n = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-            int b, h, c, npages, ctx;
-            decode_item(item, b, h, c, npages, ctx);
-            const uint32_t my_block = lane < npages ? p.block_tables[(int64_t)b * p.max_blocks + c * p.chunk_pages + lane] : 0u;
-            for (int j = 0; j < npages; ++j, ++n) {
-                const int blk = (int)__shfl_sync(0xffffffffu, my_block, j);
-                if (lane == 0) {
-                    const int s = n % kStages;
-                    mbar_wait(empty_bar(s), ((n / kStages) & 1) ^ 1);
-                    mbar_expect_tx(full_bar(s), kStageBytes);
-                    const uint32_t dst = smem_base + s * kStageBytes;
-                    tma_load_4d(dst, &kmap, full_bar(s), 0, h, 0, blk, policy);
-                    tma_load_4d(dst + kHalfTileBytes, &kmap, full_bar(s), 64, h, 0, blk, policy);
-                    tma_load_4d(dst + 2 * kHalfTileBytes, &vmap, full_bar(s), 0, h, 0, blk, policy);
-                    tma_load_4d(dst + 3 * kHalfTileBytes, &vmap, full_bar(s), 64, h, 0, blk, policy);
-                }
-            }
-        }
-        return;
-    }
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
-    // ========================================= CONSUMERS ==========================================
+    // ---- producer cursor: runs kStagesPerWarp tiles ahead of the consumer ---------------------------
+    bool pc_valid, pn_valid;
+    int pc_h, pc_ntiles, pn_h, pn_ntiles, p_tile = 0;
+    uint32_t pc_blk = claim(pc_valid, pc_h, pc_ntiles);
+    uint32_t pn_blk = claim(pn_valid, pn_h, pn_ntiles);
+    unsigned int issued = 0;
+    auto issue_one = [&]() {
+        if (!pc_valid) return;
+        const int blk = (int)__shfl_sync(0xffffffffu, pc_blk, p_tile >> 1);
+        if (lane == 0) {
+            const int s = issued % kStagesPerWarp;
+            const uint32_t bar = my_bars + s * 8, dst = my_stages + s * kStageBytes;
+            const int tok = (p_tile & 1) * kTile;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // our generic accesses to this stage are done
+            mbar_expect_tx(bar, kStageBytes);
+            tma_load_4d(dst, &kmap, bar, 0, pc_h, tok, blk, policy);
+            tma_load_4d(dst + kSubTileBytes, &kmap, bar, 64, pc_h, tok, blk, policy);
+            tma_load_4d(dst + 2 * kSubTileBytes, &vmap, bar, 0, pc_h, tok, blk, policy);
+            tma_load_4d(dst + 3 * kSubTileBytes, &vmap, bar, 64, pc_h, tok, blk, policy);
+        }
+        ++issued;
+        if (++p_tile == pc_ntiles) {
+            pc_valid = pn_valid; pc_h = pn_h; pc_ntiles = pn_ntiles; pc_blk = pn_blk; p_tile = 0;
+            pn_blk = claim(pn_valid, pn_h, pn_ntiles);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < kStagesPerWarp; ++s) issue_one();
+
+    // ---- consumer -----------------------------------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
-    float* scr_o = reinterpret_cast<float*>(smem + SmemLayout::kScratchO);
-    float* scr_ml = reinterpret_cast<float*>(smem + SmemLayout::kScratchML);
     const T* qbase = static_cast<const T*>(p.q);
-    int n_base = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int b, h, c, npages, ctx;
-        decode_item(item, b, h, c, npages, ctx);
+    unsigned int consumed = 0;
+    for (int c_slot = 0;; ++c_slot) {
+        __syncwarp();
+        const int* hd = hdr + (c_slot & 3) * 8;
+        if (hd[0] == 0) break;
+        const int b = hd[1], h = hd[2], c = hd[3], ctx = hd[4], ntiles = hd[5];
 
         // Q fragments: rows = the group's query heads (g < kGroup), zero padding otherwise
         uint32_t qa[8][2];
@@ -227,26 +256,25 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         float o[16][4];
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;         // log2-domain running max, this thread's partial row sum
+        float m_run = -INFINITY, l_run = 0.f;         // log2-domain running max; this thread's partial row sum
 
-        for (int j = warp; j < npages; j += kConsumerWarps) {
-            const int n = n_base + j;
-            const int s = n % kStages;
-            mbar_wait(full_bar(s), (n / kStages) & 1);
-            const uint32_t kt = smem_base + s * kStageBytes, vt = kt + 2 * kHalfTileBytes;
-            const int valid = min(kPage, ctx - (c * p.chunk_pages + j) * kPage);
+        for (int tl = 0; tl < ntiles; ++tl) {
+            const int s = consumed % kStagesPerWarp;
+            mbar_wait(my_bars + s * 8, (consumed / kStagesPerWarp) & 1);
+            const uint32_t kt = my_stages + s * kStageBytes, vt = kt + 2 * kSubTileBytes;
+            const int valid = min(kTile, ctx - (c * chunk_tokens + tl * kTile));
 
-            // ---- S = Q K^T : 8 n-tiles (8 tokens each) x 8 k-steps --------------------------------
-            float sacc[8][4];
+            // ---- S = Q K^T : 4 n-tiles (8 tokens each) x 8 k-steps --------------------------------
+            float sacc[4][4];
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+            for (int nt = 0; nt < 4; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
+            for (int nt = 0; nt < 4; ++nt) {
                 const int row = nt * 8 + (lane & 7);
 #pragma unroll
                 for (int kp = 0; kp < 4; ++kp) {            // 32 dims (2 k-steps) per ldmatrix.x4
                     const int chunk = kp * 4 + (lane >> 3);  // 16-byte chunk index 0..15 along the 128 dims
-                    const uint32_t addr = kt + (chunk >> 3) * kHalfTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+                    const uint32_t addr = kt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
                     uint32_t kb[4];
                     ldmatrix_x4(kb, addr);
                     const uint32_t a0[4] = {qa[2 * kp][0], 0u, qa[2 * kp][1], 0u};
@@ -258,7 +286,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             // ---- mask + online softmax (rows g; rows g+8 are padding) -----------------------------
             float mx = -INFINITY;
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
+            for (int nt = 0; nt < 4; ++nt) {
                 const int tok = nt * 8 + 2 * t;
                 sacc[nt][0] = tok < valid ? sacc[nt][0] * p.scale_log2 : -INFINITY;
                 sacc[nt][1] = tok + 1 < valid ? sacc[nt][1] * p.scale_log2 : -INFINITY;
@@ -266,13 +294,13 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            const float m_new = fmaxf(m_run, mx);            // finite: every page holds >= 1 valid token
+            const float m_new = fmaxf(m_run, mx);            // finite: every tile holds >= 1 valid token
             const float corr = fast_exp2(m_run - m_new);
             m_run = m_new;
             l_run *= corr;
-            uint32_t pa[8];                                  // P as packed 16-bit pairs, per n-tile
+            uint32_t pa[4];                                  // P as packed 16-bit pairs, per n-tile
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
+            for (int nt = 0; nt < 4; ++nt) {
                 const float p0 = fast_exp2(sacc[nt][0] - m_new), p1 = fast_exp2(sacc[nt][1] - m_new);
                 l_run += p0 + p1;
                 pa[nt] = pack2<T>(p0, p1);
@@ -282,24 +310,23 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
                 for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
             }
             // V rows past the context may hold non-finite garbage: 0 * NaN would poison O
-            if (valid < kPage) {
-                for (int r = valid + (lane >> 4); r < kPage; r += 2) {
+            if (valid < kTile) {
+                for (int r = valid + (lane >> 4); r < kTile; r += 2) {
                     const int ch = lane & 15;
-                    *reinterpret_cast<int4*>(smem + (vt - smem_base) + (ch >> 3) * kHalfTileBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+                    *reinterpret_cast<int4*>(smem + (vt - smem_base) + (ch >> 3) * kSubTileBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
                         make_int4(0, 0, 0, 0);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes vs the next TMA refill
                 __syncwarp();
             }
-            // ---- O += P V : 4 k-steps (16 tokens) x 16 n-tiles (8 dims) ---------------------------
+            // ---- O += P V : 2 k-steps (16 tokens) x 16 n-tiles (8 dims) ---------------------------
 #pragma unroll
-            for (int ktk = 0; ktk < 4; ++ktk) {
+            for (int ktk = 0; ktk < 2; ++ktk) {
                 const uint32_t a[4] = {pa[2 * ktk], 0u, pa[2 * ktk + 1], 0u};
                 const int row = ktk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
 #pragma unroll
                 for (int np = 0; np < 8; ++np) {            // two 8-dim n-tiles per ldmatrix.x4.trans
                     const int chunk = np * 2 + (lane >> 4);
-                    const uint32_t addr = vt + (chunk >> 3) * kHalfTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+                    const uint32_t addr = vt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
                     uint32_t vb[4];
                     ldmatrix_x4_trans(vb, addr);
                     mma_16816<T>(o[2 * np], a, vb[0], vb[1]);
@@ -307,41 +334,20 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar(s));
+            issue_one();                                     // refill the stage we just drained (tile consumed + 2)
+            ++consumed;
         }
-        n_base += npages;
 
-        // ---- combine the 4 warps of this item, write the fp32 partial ------------------------------
+        // ---- fp32 partial of this item straight from registers ----------------------------------------
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
         if (g < kGroup) {
-            float* orow = scr_o + (warp * 8 + g) * kORow;
+            const int64_t slot = (((int64_t)b * p.num_kv_heads + h) * p.max_chunks + c) * kGroup + g;
+            float* orow = p.part_o + slot * kHeadDim;
 #pragma unroll
             for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(orow + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
-            if (t == 0) { scr_ml[(warp * 8 + g) * 2] = m_run; scr_ml[(warp * 8 + g) * 2 + 1] = l_run; }
+            if (t == 0) { p.part_ml[slot * 2] = m_run; p.part_ml[slot * 2 + 1] = l_run; }
         }
-        named_bar_sync(1, kConsumerWarps * 32);
-        {
-            const int d = threadIdx.x;                      // 0..127 = output dim
-            const int64_t slot = ((int64_t)b * p.num_kv_heads + h) * p.max_chunks + c;
-#pragma unroll
-            for (int r = 0; r < kGroup; ++r) {
-                float M = -INFINITY;
-#pragma unroll
-                for (int w = 0; w < kConsumerWarps; ++w) M = fmaxf(M, scr_ml[(w * 8 + r) * 2]);
-                float acc = 0.f, L = 0.f;
-#pragma unroll
-                for (int w = 0; w < kConsumerWarps; ++w) {
-                    const float mw = scr_ml[(w * 8 + r) * 2];
-                    const float wgt = mw == -INFINITY ? 0.f : exp2f(mw - M);
-                    acc += wgt * scr_o[(w * 8 + r) * kORow + d];
-                    L += wgt * scr_ml[(w * 8 + r) * 2 + 1];
-                }
-                p.part_o[(slot * kGroup + r) * kHeadDim + d] = acc;
-                if (d == 0) { p.part_ml[(slot * kGroup + r) * 2] = M; p.part_ml[(slot * kGroup + r) * 2 + 1] = L; }
-            }
-        }
-        named_bar_sync(1, kConsumerWarps * 32);
     }
 }
 
@@ -349,9 +355,10 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
 template <typename T, typename TOut>
 __global__ void __launch_bounds__(kHeadDim)
 paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o, const float* __restrict__ part_ml,
-                        const uint32_t* __restrict__ context_lens, int num_heads, int num_kv_heads, int group,
-                        int chunk_tokens, int max_chunks) {
+                        const uint32_t* __restrict__ context_lens, unsigned int* __restrict__ counter, int num_heads,
+                        int num_kv_heads, int group, int chunk_tokens, int max_chunks) {
     const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    if (head == 0 && b == 0 && d == 0) *counter = 0u;        // leave the work queue ready for the next launch
     const int h = head / group, r = head - h * group;
     const int ctx = (int)context_lens[b];
     const int nchunks = (ctx + chunk_tokens - 1) / chunk_tokens;
@@ -389,7 +396,7 @@ bool make_kv_map(CUtensorMap* map, const void* cache, int64_t num_blocks, int kv
     if (!enc) { set_error(kErrCuda, "paged_attention_decode: cuTensorMapEncodeTiled unavailable"); return false; }
     const cuuint64_t dims[4] = {(cuuint64_t)kHeadDim, (cuuint64_t)kvh, (cuuint64_t)kPage, (cuuint64_t)num_blocks};
     const cuuint64_t strides[3] = {(cuuint64_t)kHeadDim * 2, (cuuint64_t)kvh * kHeadDim * 2, (cuuint64_t)kPage * kvh * kHeadDim * 2};
-    const cuuint32_t box[4] = {64, 1, (cuuint32_t)kPage, 1};
+    const cuuint32_t box[4] = {64, 1, (cuuint32_t)kTile, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(map, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                            const_cast<void*>(cache), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -414,11 +421,12 @@ void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vma
         attr_set = true;
     }
     const int64_t max_items = (int64_t)a.num_seqs * a.num_kv_heads * p.max_chunks;
-    const int grid = (int)(max_items < sm_count() ? max_items : sm_count());
+    const int64_t want = (max_items + kWarps - 1) / kWarps;
+    const int grid = (int)(want < sm_count() ? want : sm_count());
     kern<<<grid, kThreads, SmemLayout::kTotal, st>>>(kmap, vmap, p);
     count_launch();
     paged_attn_merge_kernel<T, TOut><<<dim3(a.num_heads, a.num_seqs), kHeadDim, 0, st>>>(
-        static_cast<TOut*>(a.out), p.part_o, p.part_ml, a.context_lens, a.num_heads, a.num_kv_heads, kGroup,
+        static_cast<TOut*>(a.out), p.part_o, p.part_ml, a.context_lens, p.counter, a.num_heads, a.num_kv_heads, kGroup,
         p.chunk_pages * kPage, p.max_chunks);
     count_launch();
 }
@@ -446,7 +454,7 @@ bool paged_attention_decode_tma_supported(const DecodeArgs& a, float softcap, in
 size_t paged_attention_decode_tma_workspace(int num_seqs, int num_heads, int head_dim, int max_blocks, int block_size) {
     (void)block_size;
     // worst case: 1-page chunks -> max_blocks partials per (sequence, head)
-    return (size_t)num_seqs * num_heads * (size_t)max_blocks * ((size_t)head_dim * 4 + 8) + 256;
+    return (size_t)num_seqs * num_heads * (size_t)max_blocks * ((size_t)head_dim * 4 + 8) + 512;
 }
 
 void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
@@ -458,12 +466,14 @@ void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
     p.max_chunks = (a.max_blocks + p.chunk_pages - 1) / p.chunk_pages;
     p.scale_log2 = a.scale * 1.4426950408889634f;
     const size_t n_part = (size_t)a.num_seqs * a.num_kv_heads * p.max_chunks * group;
-    const size_t need = n_part * (kHeadDim * 4 + 8) + 16;
+    const size_t need = n_part * (kHeadDim * 4 + 8) + 256;
     if (!a.workspace || a.workspace_bytes < need) {
         set_error(kErrBadArg, "paged_attention_decode: workspace too small (%zu < %zu bytes)", a.workspace_bytes, need);
         return;
     }
-    p.part_o = static_cast<float*>(a.workspace);
+    // layout: [counter (256 B)] [partial O] [partial (m, l)]
+    p.counter = static_cast<unsigned int*>(a.workspace);
+    p.part_o = reinterpret_cast<float*>(static_cast<char*>(a.workspace) + 256);
     p.part_ml = p.part_o + n_part * kHeadDim;
     CUtensorMap km, vm;
     if (!make_kv_map(&km, a.kc, a.num_blocks, a.num_kv_heads, a.dtype) || !make_kv_map(&vm, a.vc, a.num_blocks, a.num_kv_heads, a.dtype)) return;

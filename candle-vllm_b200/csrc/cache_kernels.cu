@@ -43,7 +43,7 @@ copy_blocks_kernel(const __grid_constant__ CopyBlocksParams p, int num_pairs, in
     }
 }
 
-// tail bytes when bytes_per_block % 16 != 0 (never for real KV shapes; kept for exactness)
+// bytewise path when blocks are not 16-byte aligned / sized (never for real KV shapes; kept for exactness)
 __global__ void copy_blocks_tail_kernel(const __grid_constant__ CopyBlocksParams p, int num_pairs,
                                         int64_t bytes_per_block, int64_t tail_start) {
     const int layer = blockIdx.y >> 1;
@@ -80,7 +80,10 @@ static void copy_blocks_impl(void* key_cache_ptrs, void* value_cache_ptrs, const
             CopyBlocksParams prm;
             for (int l = 0; l < nl; ++l) { prm.kptr[l] = kp[l0 + l]; prm.vptr[l] = vp[l0 + l]; }
             for (int i = 0; i < np; ++i) { prm.src[i] = (int32_t)map[2 * (p0 + i)]; prm.dst[i] = (int32_t)map[2 * (p0 + i) + 1]; }
-            const int64_t vecs = (bytes >> 4) * np;
+            // 16-byte vector path needs every block start 16-byte aligned; otherwise copy bytewise
+            bool aligned = (bytes & 15) == 0;
+            for (int l = 0; l < nl && aligned; ++l) aligned = ((prm.kptr[l] | prm.vptr[l]) & 15) == 0;
+            const int64_t vecs = aligned ? (bytes >> 4) * np : 0;
             if (vecs > 0) {
                 int gx = (int)((vecs + 255) / 256);
                 const int cap = 8 * sm_count() / (2 * nl) + 1;     // ~8 CTAs/SM in total
@@ -88,8 +91,8 @@ static void copy_blocks_impl(void* key_cache_ptrs, void* value_cache_ptrs, const
                 copy_blocks_kernel<<<dim3(gx, 2 * nl), 256, 0, as_stream(stream)>>>(prm, np, bytes);
                 count_launch();
             }
-            if (bytes & 15) {
-                copy_blocks_tail_kernel<<<dim3(1, 2 * nl), 64, 0, as_stream(stream)>>>(prm, np, bytes, bytes & ~15ll);
+            if (!aligned) {
+                copy_blocks_tail_kernel<<<dim3(8, 2 * nl), 256, 0, as_stream(stream)>>>(prm, np, bytes, 0);
                 count_launch();
             }
         }

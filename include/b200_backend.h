@@ -86,7 +86,8 @@ void reshape_and_cache(const void* key, const void* value, void* key_cache, void
  * host max_context_len), so a graph captured with padded tables replays correctly (graph.rs:604).
  * softcap <= 0: none.  sliding_window <= 0: none.  out_dtype: `dtype`, or B200_F16 to hand the
  * result straight to a quantised GEMM (values are rounded to `dtype` first).
- * workspace: >= paged_attention_decode_workspace_bytes(...) bytes of device memory. */
+ * workspace: >= paged_attention_decode_workspace_bytes(...) bytes of device memory, zero-filled once
+ * before its first use (it holds the work-queue head, which every call leaves at zero again). */
 size_t paged_attention_decode_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t head_dim,
                                               int32_t max_blocks_per_seq, int32_t block_size);
 void paged_attention_decode(void* out, const void* q, const void* key_cache, const void* value_cache,
