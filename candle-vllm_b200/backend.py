@@ -26,7 +26,7 @@ from ._lib import BackendError, check, lib, require_device
 
 
 class DType:
-    F32, F16, BF16, U8, FP8_E4M3 = 0, 1, 2, 3, 4
+    F32, F16, BF16, U8, FP8_E4M3, F16_K4 = 0, 1, 2, 3, 4, 5
 
 
 class GgmlType:
@@ -332,7 +332,9 @@ class QMatMul:
         L = lib()
         with torch.cuda.device(x.device):
             if x2.dtype == torch.float16:
-                L.qmatmul_f16act(_ptr(x2), _ptr(self.w.data), _ptr(y), C.c_int32(m), C.c_int32(n), C.c_int32(k),
+                xk4 = torch.empty_like(x2)          # the GEMM consumes fp16 activations in K4 order (b200_backend.h)
+                L.cast(_ptr(x2), _ptr(xk4), C.c_int64(x2.numel()), C.c_int32(DType.F16), C.c_int32(DType.F16_K4), _stream(x.device))
+                L.qmatmul_f16act(_ptr(xk4), _ptr(self.w.data), _ptr(y), C.c_int32(m), C.c_int32(n), C.c_int32(k),
                                  C.c_int32(self.w.ggml_type), C.c_int32(0), _stream(x.device))
             else:
                 need = L.qmatmul_workspace_bytes(C.c_int32(m), C.c_int32(n), C.c_int32(k))

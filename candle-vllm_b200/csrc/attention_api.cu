@@ -25,7 +25,9 @@ void paged_attention_decode(void* out, const void* q, const void* key_cache, con
     B200_REQUIRE(num_heads % num_kv_heads == 0, kErrBadArg, "paged_attention_decode: heads %d %% kv heads %d != 0", num_heads, num_kv_heads);
     B200_REQUIRE(head_dim <= 256, kErrUnsupported, "paged_attention_decode: head_dim %d > 256", head_dim);
     B200_REQUIRE(dtype == B200_BF16 || dtype == B200_F16, kErrUnsupported, "paged_attention_decode: dtype %d (bf16/f16 only)", dtype);
-    B200_REQUIRE(out_dtype == dtype || (dtype == B200_BF16 && out_dtype == B200_F16), kErrUnsupported, "paged_attention_decode: out dtype %d", out_dtype);
+    B200_REQUIRE(out_dtype == dtype || out_dtype == B200_F16_K4 || (dtype == B200_BF16 && out_dtype == B200_F16), kErrUnsupported,
+                 "paged_attention_decode: out dtype %d", out_dtype);
+    B200_REQUIRE(out_dtype != B200_F16_K4 || head_dim % 4 == 0, kErrBadArg, "paged_attention_decode: K4 output needs head_dim %% 4 == 0");
     const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
     B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "paged_attention_decode: cache dtype %d vs %d", cache_dtype, dtype);
     B200_REQUIRE(layout == B200_KV_FLASH || layout == B200_KV_PAGED, kErrBadArg, "paged_attention_decode: layout %d", layout);

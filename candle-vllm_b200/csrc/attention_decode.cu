@@ -352,7 +352,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
 }
 
 // merge the chunk partials of one (sequence, head); one CTA of 128 threads (= dims) each
-template <typename T, typename TOut>
+template <typename T, typename TOut, bool kK4 = false>
 __global__ void __launch_bounds__(kHeadDim)
 paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o, const float* __restrict__ part_ml,
                         const uint32_t* __restrict__ context_lens, unsigned int* __restrict__ counter, int num_heads,
@@ -372,7 +372,7 @@ paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o
         L += w * part_ml[((base + c) * group + r) * 2 + 1];
     }
     const float res = nchunks > 0 && L > 0.f ? acc / L : 0.f;
-    out[((int64_t)b * num_heads + head) * kHeadDim + d] = from_f32<TOut>(to_f32(from_f32<T>(res)));
+    out[((int64_t)b * num_heads + head) * kHeadDim + (kK4 ? (int)k4_index(d) : d)] = from_f32<TOut>(to_f32(from_f32<T>(res)));
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -412,7 +412,7 @@ int pick_chunk_pages(int num_seqs, int kvh, int max_blocks) {
     return chunk;
 }
 
-template <typename T, typename TOut, int kGroup>
+template <typename T, typename TOut, int kGroup, bool kK4 = false>
 void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, cudaStream_t st) {
     auto kern = paged_attn_decode_kernel<T, kGroup>;
     static bool attr_set = false;
@@ -425,19 +425,19 @@ void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vma
     const int grid = (int)(want < sm_count() ? want : sm_count());
     kern<<<grid, kThreads, SmemLayout::kTotal, st>>>(kmap, vmap, p);
     count_launch();
-    paged_attn_merge_kernel<T, TOut><<<dim3(a.num_heads, a.num_seqs), kHeadDim, 0, st>>>(
+    paged_attn_merge_kernel<T, TOut, kK4><<<dim3(a.num_heads, a.num_seqs), kHeadDim, 0, st>>>(
         static_cast<TOut*>(a.out), p.part_o, p.part_ml, a.context_lens, p.counter, a.num_heads, a.num_kv_heads, kGroup,
         p.chunk_pages * kPage, p.max_chunks);
     count_launch();
 }
 
-template <typename T, typename TOut>
+template <typename T, typename TOut, bool kK4 = false>
 void launch_group(const DecodeArgs& a, const CUtensorMap& km, const CUtensorMap& vm, const DecodeParams& p, int group, cudaStream_t st) {
     switch (group) {
-        case 1: launch<T, TOut, 1>(a, km, vm, p, st); break;
-        case 2: launch<T, TOut, 2>(a, km, vm, p, st); break;
-        case 4: launch<T, TOut, 4>(a, km, vm, p, st); break;
-        case 8: launch<T, TOut, 8>(a, km, vm, p, st); break;
+        case 1: launch<T, TOut, 1, kK4>(a, km, vm, p, st); break;
+        case 2: launch<T, TOut, 2, kK4>(a, km, vm, p, st); break;
+        case 4: launch<T, TOut, 4, kK4>(a, km, vm, p, st); break;
+        case 8: launch<T, TOut, 8, kK4>(a, km, vm, p, st); break;
     }
 }
 
@@ -478,10 +478,12 @@ void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
     CUtensorMap km, vm;
     if (!make_kv_map(&km, a.kc, a.num_blocks, a.num_kv_heads, a.dtype) || !make_kv_map(&vm, a.vc, a.num_blocks, a.num_kv_heads, a.dtype)) return;
     if (a.dtype == B200_BF16) {
-        if (a.out_dtype == B200_F16) launch_group<__nv_bfloat16, __half>(a, km, vm, p, group, st);
+        if (a.out_dtype == B200_F16_K4) launch_group<__nv_bfloat16, __half, true>(a, km, vm, p, group, st);
+        else if (a.out_dtype == B200_F16) launch_group<__nv_bfloat16, __half>(a, km, vm, p, group, st);
         else launch_group<__nv_bfloat16, __nv_bfloat16>(a, km, vm, p, group, st);
     } else {
-        launch_group<__half, __half>(a, km, vm, p, group, st);
+        if (a.out_dtype == B200_F16_K4) launch_group<__half, __half, true>(a, km, vm, p, group, st);
+        else launch_group<__half, __half>(a, km, vm, p, group, st);
     }
     check_launch("paged_attention_decode");
 }

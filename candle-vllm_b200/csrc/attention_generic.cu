@@ -25,7 +25,7 @@ constexpr int kMaxDimPerLane = 8;   // head_dim <= 256
 template <typename T, typename TC, bool kFp8, typename TOut>
 __global__ void __launch_bounds__(kGenWarps * 32)
 paged_attention_generic_kernel(TOut* __restrict__ out, const T* __restrict__ q, const TC* __restrict__ kc,
-                               const TC* __restrict__ vc, const GenericAttnArgs a) {
+                               const TC* __restrict__ vc, const GenericAttnArgs a, const int k4) {
     const int h = blockIdx.x, row = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hd = a.head_dim;
@@ -105,28 +105,29 @@ paged_attention_generic_kernel(TOut* __restrict__ out, const T* __restrict__ q, 
         for (int w = 0; w < kGenWarps; ++w) o += sm_m[w] == -INFINITY ? 0.f : sm_acc[w][d] * __expf(sm_m[w] - gm);
         const float r = gl > 0.f ? o / gl : 0.f;
         // round to the model dtype first (the reference returns `dtype`), then to the requested out type
-        out[((int64_t)row * a.num_heads + h) * hd + d] = from_f32<TOut>(to_f32(from_f32<T>(r)));
+        out[((int64_t)row * a.num_heads + h) * hd + (k4 ? (int)k4_index(d) : d)] = from_f32<TOut>(to_f32(from_f32<T>(r)));
     }
 }
 
 template <typename T, typename TOut>
 static void launch_generic(void* out, const void* q, const void* kc, const void* vc, const GenericAttnArgs& a,
-                           int rows, int cache_dtype, cudaStream_t st) {
+                           int rows, int cache_dtype, int k4, cudaStream_t st) {
     dim3 grid(a.num_heads, rows);
     if (cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8)
-        paged_attention_generic_kernel<T, uint8_t, true, TOut><<<grid, kGenWarps * 32, 0, st>>>((TOut*)out, (const T*)q, (const uint8_t*)kc, (const uint8_t*)vc, a);
+        paged_attention_generic_kernel<T, uint8_t, true, TOut><<<grid, kGenWarps * 32, 0, st>>>((TOut*)out, (const T*)q, (const uint8_t*)kc, (const uint8_t*)vc, a, k4);
     else
-        paged_attention_generic_kernel<T, T, false, TOut><<<grid, kGenWarps * 32, 0, st>>>((TOut*)out, (const T*)q, (const T*)kc, (const T*)vc, a);
+        paged_attention_generic_kernel<T, T, false, TOut><<<grid, kGenWarps * 32, 0, st>>>((TOut*)out, (const T*)q, (const T*)kc, (const T*)vc, a, k4);
     count_launch();
 }
 
 void paged_attention_generic(void* out, const void* q, const void* kc, const void* vc, const GenericAttnArgs& a,
                              int rows, int dtype, int cache_dtype, int out_dtype, cudaStream_t st) {
+    const int k4 = out_dtype == B200_F16_K4;
     if (dtype == B200_BF16) {
-        if (out_dtype == B200_F16) launch_generic<__nv_bfloat16, __half>(out, q, kc, vc, a, rows, cache_dtype, st);
-        else launch_generic<__nv_bfloat16, __nv_bfloat16>(out, q, kc, vc, a, rows, cache_dtype, st);
+        if (out_dtype == B200_F16 || k4) launch_generic<__nv_bfloat16, __half>(out, q, kc, vc, a, rows, cache_dtype, k4, st);
+        else launch_generic<__nv_bfloat16, __nv_bfloat16>(out, q, kc, vc, a, rows, cache_dtype, 0, st);
     } else {
-        launch_generic<__half, __half>(out, q, kc, vc, a, rows, cache_dtype, st);
+        launch_generic<__half, __half>(out, q, kc, vc, a, rows, cache_dtype, k4, st);
     }
     check_launch("paged_attention_generic");
 }

@@ -62,6 +62,9 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// position of natural index k in the K4 activation order (swap the middle two of every 4; self-inverse)
+__host__ __device__ __forceinline__ int64_t k4_index(int64_t k) { return (k & ~3ll) | ((0xD8 >> ((k & 3) * 2)) & 3); }
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- GGML block formats (GGUF spec) -----------------------------------

@@ -10,7 +10,7 @@
 namespace b200 {
 
 // ---- rms_norm: one CTA per row, row cached in registers (n <= 8 * 1024 with 256 threads x 4 x float4...)
-template <typename TOut>
+template <typename TOut, bool kK4 = false>
 __global__ void __launch_bounds__(256)
 rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, TOut* __restrict__ out, int n, float eps) {
     const int row = blockIdx.x;
@@ -33,7 +33,7 @@ rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, TOut* 
     for (int i = 0; i < 8; ++i) tot += (i < (int)(blockDim.x >> 5)) ? red[i] : 0.f;
     const float sc = rsqrtf(tot / (float)n + eps);
     TOut* o = out + (int64_t)row * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) o[i] = from_f32<TOut>(xr[i] * sc * w[i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) o[kK4 ? k4_index(i) : i] = from_f32<TOut>(xr[i] * sc * w[i]);
 }
 
 // ---- RoPE in place on f32 q,k --------------------------------------------------------------
@@ -59,9 +59,9 @@ __global__ void fused_rope_f32_kernel(float* __restrict__ q, float* __restrict__
 
 // ---- fused: rope(q,k) + q -> 16-bit + k,v -> cache (flash layout) ----------------------------
 // qkv f32 [T, (h + 2 kvh) * hd] is the packed output of the fused QKV projection.
-template <typename T16, bool kFp8>
+template <typename T16, bool kFp8, bool kZeroSrc = false>
 __global__ void __launch_bounds__(256)
-rope_and_cache_kernel(const float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
+rope_and_cache_kernel(float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
                       const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                       const int64_t* __restrict__ positions, const int64_t* __restrict__ slot_mapping,
                       int num_heads, int num_kv_heads, int head_dim, int interleaved) {
@@ -70,7 +70,7 @@ rope_and_cache_kernel(const float* __restrict__ qkv, T16* __restrict__ q_out, vo
     const int64_t pos = positions[t];
     const int64_t slot = slot_mapping[t];
     const int row = (num_heads + 2 * num_kv_heads) * head_dim;
-    const float* src = qkv + (int64_t)t * row;
+    float* src = qkv + (int64_t)t * row;
     const int nrot = (num_heads + num_kv_heads) * half;
     const int kvn = num_kv_heads * head_dim;
     for (int i = threadIdx.x; i < nrot; i += blockDim.x) {
@@ -98,18 +98,24 @@ rope_and_cache_kernel(const float* __restrict__ qkv, T16* __restrict__ q_out, vo
     }
     if (slot >= 0) {
         const float* v = src + (num_heads + num_kv_heads) * head_dim;
+        (void)v;
         for (int i = threadIdx.x; i < kvn; i += blockDim.x) {
             if constexpr (kFp8) static_cast<uint8_t*>(vc_)[slot * kvn + i] = f32_to_e4m3(to_f32(from_f32<T16>(v[i])));
             else static_cast<T16*>(vc_)[slot * kvn + i] = from_f32<T16>(v[i]);
         }
     }
+    if constexpr (kZeroSrc) {          // leave the split-K accumulator zeroed for the next layer's QKV GEMM
+        __syncthreads();
+        for (int i = threadIdx.x; i < row; i += blockDim.x) src[i] = 0.f;
+    }
 }
 
-template <typename TOut>
-__global__ void silu_mul_kernel(const float* __restrict__ g, const float* __restrict__ u, TOut* __restrict__ out, int64_t n) {
+template <typename TOut, bool kK4 = false, bool kZeroSrc = false>
+__global__ void silu_mul_kernel(float* __restrict__ g, float* __restrict__ u, TOut* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float a = g[i];
-        out[i] = from_f32<TOut>(a / (1.f + __expf(-a)) * u[i]);
+        out[kK4 ? k4_index(i) : i] = from_f32<TOut>(a / (1.f + __expf(-a)) * u[i]);
+        if (kZeroSrc) { g[i] = 0.f; u[i] = 0.f; }           // leave the split-K accumulators zeroed for the next GEMM
     }
 }
 
@@ -117,10 +123,10 @@ __global__ void add_f32_kernel(float* __restrict__ x, const float* __restrict__ 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += y[i];
 }
 
-template <typename TS, typename TD>
+template <typename TS, typename TD, bool kK4 = false>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        d[i] = from_f32<TD>(to_f32(s[i]));
+        d[kK4 ? k4_index(i) : i] = from_f32<TD>(to_f32(s[i]));
 }
 
 __global__ void embedding_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
@@ -184,6 +190,7 @@ void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int3
     B200_REQUIRE(((uintptr_t)x & 15) == 0 && n % 4 == 0, kErrBadArg, "rms_norm: x must be 16-byte aligned, n %% 4 == 0");
     if (out_dtype == B200_F32) rms_norm_kernel<float><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (float*)out, n, eps);
     else if (out_dtype == B200_F16) rms_norm_kernel<__half><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);
+    else if (out_dtype == B200_F16_K4) rms_norm_kernel<__half, true><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);
     else if (out_dtype == B200_BF16) rms_norm_kernel<__nv_bfloat16><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__nv_bfloat16*)out, n, eps);
     else { set_error(kErrUnsupported, "rms_norm: out dtype %d", out_dtype); return; }
     count_launch();
@@ -200,31 +207,56 @@ void fused_rope_f32(float* q, float* k, const float* cos_t, const float* sin_t, 
     check_launch("fused_rope");
 }
 
+}  // extern "C"
+
+namespace b200 {
+void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_cache,
+                    const float* cos_t, const float* sin_t, const int64_t* positions,
+                    const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
+                    int32_t num_kv_heads, int32_t head_dim, int32_t interleaved,
+                    int32_t dtype, int32_t cache_dtype, bool zero_src, int64_t stream) {
+    if (num_tokens == 0) return;
+    B200_REQUIRE(qkv && q_out && key_cache && value_cache && cos_t && sin_t && positions && slot_mapping, kErrBadArg, "rope_and_cache: null pointer");
+    const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
+    B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "rope_and_cache: cache dtype %d vs dtype %d", cache_dtype, dtype);
+    cudaStream_t st = as_stream(stream);
+#define LAUNCH(T16, F8, Z) rope_and_cache_kernel<T16, F8, Z><<<num_tokens, 256, 0, st>>>(qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved)
+#define LAUNCH2(T16, F8) do { if (zero_src) LAUNCH(T16, F8, true); else LAUNCH(T16, F8, false); } while (0)
+    if (dtype == B200_BF16) { if (fp8) LAUNCH2(__nv_bfloat16, true); else LAUNCH2(__nv_bfloat16, false); }
+    else if (dtype == B200_F16) { if (fp8) LAUNCH2(__half, true); else LAUNCH2(__half, false); }
+    else { set_error(kErrUnsupported, "rope_and_cache: dtype %d", dtype); return; }
+#undef LAUNCH2
+#undef LAUNCH
+    count_launch();
+    check_launch("rope_and_cache");
+}
+
+void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, int64_t stream) {
+    silu_mul_kernel<__half, true, true><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(gate, up, (__half*)out_f16_k4, numel);
+    count_launch();
+    check_launch("silu_mul");
+}
+}  // namespace b200
+
+extern "C" {
+
 void rope_and_cache(const float* qkv, void* q_out, void* key_cache, void* value_cache,
                     const float* cos_t, const float* sin_t, const int64_t* positions,
                     const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
                     int32_t num_kv_heads, int32_t head_dim, int32_t block_size, int32_t interleaved,
                     int32_t dtype, int32_t cache_dtype, int64_t stream) {
     (void)block_size;
-    if (num_tokens == 0) return;
-    B200_REQUIRE(qkv && q_out && key_cache && value_cache && cos_t && sin_t && positions && slot_mapping, kErrBadArg, "rope_and_cache: null pointer");
-    const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
-    B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "rope_and_cache: cache dtype %d vs dtype %d", cache_dtype, dtype);
-    cudaStream_t st = as_stream(stream);
-#define LAUNCH(T16, F8) rope_and_cache_kernel<T16, F8><<<num_tokens, 256, 0, st>>>(qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved)
-    if (dtype == B200_BF16) { if (fp8) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
-    else if (dtype == B200_F16) { if (fp8) LAUNCH(__half, true); else LAUNCH(__half, false); }
-    else { set_error(kErrUnsupported, "rope_and_cache: dtype %d", dtype); return; }
-#undef LAUNCH
-    count_launch();
-    check_launch("rope_and_cache");
+    rope_and_cache_impl(const_cast<float*>(qkv), q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_tokens,
+                        num_heads, num_kv_heads, head_dim, interleaved, dtype, cache_dtype, false, stream);
 }
 
 void silu_mul(const float* gate, const float* up, void* out, int64_t numel, int32_t out_dtype, int64_t stream) {
     if (numel == 0) return;
     B200_REQUIRE(gate && up && out && numel > 0, kErrBadArg, "silu_mul: bad arguments");
-    if (out_dtype == B200_F32) silu_mul_kernel<float><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(gate, up, (float*)out, numel);
-    else if (out_dtype == B200_F16) silu_mul_kernel<__half><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(gate, up, (__half*)out, numel);
+    float* g = const_cast<float*>(gate); float* u = const_cast<float*>(up);
+    if (out_dtype == B200_F32) silu_mul_kernel<float><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(g, u, (float*)out, numel);
+    else if (out_dtype == B200_F16) silu_mul_kernel<__half><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(g, u, (__half*)out, numel);
+    else if (out_dtype == B200_F16_K4) silu_mul_kernel<__half, true><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(g, u, (__half*)out, numel);
     else { set_error(kErrUnsupported, "silu_mul: out dtype %d", out_dtype); return; }
     count_launch();
     check_launch("silu_mul");
@@ -248,6 +280,9 @@ void cast(const void* src, void* dst, int64_t numel, int32_t sd, int32_t dd, int
     C(B200_F16, __half, B200_F32, float) C(B200_BF16, __nv_bfloat16, B200_F32, float)
     C(B200_BF16, __nv_bfloat16, B200_F16, __half) C(B200_F16, __half, B200_BF16, __nv_bfloat16)
 #undef C
+#define C4(SD, ST) if (sd == SD && dd == B200_F16_K4) { cast_kernel<ST, __half, true><<<g, 256, 0, st>>>((const ST*)src, (__half*)dst, numel); count_launch(); check_launch("cast"); return; }
+    C4(B200_F32, float) C4(B200_F16, __half) C4(B200_BF16, __nv_bfloat16)
+#undef C4
     set_error(kErrUnsupported, "cast: %d -> %d unsupported", sd, dd);
 }
 

@@ -97,15 +97,17 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
     embedding_f32(m->tok_embeddings, m->d_tokens, m->x, B, H, s);
     for (int l = 0; l < c.num_layers; ++l) {
         const b200_llama_layer& w = m->layers[l];
-        rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16, s);
-        qmatmul_dispatch(m->xn, w.wq, m->qkv, m->qkv_row, B, qd, H, w.tq, 0, st);
-        qmatmul_dispatch(m->xn, w.wk, m->qkv + qd, m->qkv_row, B, kd, H, w.tk, 0, st);
-        qmatmul_dispatch(m->xn, w.wv, m->qkv + qd + kd, m->qkv_row, B, kd, H, w.tv, 0, st);
-        rope_and_cache(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
-                       m->heads_l, m->kv_l, hd, c.block_size, /*interleaved=*/1, B200_BF16, c.kv_dtype, s);
+        rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+        // QKV / gate / up accumulate (split-K) into buffers that their consumers leave zeroed
+        qmatmul_dispatch(m->xn, w.wq, m->qkv, m->qkv_row, B, qd, H, w.tq, 1, st);
+        qmatmul_dispatch(m->xn, w.wk, m->qkv + qd, m->qkv_row, B, kd, H, w.tk, 1, st);
+        qmatmul_dispatch(m->xn, w.wv, m->qkv + qd + kd, m->qkv_row, B, kd, H, w.tv, 1, st);
+        // (also re-zeroes qkv: the split-K GEMMs accumulate into it)
+        rope_and_cache_impl(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
+                            m->heads_l, m->kv_l, hd, /*interleaved=*/1, B200_BF16, c.kv_dtype, /*zero_src=*/true, s);
         paged_attention_decode(m->attn16, m->q16, m->kc[l], m->vc[l], m->d_tables, m->d_ctx, B, m->heads_l, m->kv_l, hd,
                                c.block_size, c.max_blocks_per_seq, m->num_blocks, 1.0f / sqrtf((float)hd), 0.f, 0,
-                               B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16, m->attn_ws, m->attn_ws_bytes, s);
+                               B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16_K4, m->attn_ws, m->attn_ws_bytes, s);
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->attn16, w.wo, m->x, H, B, H, qd, w.to, 1, st);          // x += wo(attn)
         } else {
@@ -115,10 +117,10 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);   // tp.cu (NCCL)
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
-        rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16, s);
-        qmatmul_dispatch(m->xn, w.w1, m->gate, m->ffn_l, B, m->ffn_l, H, w.t1, 0, st);
-        qmatmul_dispatch(m->xn, w.w3, m->up, m->ffn_l, B, m->ffn_l, H, w.t3, 0, st);
-        silu_mul(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, B200_F16, s);
+        rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+        qmatmul_dispatch(m->xn, w.w1, m->gate, m->ffn_l, B, m->ffn_l, H, w.t1, 1, st);
+        qmatmul_dispatch(m->xn, w.w3, m->up, m->ffn_l, B, m->ffn_l, H, w.t3, 1, st);
+        silu_mul_zero_src(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, s);      // act = silu(gate)*up; gate/up re-zeroed
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->act16, w.w2, m->x, H, B, H, m->ffn_l, w.t2, 1, st);     // x += w2(act)
         } else {
@@ -128,7 +130,10 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
     }
-    rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, B200_F16, s);
+    rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+    if (qmatmul_tc_supported(B, m->vocab_l, H, m->output_type) && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) {
+        zero_f32_kernel<<<sm_count() * 2, 256, 0, st>>>(m->logits, (int64_t)B * m->vocab_l); count_launch();
+    }
     qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
     argmax_f32(m->logits, m->next_tokens, B, m->vocab_l, s);
     return (int)(b200_total_kernel_launches() - n0);

@@ -10,6 +10,15 @@ void qmatmul_generic(const void* x, bool x_is_f16, const void* w, float* y, int6
 
 // tcgen05 path (qmatmul_tc.cu): fp16 activations [m,k], m <= 32 * n_mtiles; returns false when the shape is not covered
 bool qmatmul_tc_supported(int m, int n, int k, int ggml_type);
+// true when some output tile is split across CTAs: y must hold the addend (zeros for a plain product)
+bool qmatmul_tc_needs_zeroed_output(int n, int k);
+
+// elementwise.cu internals used by the engine
+void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_cache, const float* cos_t, const float* sin_t,
+                         const int64_t* positions, const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
+                         int32_t num_kv_heads, int32_t head_dim, int32_t interleaved, int32_t dtype, int32_t cache_dtype,
+                         bool zero_src, int64_t stream);
+void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, int64_t stream);
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
                 int accumulate, cudaStream_t st);
 

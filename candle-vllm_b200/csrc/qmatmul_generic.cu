@@ -49,8 +49,10 @@ qmatmul_generic_kernel(const TX* __restrict__ x, const void* __restrict__ w_, fl
         for (int i = 0; i < kMTile; ++i) {
             if (m0 + i < m) {
                 const TX* xr = x + (int64_t)(m0 + i) * k + k0;
+                // fp16 activations arrive in K4 order (middle two of every 4 swapped); f32 ones are natural
+                constexpr bool k4 = sizeof(TX) == 2;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i] += to_f32(from_f32<__half>(to_f32(xr[j]))) * wv[j];
+                for (int j = 0; j < 8; ++j) acc[i] += to_f32(from_f32<__half>(to_f32(xr[k4 ? (int)k4_index(j) : j]))) * wv[j];
             }
         }
     }
@@ -121,6 +123,8 @@ void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32
                     int32_t ggml_type, int32_t accumulate, int64_t stream) {
     if (m == 0 || n == 0) return;
     if (!qmm_check("qmatmul_f16act", x_f16, w, y, m, n, k, ggml_type)) return;
+    if (!accumulate && qmatmul_tc_supported(m, n, k, ggml_type) && qmatmul_tc_needs_zeroed_output(n, k))
+        cudaMemsetAsync(y, 0, (size_t)m * n * sizeof(float), as_stream(stream));
     qmatmul_dispatch(x_f16, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));
 }
 
@@ -131,7 +135,8 @@ void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, 
     if (qmatmul_tc_supported(m, n, k, ggml_type)) {
         B200_REQUIRE(workspace && workspace_bytes >= qmatmul_workspace_bytes(m, n, k), kErrBadArg,
                      "qmatmul_f32: workspace too small (%zu < %zu)", workspace_bytes, qmatmul_workspace_bytes(m, n, k));
-        cast(x, workspace, (int64_t)m * k, B200_F32, B200_F16, stream);
+        cast(x, workspace, (int64_t)m * k, B200_F32, B200_F16_K4, stream);
+        if (!accumulate && qmatmul_tc_needs_zeroed_output(n, k)) cudaMemsetAsync(y, 0, (size_t)m * n * sizeof(float), as_stream(stream));
         qmatmul_tc(workspace, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));
     } else {
         qmatmul_generic(x, false, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));

@@ -1,6 +1,414 @@
-// qmatmul_tc.cu -- placeholder until the tcgen05 dequant-GEMM lands.
+// qmatmul_tc.cu -- tcgen05 dequant-GEMM for GGML Q4_K weights at decode batch sizes (m <= 64).
+//
+//   y[m, n] (+)= sum_k x[m, k] * dequant(W)[n, k]        W = verbatim GGUF Q4_K blocks, row-major over n
+//
+// The op is an HBM-bound weight stream (0.5625 B/weight, 114 flop/B at m = 32); the tensor core is
+// there so that the CUDA cores only have to DEQUANTISE, never multiply:
+//   * "swap-AB": the weight tile is the UMMA A operand (M = 128 weight rows), the activations are the
+//     B operand (N = 32 or 64 batch rows), D[128 x N] fp32 lives in TMEM.
+//   * warp 8 (one lane) streams raw Q4_K super-blocks with TMA: a 2-D byte tensor map over W with a
+//     {144 B, 128 rows} box (one super-block column of the tile = 18 KB) plus the matching 256-wide
+//     slice of the fp16 activations (4 swizzled {64, N} boxes) into a 6-stage mbarrier ring.
+//   * warps 0-7 dequantise: thread = weight row = TMEM lane.  Each thread reads its own 144-byte
+//     block from shared memory (conflict-free LDS.128), decodes the 6-bit scales/mins, turns nibbles
+//     into fp16 with a subnormal bit trick (nibble placed in mantissa bits 6-9 = q * 2^-18, one HFMA2
+//     with (d*sc*2^18, -dmin*m) gives d*sc*q - dmin*m with a single rounding) and writes the fp16 row
+//     straight into TMEM (tcgen05.st) as the A operand -- the dequantised weights never touch shared
+//     memory.  Nibble pairs come out as (k0,k2),(k1,k3) per 4 weights; instead of permuting them the
+//     activations are stored in the matching "K4" order (see B200_F16_K4 in the header).
+//   * warp 9 (one lane) issues tcgen05.mma kind::f16 (A from TMEM, B from the swizzled smem tile),
+//     16 k-steps per super-block, commits to the stage / A-buffer barriers.
+//   * persistent stream-K: the (tile, super-block) space is cut into one contiguous range per CTA, so
+//     every SM streams the same number of bytes; tile segments are reduced with fp32 red.global.add
+//     (the residual add of wo / w2 falls out for free), whole tiles are stored.
+//
+// Reference semantics: QMatMul::forward (/root/reference/src/openai/models/linear.rs:765-806); block
+// format SURVEY.md Appendix A.  The reference's CUDA path quantises activations to Q8_1 and uses
+// dp4a; here activations are fp16 and accumulation fp32 (strictly closer to the fp32 target).
+#include <cuda.h>
+
 #include "qmatmul.cuh"
+
 namespace b200 {
-bool qmatmul_tc_supported(int, int, int, int) { return false; }
-void qmatmul_tc(const void*, const void*, float*, int64_t, int, int, int, int, int, cudaStream_t) {}
+
+namespace {
+
+constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
+constexpr int kSB = 256;             // weights per super-block
+constexpr int kDequantWarps = 8;
+constexpr int kThreads = (kDequantWarps + 2) * 32;
+constexpr int kWBytes = kTileN * 144;                   // 18432
+constexpr int kXSubBytes = 64 * 2;                      // 128-byte swizzled row
+constexpr int kColD = 0, kColA0 = 128, kColA1 = 256;    // TMEM columns (512 allocated)
+
+template <int kMB>   // batch rows padded to kMB (32 or 64) = UMMA N
+struct Cfg {
+    static constexpr int kStages = kMB == 32 ? 6 : 4;          // 34 KB / 50 KB per stage
+    static constexpr int kXBytes = 4 * kMB * kXSubBytes;        // 4 sub-tiles of [kMB][64] fp16
+    static constexpr int kStageBytes = kXBytes + kWBytes;       // X first (1024-aligned), then W
+    static constexpr int kBars = kStages * kStageBytes;         // full[kStages] empty[kStages] a_ready[2] a_free[2] d_full d_empty
+    static constexpr int kTmemSlot = kBars + (2 * kStages + 6) * 8;
+    static constexpr int kTotal = kTmemSlot + 16;
+    static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) = 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset        bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
+    return d;
+}
+
+struct GemmParams {
+    float* y;
+    int64_t ldy;
+    int m, n, nsb;                 // nsb = k / 256
+    int n_tiles;
+    int accumulate;
+};
+
+// 6-bit scale / min of sub-block J from the 12 packed bytes held in three 32-bit words (ggml get_scale_min_k4)
+template <int J>
+__device__ __forceinline__ void scale_min(uint32_t s0, uint32_t s1, uint32_t s2, int& sc, int& mn) {
+    auto byte = [&](int i) -> uint32_t { return ((i < 4 ? s0 : (i < 8 ? s1 : s2)) >> (8 * (i & 3))) & 0xffu; };
+    if constexpr (J < 4) { sc = byte(J) & 63; mn = byte(J + 4) & 63; }
+    else { sc = (byte(J + 4) & 0xF) | ((byte(J - 4) >> 6) << 4); mn = (byte(J + 4) >> 4) | ((byte(J) >> 6) << 4); }
+}
+
+// Dequantise sub-blocks 4*kHf .. 4*kHf+3 (128 weights) of this thread's Q4_K block into fp16 and store
+// them to 64 TMEM columns (two weights per 32-bit column; K4 order inside each group of four).
+template <int kHf>
+__device__ __forceinline__ void dequant_half(const uint8_t* blk, uint32_t a_col) {
+    const uint4 hdr = *reinterpret_cast<const uint4*>(blk);              // d | dmin | scales[12]
+    const __half2 dd = *reinterpret_cast<const __half2*>(&hdr.x);
+    const float d = __low2float(dd) * 262144.f;                          // 2^18 undoes the subnormal placement of the nibble
+    const float dmin = -__high2float(dd);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        constexpr int dummy = 0; (void)dummy;
+        int sc_lo, m_lo, sc_hi, m_hi;
+        if (cc == 0) { scale_min<4 * kHf>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo); scale_min<4 * kHf + 1>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi); }
+        else { scale_min<4 * kHf + 2>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo); scale_min<4 * kHf + 3>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi); }
+        const __half2 s_lo = __float2half2_rn(fminf(d * (float)sc_lo, 65504.f));
+        const __half2 s_hi = __float2half2_rn(fminf(d * (float)sc_hi, 65504.f));
+        const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
+        const int c = 2 * kHf + cc;                                      // 32-byte chunk of qs: sub-blocks 2c (lo nibbles), 2c+1 (hi)
+        const uint4 qa = *reinterpret_cast<const uint4*>(blk + 16 + c * 32);
+        const uint4 qb = *reinterpret_cast<const uint4*>(blk + 32 + c * 32);
+        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t x = w[i];
+            uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
+            uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
+            const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
+            const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
+            const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
+            const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
+            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+            v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+            v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+        }
+        tc_st32(a_col + cc * 32, v);
+    }
+}
+
+// =================================================================================================
+template <int kMB>
+__global__ void __launch_bounds__(kThreads, 1)
+qmatmul_q4k_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
+    using C = Cfg<kMB>;
+    constexpr int kStages = C::kStages;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base + C::kBars;
+    auto full_bar = [&](int s) { return bars + s * 8; };
+    auto empty_bar = [&](int s) { return bars + (kStages + s) * 8; };
+    auto a_ready = [&](int b) { return bars + (2 * kStages + b) * 8; };
+    auto a_free = [&](int b) { return bars + (2 * kStages + 2 + b) * 8; };
+    const uint32_t d_full = bars + (2 * kStages + 4) * 8, d_empty = bars + (2 * kStages + 5) * 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::kTmemSlot);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(a_ready(b), kDequantWarps); mbar_init(a_free(b), 1); }
+        mbar_init(d_full, 1);
+        mbar_init(d_empty, kDequantWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == kDequantWarps + 1) {      // MMA warp owns the TMEM allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- stream-K range of this CTA over the flattened (tile, super-block) space -----------------
+    const int64_t total = (int64_t)p.n_tiles * p.nsb;
+    const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == kDequantWarps) {
+        // ===================================== TMA PRODUCER =====================================
+        if (lane == 0) {
+            uint64_t pol_w, pol_x;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
+            int it = 0;
+            for (int64_t u = u0; u < u1; ++u, ++it) {
+                const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
+                const int s = it % kStages;
+                mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+                mbar_expect_tx(full_bar(s), C::kStageBytes);
+                const uint32_t dst = smem_base + s * C::kStageBytes;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, full_bar(s), sb * kSB + q * 64, 0, pol_x);
+                tma_load_2d(dst + C::kXBytes, &wmap, full_bar(s), sb * 144, tile * kTileN, pol_w);
+            }
+        }
+    } else if (warp == kDequantWarps + 1) {
+        // ======================================= MMA ISSUER ======================================
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A = B = f16, both K-major, N = kMB, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(kMB >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+            int it = 0, seg = 0;
+            for (int64_t u = u0; u < u1;) {
+                const int tile = (int)(u / p.nsb);
+                const int64_t tile_end = (int64_t)(tile + 1) * p.nsb;
+                const int64_t seg_end = tile_end < u1 ? tile_end : u1;
+                mbar_wait(d_empty, (seg & 1) ^ 1);                 // epilogue of the previous segment has drained D
+                tc_fence_after();
+                bool first = true;
+                for (; u < seg_end; ++u, ++it) {
+                    const int s = it % kStages, ab = it & 1;
+                    mbar_wait(full_bar(s), (it / kStages) & 1);       // activations landed (TMA)
+                    mbar_wait(a_ready(ab), (it >> 1) & 1);            // dequantised A tile is in TMEM
+                    tc_fence_after();
+                    const uint32_t a_t = tmem + (ab ? kColA1 : kColA0);
+                    const uint32_t xs = smem_base + s * C::kStageBytes;
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks) {
+                        const uint64_t bd = make_b_desc(xs + (ks >> 2) * kMB * kXSubBytes + (ks & 3) * 32);
+                        tc_mma_ts(tmem + kColD, a_t + ks * 8, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                    }
+                    first = false;
+                    tc_commit(empty_bar(s));          // stage (W bytes + X slice) reusable once these MMAs retire
+                    tc_commit(a_free(ab));            // and so is the A buffer
+                }
+                tc_commit(d_full);                    // accumulator of this segment complete
+                ++seg;
+            }
+        }
+    } else {
+        // ================================ DEQUANT + EPILOGUE WARPS ================================
+        const int qd = warp & 3, hf = warp >> 2;           // TMEM lane quadrant; which half of the super-block
+        const int row = qd * 32 + lane;                    // weight row within the tile = TMEM lane
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        int it = 0, seg = 0;
+        for (int64_t u = u0; u < u1;) {
+            const int tile = (int)(u / p.nsb);
+            const int64_t tile_begin = (int64_t)tile * p.nsb, tile_end = tile_begin + p.nsb;
+            const int64_t seg_begin = u, seg_end = tile_end < u1 ? tile_end : u1;
+            for (; u < seg_end; ++u, ++it) {
+                const int s = it % kStages, ab = it & 1;
+                mbar_wait(full_bar(s), (it / kStages) & 1);
+                mbar_wait(a_free(ab), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint8_t* blk = smem + s * C::kStageBytes + C::kXBytes + row * 144;
+                const uint32_t a_col = tmem + (ab ? kColA1 : kColA0) + lane_addr + hf * 64;
+                if (hf == 0) dequant_half<0>(blk, a_col); else dequant_half<1>(blk, a_col);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready(ab));
+            }
+            // ---- epilogue of the segment: D (TMEM) -> y ------------------------------------------------
+            mbar_wait(d_full, seg & 1);
+            tc_fence_after();
+            const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
+            const int n_idx = tile * kTileN + row;
+            constexpr int kColsPerHalf = kMB / 2;                 // this warp's share of the batch columns
+#pragma unroll
+            for (int c0 = 0; c0 < kColsPerHalf; c0 += 16) {
+                uint32_t acc[16];
+                tc_ld16(tmem + kColD + lane_addr + hf * kColsPerHalf + c0, acc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (n_idx < p.n) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int mi = hf * kColsPerHalf + c0 + i;
+                        if (mi < p.m) {
+                            float* o = p.y + (int64_t)mi * p.ldy + n_idx;
+                            const float val = __uint_as_float(acc[i]);
+                            if (whole && !p.accumulate) *o = val;
+                            else atomicAdd(o, val);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_empty);
+            ++seg;
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kDequantWarps + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int kMB>
+void launch(const CUtensorMap& wm, const CUtensorMap& xm, const GemmParams& p, cudaStream_t st) {
+    auto kern = qmatmul_q4k_tc_kernel<kMB>;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kMB>::kTotal); attr = true; }
+    const int64_t total = (int64_t)p.n_tiles * p.nsb;
+    int grid = sm_count();
+    if (total < grid) grid = (int)total;
+    kern<<<grid, kThreads, Cfg<kMB>::kTotal, st>>>(wm, xm, p);
+    count_launch();
+}
+
+}  // namespace
+
+bool qmatmul_tc_supported(int m, int n, int k, int ggml_type) {
+    return ggml_type == B200_GGML_Q4_K && m >= 1 && m <= 64 && k % 256 == 0 && k >= 256 && n >= 1 &&
+           ((int64_t)(k / 256) * 144) % 16 == 0;
+}
+
+// true when some output tile is produced by more than one CTA (or accumulate): y must then hold the
+// addend (zeros for a plain product) before the launch
+bool qmatmul_tc_needs_zeroed_output(int n, int k) {
+    const int64_t n_tiles = (n + kTileN - 1) / kTileN, nsb = k / 256, total = n_tiles * nsb;
+    const int64_t grid = total < sm_count() ? total : sm_count();
+    for (int64_t c = 1; c < grid; ++c)
+        if ((total * c / grid) % nsb != 0) return true;
+    return false;
+}
+
+void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
+                int accumulate, cudaStream_t st) {
+    (void)ggml_type;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error(kErrCuda, "qmatmul: cuTensorMapEncodeTiled unavailable"); return; }
+    if (((uintptr_t)w & 15) || ((uintptr_t)x_f16 & 15)) { set_error(kErrBadArg, "qmatmul: w and x must be 16-byte aligned"); return; }
+    const int nsb = k / 256;
+    const int mb = m <= 32 ? 32 : 64;
+    CUtensorMap wm, xm;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)nsb * 144, (cuuint64_t)n};
+        const cuuint64_t strides[1] = {(cuuint64_t)nsb * 144};
+        const cuuint32_t box[2] = {144, (cuuint32_t)kTileN};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&wm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: weight tensor map failed (%d)", (int)r); return; }
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
+        const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+        const cuuint32_t box[2] = {64, (cuuint32_t)mb};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return; }
+    }
+    GemmParams p{y, ldy, m, n, nsb, (n + kTileN - 1) / kTileN, accumulate};
+    if (mb == 32) launch<32>(wm, xm, p, st); else launch<64>(wm, xm, p, st);
+    check_launch("qmatmul_tc");
+}
+
 }  // namespace b200

@@ -36,7 +36,12 @@ int         b200_device_sm_count(void);
 int         b200_device_cc(void);
 
 /* data-type tags used by the entry points below */
-enum { B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2, B200_U8 = 3, B200_FP8_E4M3 = 4 };
+enum { B200_F32 = 0, B200_F16 = 1, B200_BF16 = 2, B200_U8 = 3, B200_FP8_E4M3 = 4,
+       /* fp16 in "K4" order: within every aligned group of 4 elements along the last dimension the middle
+        * two are swapped ([k0,k2,k1,k3]).  This is the activation layout the tcgen05 dequant-GEMM consumes
+        * (it matches the order in which two nibbles fall out of one 32-bit word of a GGML block, so the
+        * weights never need a byte permute); rms_norm / silu_mul / cast / paged_attention_decode can emit it. */
+       B200_F16_K4 = 5 };
 /* GGML tensor types (values = ggml_type, as stored in GGUF files) */
 enum { B200_GGML_Q8_0 = 8, B200_GGML_Q4_K = 12, B200_GGML_Q6_K = 14 };
 /* KV layouts (/root/reference/src/scheduler/cache_engine.rs:298-341) */
@@ -123,7 +128,8 @@ size_t qmatmul_workspace_bytes(int32_t m, int32_t n, int32_t k);
 void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, int32_t k,
                  int32_t ggml_type, int32_t accumulate, void* workspace, size_t workspace_bytes,
                  int64_t stream);
-/* same with activations already in fp16 [m,k] (what the fused decode layer feeds) */
+/* same with activations already in fp16 [m,k] in B200_F16_K4 order (what the fused decode layer feeds).
+ * When accumulate == 0 and the product is split over K, y is zero-filled first (contiguous y only). */
 void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32_t n, int32_t k,
                     int32_t ggml_type, int32_t accumulate, int64_t stream);
 /* QTensor::dequantize: W -> f32 [n,k] (linear.rs:808-842 forward_via_dequant) */

@@ -48,7 +48,10 @@ def test_decode_steps_match_oracle(use_graph):
         scale = np.abs(ref).max()
         err = np.abs(logits - ref).max() / scale
         assert err < 1e-3, (step, err)
-        assert np.array_equal(nxt, ref.argmax(axis=1)) or err < 1e-4          # greedy tokens agree
+        # greedy tokens agree wherever the oracle's top-1 margin exceeds the logit error bound
+        for b in range(B):
+            if nxt[b] != ref[b].argmax():
+                assert ref[b].max() - ref[b, nxt[b]] <= 2 * err * scale, (step, b)
         # the engine wrote this step's K/V into the paged cache exactly where the oracle did
         for l in range(cfg.num_layers):
             assert np.abs(eng.gpu_cache[l][0].float().cpu().numpy() - okc[l]).max() < 2e-2
