@@ -5,35 +5,66 @@
 // (layers/rotary_emb.rs:52-69, interleaved = rope_i for GGUF llama quantized_llama.rs:313-318),
 // silu(w1 x) * (w3 x) (quantized_llama.rs:32-37), to_dtype casts (layers/attention.rs:971-975),
 // tok_embeddings lookup (quantized_llama.rs:449), argmax sampling (pipeline.rs:2338).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
 
-// ---- rms_norm: one CTA per row, row cached in registers (n <= 8 * 1024 with 256 threads x 4 x float4...)
+// ---- rms_norm: one CTA per row; the row stays in registers (float4 per thread per 1024 columns) ----
+template <typename TOut, bool kK4>
+__device__ __forceinline__ void store4(TOut* o, int i, float a, float b, float c, float d) {
+    // K4 order swaps the middle two of every aligned group of four
+    if constexpr (kK4) { const float t = b; b = c; c = t; }
+    if constexpr (sizeof(TOut) == 2) {
+        uint2 v;
+        if constexpr (std::is_same<TOut, __half>::value) {
+            __half2 p0 = __halves2half2(from_f32<__half>(a), from_f32<__half>(b)), p1 = __halves2half2(from_f32<__half>(c), from_f32<__half>(d));
+            v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+            v.x = *reinterpret_cast<uint32_t*>(&p0); v.y = *reinterpret_cast<uint32_t*>(&p1);
+        }
+        *reinterpret_cast<uint2*>(o + i) = v;
+    } else {
+        *reinterpret_cast<float4*>(o + i) = make_float4(a, b, c, d);
+    }
+}
+
 template <typename TOut, bool kK4 = false>
 __global__ void __launch_bounds__(256)
 rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, TOut* __restrict__ out, int n, float eps) {
+    constexpr int kMaxIt = 8;                             // rows up to 8192 columns stay in registers
     const int row = blockIdx.x;
-    const float* xr = x + (int64_t)row * n;
+    const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * n);
+    const float4* wr = reinterpret_cast<const float4*>(w);
+    const int nv = n >> 2;
     __shared__ float red[8];
+    float4 v[kMaxIt];
     float ss = 0.f;
-    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) {
-        if (i + 3 < n) {
-            const float4 v = *reinterpret_cast<const float4*>(xr + i);
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        } else {
-            for (int j = i; j < n; ++j) ss += xr[j] * xr[j];
-        }
+#pragma unroll
+    for (int it = 0; it < kMaxIt; ++it) {
+        const int i = threadIdx.x + it * 256;
+        if (i < nv) { v[it] = xr[i]; ss += v[it].x * v[it].x + v[it].y * v[it].y + v[it].z * v[it].z + v[it].w * v[it].w; }
     }
+    for (int i = threadIdx.x + kMaxIt * 256; i < nv; i += 256) { const float4 t = xr[i]; ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w; }
     ss = warp_sum(ss);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += (i < (int)(blockDim.x >> 5)) ? red[i] : 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
     const float sc = rsqrtf(tot / (float)n + eps);
     TOut* o = out + (int64_t)row * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) o[kK4 ? k4_index(i) : i] = from_f32<TOut>(xr[i] * sc * w[i]);
+#pragma unroll
+    for (int it = 0; it < kMaxIt; ++it) {
+        const int i = threadIdx.x + it * 256;
+        if (i < nv) { const float4 g = __ldg(wr + i); store4<TOut, kK4>(o, 4 * i, v[it].x * sc * g.x, v[it].y * sc * g.y, v[it].z * sc * g.z, v[it].w * sc * g.w); }
+    }
+    for (int i = threadIdx.x + kMaxIt * 256; i < nv; i += 256) {
+        const float4 t = xr[i], g = __ldg(wr + i);
+        store4<TOut, kK4>(o, 4 * i, t.x * sc * g.x, t.y * sc * g.y, t.z * sc * g.z, t.w * sc * g.w);
+    }
 }
 
 // ---- RoPE in place on f32 q,k --------------------------------------------------------------
@@ -187,7 +218,8 @@ void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int3
               int32_t out_dtype, int64_t stream) {
     if (rows == 0) return;
     B200_REQUIRE(x && weight && out && rows > 0 && n > 0, kErrBadArg, "rms_norm: bad arguments");
-    B200_REQUIRE(((uintptr_t)x & 15) == 0 && n % 4 == 0, kErrBadArg, "rms_norm: x must be 16-byte aligned, n %% 4 == 0");
+    B200_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)weight & 15) == 0 && ((uintptr_t)out & 15) == 0 && n % 4 == 0, kErrBadArg,
+                 "rms_norm: x, weight, out must be 16-byte aligned and n %% 4 == 0");
     if (out_dtype == B200_F32) rms_norm_kernel<float><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (float*)out, n, eps);
     else if (out_dtype == B200_F16) rms_norm_kernel<__half><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);
     else if (out_dtype == B200_F16_K4) rms_norm_kernel<__half, true><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);

@@ -99,9 +99,12 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
         const b200_llama_layer& w = m->layers[l];
         rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
         // QKV / gate / up accumulate (split-K) into buffers that their consumers leave zeroed
-        qmatmul_dispatch(m->xn, w.wq, m->qkv, m->qkv_row, B, qd, H, w.tq, 1, st);
-        qmatmul_dispatch(m->xn, w.wk, m->qkv + qd, m->qkv_row, B, kd, H, w.tk, 1, st);
-        qmatmul_dispatch(m->xn, w.wv, m->qkv + qd + kd, m->qkv_row, B, kd, H, w.tv, 1, st);
+        {   // fused QKV: three weight matrices, one launch
+            const void* ws[3] = {w.wq, w.wk, w.wv};
+            const int ts[3] = {w.tq, w.tk, w.tv}, ns[3] = {qd, kd, kd};
+            float* ys[3] = {m->qkv, m->qkv + qd, m->qkv + qd + kd};
+            qmatmul_dispatch_multi(m->xn, 3, ws, ts, ys, ns, m->qkv_row, B, H, 1, st);
+        }
         // (also re-zeroes qkv: the split-K GEMMs accumulate into it)
         rope_and_cache_impl(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
                             m->heads_l, m->kv_l, hd, /*interleaved=*/1, B200_BF16, c.kv_dtype, /*zero_src=*/true, s);
@@ -118,8 +121,12 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
         rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
-        qmatmul_dispatch(m->xn, w.w1, m->gate, m->ffn_l, B, m->ffn_l, H, w.t1, 1, st);
-        qmatmul_dispatch(m->xn, w.w3, m->up, m->ffn_l, B, m->ffn_l, H, w.t3, 1, st);
+        {   // fused gate | up
+            const void* ws[2] = {w.w1, w.w3};
+            const int ts[2] = {w.t1, w.t3}, ns[2] = {m->ffn_l, m->ffn_l};
+            float* ys[2] = {m->gate, m->up};
+            qmatmul_dispatch_multi(m->xn, 2, ws, ts, ys, ns, m->ffn_l, B, H, 1, st);
+        }
         silu_mul_zero_src(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, s);      // act = silu(gate)*up; gate/up re-zeroed
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->act16, w.w2, m->x, H, B, H, m->ffn_l, w.t2, 1, st);     // x += w2(act)

@@ -22,6 +22,12 @@ void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
                 int accumulate, cudaStream_t st);
 
+// several weight matrices (same type / k) on one activation in one launch; falls back to separate launches
+void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
+                      int ggml_type, int accumulate, cudaStream_t st);
+void qmatmul_dispatch_multi(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
+                            int64_t ldy, int m, int k, int accumulate, cudaStream_t st);
+
 // picks tc or generic; y row stride ldy (elements)
 void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k,
                       int ggml_type, int accumulate, cudaStream_t st);

@@ -99,6 +99,14 @@ void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, i
     else qmatmul_generic(x_f16, true, w, y, ldy, m, n, k, ggml_type, accumulate, st);
 }
 
+void qmatmul_dispatch_multi(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
+                            int64_t ldy, int m, int k, int accumulate, cudaStream_t st) {
+    bool fuse = nseg >= 1 && nseg <= 3;
+    for (int i = 0; i < nseg && fuse; ++i) fuse = types[i] == types[0] && qmatmul_tc_supported(m, n[i], k, types[i]);
+    if (fuse) { qmatmul_tc_multi(x_f16, nseg, w, y, n, ldy, m, k, types[0], accumulate, st); return; }
+    for (int i = 0; i < nseg; ++i) qmatmul_dispatch(x_f16, w[i], y[i], ldy, m, n[i], k, types[i], accumulate, st);
+}
+
 }  // namespace b200
 
 using namespace b200;

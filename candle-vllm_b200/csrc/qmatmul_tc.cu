@@ -1,4 +1,4 @@
-// qmatmul_tc.cu -- tcgen05 dequant-GEMM for GGML Q4_K weights at decode batch sizes (m <= 64).
+// qmatmul_tc.cu -- tcgen05 dequant-GEMM for GGML Q4_K / Q6_K weights at decode batch sizes (m <= 64).
 //
 //   y[m, n] (+)= sum_k x[m, k] * dequant(W)[n, k]        W = verbatim GGUF Q4_K blocks, row-major over n
 //
@@ -37,19 +37,23 @@ constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
 constexpr int kSB = 256;             // weights per super-block
 constexpr int kDequantWarps = 8;
 constexpr int kThreads = (kDequantWarps + 2) * 32;
-constexpr int kWBytes = kTileN * 144;                   // 18432
 constexpr int kXSubBytes = 64 * 2;                      // 128-byte swizzled row
 constexpr int kColD = 0, kColA0 = 128, kColA1 = 256;    // TMEM columns (512 allocated)
 
-template <int kMB>   // batch rows padded to kMB (32 or 64) = UMMA N
+template <int kMB, int kType>   // batch rows padded to kMB (32 or 64) = UMMA N; GGML type of W
 struct Cfg {
-    static constexpr int kStages = kMB == 32 ? 6 : 4;          // 34 KB / 50 KB per stage
+    // bytes of one super-block as staged in shared memory: Q4_K 144; Q6_K a 240-byte window that starts at the
+    // 210-byte block's address rounded down to 16 (TMA box starts must be 16-byte aligned)
+    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : 240;
+    static constexpr int kBlkGlobal = kType == B200_GGML_Q4_K ? 144 : 210;
+    static constexpr int kWBytes = kTileN * kBlk;
+    static constexpr int kStages = kMB == 32 ? (kType == B200_GGML_Q4_K ? 6 : 4) : (kType == B200_GGML_Q4_K ? 4 : 3);
     static constexpr int kXBytes = 4 * kMB * kXSubBytes;        // 4 sub-tiles of [kMB][64] fp16
-    static constexpr int kStageBytes = kXBytes + kWBytes;       // X first (1024-aligned), then W
+    static constexpr int kStageBytes = (kXBytes + kWBytes + 1023) / 1024 * 1024;   // X first (1024-aligned), then W
     static constexpr int kBars = kStages * kStageBytes;         // full[kStages] empty[kStages] a_ready[2] a_free[2] d_full d_empty
     static constexpr int kTmemSlot = kBars + (2 * kStages + 6) * 8;
     static constexpr int kTotal = kTmemSlot + 16;
-    static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
+    static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
@@ -106,6 +110,13 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
         "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -126,13 +137,17 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
     return d;
 }
 
+constexpr int kMaxSeg = 3;           // weight matrices sharing one activation (fused QKV, gate|up) in one launch
 struct GemmParams {
-    float* y;
+    float* y[kMaxSeg];             // output base of each segment (row stride ldy)
+    int n[kMaxSeg];                // rows of each weight matrix
+    int tile_end[kMaxSeg];         // cumulative 128-row tile count
     int64_t ldy;
-    int m, n, nsb;                 // nsb = k / 256
-    int n_tiles;
+    int m, nsb;                    // nsb = k / 256
+    int n_tiles;                   // tiles over all segments
     int accumulate;
 };
+__device__ __forceinline__ int seg_of_tile(const GemmParams& p, int tile) { return (tile >= p.tile_end[0]) + (tile >= p.tile_end[1]); }
 
 // 6-bit scale / min of sub-block J from the 12 packed bytes held in three 32-bit words (ggml get_scale_min_k4)
 template <int J>
@@ -144,49 +159,158 @@ __device__ __forceinline__ void scale_min(uint32_t s0, uint32_t s1, uint32_t s2,
 
 // Dequantise sub-blocks 4*kHf .. 4*kHf+3 (128 weights) of this thread's Q4_K block into fp16 and store
 // them to 64 TMEM columns (two weights per 32-bit column; K4 order inside each group of four).
+// Fast path: the nibble is dropped into fp16 mantissa bits 6-9 (a subnormal = q * 2^-18) and ONE HFMA2 with
+// (d*sc*2^18, -dmin*m) yields d*sc*q - dmin*m with a single rounding.  It needs d*sc*2^18 <= 65504
+// (sub-block scale < 0.25, i.e. weight range < 3.75 -- always true for LLM weights); otherwise the
+// exact two-step path (1024+q magic, HSUB2, HFMA2) is taken for that row.
 template <int kHf>
-__device__ __forceinline__ void dequant_half(const uint8_t* blk, uint32_t a_col) {
+__device__ __forceinline__ void dequant_q4k_half(const uint8_t* blk, uint32_t a_col) {
     const uint4 hdr = *reinterpret_cast<const uint4*>(blk);              // d | dmin | scales[12]
     const __half2 dd = *reinterpret_cast<const __half2*>(&hdr.x);
-    const float d = __low2float(dd) * 262144.f;                          // 2^18 undoes the subnormal placement of the nibble
+    const float d = __low2float(dd);
     const float dmin = -__high2float(dd);
+    // warp-uniform so that the .aligned tcgen05.st below is reached convergently
+    const bool fast = __all_sync(0xffffffffu, fabsf(d) * 63.f * 262144.f <= 65504.f);
+    const float dk = fast ? d * 262144.f : d;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
-        constexpr int dummy = 0; (void)dummy;
         int sc_lo, m_lo, sc_hi, m_hi;
         if (cc == 0) { scale_min<4 * kHf>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo); scale_min<4 * kHf + 1>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi); }
         else { scale_min<4 * kHf + 2>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo); scale_min<4 * kHf + 3>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi); }
-        const __half2 s_lo = __float2half2_rn(fminf(d * (float)sc_lo, 65504.f));
-        const __half2 s_hi = __float2half2_rn(fminf(d * (float)sc_hi, 65504.f));
+        const __half2 s_lo = __float2half2_rn(dk * (float)sc_lo), s_hi = __float2half2_rn(dk * (float)sc_hi);
         const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
         const int c = 2 * kHf + cc;                                      // 32-byte chunk of qs: sub-blocks 2c (lo nibbles), 2c+1 (hi)
         const uint4 qa = *reinterpret_cast<const uint4*>(blk + 16 + c * 32);
         const uint4 qb = *reinterpret_cast<const uint4*>(blk + 32 + c * 32);
         const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
         uint32_t v[32];
+        if (fast) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t x = w[i];
-            uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
-            uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
-            const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
-            const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
-            const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
-            const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
-            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
-            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
-            v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
-            v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = w[i];
+                uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
+                uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
+                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
+                const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
+                const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
+                const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+                v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            }
+        } else {
+            const uint32_t magic = 0x64006400u;                          // half2(1024, 1024): (q | 0x6400) = 1024 + q exactly
+            const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = w[i];
+                uint32_t t0 = (x & 0x000f000fu) | magic, t1 = ((x >> 8) & 0x000f000fu) | magic;
+                uint32_t t2 = ((x >> 4) & 0x000f000fu) | magic, t3 = ((x >> 12) & 0x000f000fu) | magic;
+                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), s_lo, n_lo);
+                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), s_lo, n_lo);
+                const __half2 r2 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t2), k1024), s_hi, n_hi);
+                const __half2 r3 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t3), k1024), s_hi, n_hi);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+                v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            }
         }
         tc_st32(a_col + cc * 32, v);
     }
 }
 
+// Q6_K staging.  A block = ql[128] | qh[64] | scales i8[16] | d f16 = 210 bytes and is only 2-byte aligned
+// in memory, while a TMA box must START 16-byte aligned (probed on B200: an unaligned start raises "illegal
+// instruction", tools/probes/tma_align_test.cu).  So the box starts at the block address rounded down to 16
+// and is 240 bytes wide (15 x 16: an odd number of 16-byte units per row keeps LDS.128 conflict-free); the
+// block then sits off = (210 * sb) % 16 bytes into the row slot, off in {0, 2, .., 14}, uniform per stage.
+// Each thread loads its slot with aligned LDS.128 and realigns the words it needs in registers:
+// word select by off/4 (two SEL levels) and a 16-bit funnel shift when off % 4 == 2 -- one code path.
+template <int kJ0, int kN>
+__device__ __forceinline__ void realign(const uint32_t (&t)[57], int wo, int sh16, uint32_t (&out)[kN]) {
+    uint32_t s1[kN + 3], s2[kN + 1];
+#pragma unroll
+    for (int i = 0; i < kN + 3; ++i) s1[i] = (wo & 1) ? t[kJ0 + i + 1] : t[kJ0 + i];
+#pragma unroll
+    for (int i = 0; i < kN + 1; ++i) s2[i] = (wo & 2) ? s1[i + 2] : s1[i];
+#pragma unroll
+    for (int i = 0; i < kN; ++i) out[i] = __funnelshift_r(s2[i], s2[i + 1], sh16);
+}
+
+// This thread's row, half kHf of the super-block (128 weights = 4 groups of 32): group g weight l is
+// ((ql[64 kHf + 32 (g&1) + l] nibble (g>>1)) | ((qh[32 kHf + l] >> 2g) & 3) << 4) - 32, times d*scales[8 kHf + 2g + l/16].
+// The 6-bit value goes to fp16 mantissa bits 4-9 (= q * 2^-20); one HFMA2 with (s*2^20, -32 s) finishes it
+// (exact path with the 1024+q magic when s*2^20 would overflow fp16).
+template <int kGp>      // kGp = 0: groups 0 (lo nibble) and 2 (hi nibble) from ql[0..31]; kGp = 1: groups 1, 3
+__device__ __forceinline__ void dequant_q6k_pair(const uint32_t (&ql)[8], uint32_t a_col, const uint32_t (&qh)[8],
+                                                 const uint32_t (&scw)[2], float dk, bool fast) {
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+        const int g = kGp + 2 * hi;             // group index 0..3 within the half
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int sidx = 2 * g + (i >> 2);                                  // scale index within this half
+            const int sc = (int)(int8_t)(((sidx < 4 ? scw[0] : scw[1]) >> (8 * (sidx & 3))) & 0xff);
+            const float s = dk * (float)sc;
+            const uint32_t lw = hi ? (ql[i] >> 4) : ql[i];                      // nibbles now at bits 0-3 of every byte
+            const uint32_t hw = qh[i] >> (2 * g);                               // 2 high bits now at bits 0-1 of every byte
+            const __half2 sh = __float2half2_rn(s);
+            if (fast) {
+                const __half2 nh = __float2half2_rn(-32.f * (__low2float(sh) * (1.f / 1048576.f)));   // q = 32 -> exactly 0
+                uint32_t t0 = ((lw << 4) & 0x00f000f0u) | ((hw << 8) & 0x03000300u);    // bytes (0,2)
+                uint32_t t1 = ((lw >> 4) & 0x00f000f0u) | (hw & 0x03000300u);           // bytes (1,3)
+                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), sh, nh);
+                const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), sh, nh);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+            } else {
+                const __half2 nh = __float2half2_rn(-32.f * __low2float(sh));
+                const uint32_t magic = 0x64006400u;
+                const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+                uint32_t t0 = (lw & 0x000f000fu) | ((hw << 4) & 0x00300030u) | magic;
+                uint32_t t1 = ((lw >> 8) & 0x000f000fu) | ((hw >> 4) & 0x00300030u) | magic;
+                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), sh, nh);
+                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), sh, nh);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+            }
+        }
+        tc_st16(a_col + g * 16, v);
+    }
+}
+
+template <int kHf>
+__device__ __forceinline__ void dequant_q6k_half(const uint8_t* slot, int off, uint32_t a_col) {
+    uint32_t t[57];
+#pragma unroll
+    for (int c = 0; c < 14; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(slot + 16 * c);
+        t[4 * c] = v.x; t[4 * c + 1] = v.y; t[4 * c + 2] = v.z; t[4 * c + 3] = v.w;
+    }
+    t[56] = 0u;
+    const int wo = off >> 2, sh16 = (off & 2) * 8;
+    uint32_t dw[1], scw[2], qh[8], ql[8];
+    realign<52, 1>(t, wo, sh16, dw);                                              // d (f16) in the low half of dw[0]
+    const float d = __half2float(__ushort_as_half((unsigned short)(dw[0] & 0xffffu)));
+    realign<48 + 2 * kHf, 2>(t, wo, sh16, scw);                                   // 8 int8 scales of this half
+    realign<32 + 8 * kHf, 8>(t, wo, sh16, qh);
+    const bool fast = __all_sync(0xffffffffu, fabsf(d) * 128.f * 1048576.f <= 65504.f);   // warp-uniform (see Q4_K)
+    const float dk = fast ? d * 1048576.f : d;
+    realign<16 * kHf, 8>(t, wo, sh16, ql);
+    dequant_q6k_pair<0>(ql, a_col, qh, scw, dk, fast);
+    realign<16 * kHf + 8, 8>(t, wo, sh16, ql);
+    dequant_q6k_pair<1>(ql, a_col, qh, scw, dk, fast);
+}
+
 // =================================================================================================
-template <int kMB>
+template <int kMB, int kType>
 __global__ void __launch_bounds__(kThreads, 1)
-qmatmul_q4k_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
-    using C = Cfg<kMB>;
+qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_constant__ CUtensorMap wmap1,
+                  const __grid_constant__ CUtensorMap wmap2, const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
+    using C = Cfg<kMB, kType>;
     constexpr int kStages = C::kStages;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,11 +355,16 @@ qmatmul_q4k_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
                 const int s = it % kStages;
                 mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-                mbar_expect_tx(full_bar(s), C::kStageBytes);
+                mbar_expect_tx(full_bar(s), C::kXBytes + C::kWBytes);
                 const uint32_t dst = smem_base + s * C::kStageBytes;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, full_bar(s), sb * kSB + q * 64, 0, pol_x);
-                tma_load_2d(dst + C::kXBytes, &wmap, full_bar(s), sb * 144, tile * kTileN, pol_w);
+                // W box start (bytes): Q4_K blocks are 144 B (16-aligned); Q6_K blocks (210 B) start at the block address
+                // rounded down to 16 -- TMA box starts must be 16-byte aligned
+                const int sg = seg_of_tile(p, tile);
+                const CUtensorMap* wm = sg == 0 ? &wmap0 : (sg == 1 ? &wmap1 : &wmap2);
+                const int ltile = tile - (sg ? p.tile_end[sg - 1] : 0);
+                tma_load_2d(dst + C::kXBytes, wm, full_bar(s), kType == B200_GGML_Q4_K ? sb * 144 : ((sb * 210) & ~15), ltile * kTileN, pol_w);
             }
         }
     } else if (warp == kDequantWarps + 1) {
@@ -286,9 +415,14 @@ qmatmul_q4k_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
                 mbar_wait(full_bar(s), (it / kStages) & 1);
                 mbar_wait(a_free(ab), ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint8_t* blk = smem + s * C::kStageBytes + C::kXBytes + row * 144;
+                const uint8_t* blk = smem + s * C::kStageBytes + C::kXBytes + row * C::kBlk;
                 const uint32_t a_col = tmem + (ab ? kColA1 : kColA0) + lane_addr + hf * 64;
-                if (hf == 0) dequant_half<0>(blk, a_col); else dequant_half<1>(blk, a_col);
+                if constexpr (kType == B200_GGML_Q4_K) {
+                    if (hf == 0) dequant_q4k_half<0>(blk, a_col); else dequant_q4k_half<1>(blk, a_col);
+                } else {
+                    const int off = ((int)(u - tile_begin) * 210) & 15;        // block offset inside the 16-byte aligned window
+                    if (hf == 0) dequant_q6k_half<0>(blk, off, a_col); else dequant_q6k_half<1>(blk, off, a_col);
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
@@ -298,19 +432,22 @@ qmatmul_q4k_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_con
             mbar_wait(d_full, seg & 1);
             tc_fence_after();
             const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
-            const int n_idx = tile * kTileN + row;
+            const int sg = seg_of_tile(p, tile);
+            const int n_idx = (tile - (sg ? p.tile_end[sg - 1] : 0)) * kTileN + row;
+            float* const ybase = p.y[sg];
+            const int n_rows = p.n[sg];
             constexpr int kColsPerHalf = kMB / 2;                 // this warp's share of the batch columns
 #pragma unroll
             for (int c0 = 0; c0 < kColsPerHalf; c0 += 16) {
                 uint32_t acc[16];
                 tc_ld16(tmem + kColD + lane_addr + hf * kColsPerHalf + c0, acc);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (n_idx < p.n) {
+                if (n_idx < n_rows) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int mi = hf * kColsPerHalf + c0 + i;
                         if (mi < p.m) {
-                            float* o = p.y + (int64_t)mi * p.ldy + n_idx;
+                            float* o = ybase + (int64_t)mi * p.ldy + n_idx;
                             const float val = __uint_as_float(acc[i]);
                             if (whole && !p.accumulate) *o = val;
                             else atomicAdd(o, val);
@@ -349,23 +486,39 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int kMB>
-void launch(const CUtensorMap& wm, const CUtensorMap& xm, const GemmParams& p, cudaStream_t st) {
-    auto kern = qmatmul_q4k_tc_kernel<kMB>;
+template <int kMB, int kType>
+void launch(const CUtensorMap* wm, const CUtensorMap& xm, const GemmParams& p, cudaStream_t st) {
+    auto kern = qmatmul_tc_kernel<kMB, kType>;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kMB>::kTotal); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kMB, kType>::kTotal); attr = true; }
     const int64_t total = (int64_t)p.n_tiles * p.nsb;
     int grid = sm_count();
     if (total < grid) grid = (int)total;
-    kern<<<grid, kThreads, Cfg<kMB>::kTotal, st>>>(wm, xm, p);
+    kern<<<grid, kThreads, Cfg<kMB, kType>::kTotal, st>>>(wm[0], wm[1], wm[2], xm, p);
     count_launch();
+}
+
+bool make_w_map(CUtensorMap* wm, const void* w, int n, int nsb, int ggml_type) {
+    EncodeTiledFn enc = encode_fn();
+    const bool q4 = ggml_type == B200_GGML_Q4_K;
+    // byte tensor [n][nsb * block]; box {144, 128} (Q4_K) or {240, 128} (Q6_K: 210-byte block + alignment slack)
+    const cuuint64_t dims[2] = {(cuuint64_t)nsb * (q4 ? 144 : 210), (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)nsb * (q4 ? 144 : 210)};
+    const cuuint32_t box[2] = {(cuuint32_t)(q4 ? 144 : 240), (cuuint32_t)kTileN};
+    const cuuint32_t es[2] = {1, 1};
+    const CUresult r = enc(wm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: weight tensor map failed (%d)", (int)r); return false; }
+    return true;
 }
 
 }  // namespace
 
 bool qmatmul_tc_supported(int m, int n, int k, int ggml_type) {
-    return ggml_type == B200_GGML_Q4_K && m >= 1 && m <= 64 && k % 256 == 0 && k >= 256 && n >= 1 &&
-           ((int64_t)(k / 256) * 144) % 16 == 0;
+    if (m < 1 || m > 64 || n < 1 || k < 256 || k % 256) return false;
+    if (ggml_type == B200_GGML_Q4_K) return true;                         // row pitch (k/256)*144 is always a multiple of 16
+    if (ggml_type == B200_GGML_Q6_K) return ((int64_t)(k / 256) * 210) % 16 == 0;   // TMA row pitch: k % 2048 == 0
+    return false;
 }
 
 // true when some output tile is produced by more than one CTA (or accumulate): y must then hold the
@@ -378,23 +531,24 @@ bool qmatmul_tc_needs_zeroed_output(int n, int k) {
     return false;
 }
 
-void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
-                int accumulate, cudaStream_t st) {
-    (void)ggml_type;
+// up to kMaxSeg weight matrices (same type, same k) applied to one activation in one launch
+void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
+                      int ggml_type, int accumulate, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) { set_error(kErrCuda, "qmatmul: cuTensorMapEncodeTiled unavailable"); return; }
-    if (((uintptr_t)w & 15) || ((uintptr_t)x_f16 & 15)) { set_error(kErrBadArg, "qmatmul: w and x must be 16-byte aligned"); return; }
+    if (nseg < 1 || nseg > kMaxSeg) { set_error(kErrBadArg, "qmatmul: %d segments (max %d)", nseg, kMaxSeg); return; }
+    if ((uintptr_t)x_f16 & 15) { set_error(kErrBadArg, "qmatmul: x must be 16-byte aligned"); return; }
     const int nsb = k / 256;
     const int mb = m <= 32 ? 32 : 64;
-    CUtensorMap wm, xm;
-    {
-        const cuuint64_t dims[2] = {(cuuint64_t)nsb * 144, (cuuint64_t)n};
-        const cuuint64_t strides[1] = {(cuuint64_t)nsb * 144};
-        const cuuint32_t box[2] = {144, (cuuint32_t)kTileN};
-        const cuuint32_t es[2] = {1, 1};
-        CUresult r = enc(&wm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: weight tensor map failed (%d)", (int)r); return; }
+    CUtensorMap wm[kMaxSeg], xm;
+    GemmParams p{};
+    int tiles = 0;
+    for (int i = 0; i < kMaxSeg; ++i) {
+        const int j = i < nseg ? i : nseg - 1;               // unused slots alias the last segment
+        if ((uintptr_t)w[j] & 15) { set_error(kErrBadArg, "qmatmul: w must be 16-byte aligned"); return; }
+        if (!make_w_map(&wm[i], w[j], n[j], nsb, ggml_type)) return;
+        if (i < nseg) tiles += (n[i] + kTileN - 1) / kTileN;
+        p.y[i] = y[j]; p.n[i] = n[j]; p.tile_end[i] = i < nseg ? tiles : 0x7fffffff;
     }
     {
         const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
@@ -406,9 +560,15 @@ void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return; }
     }
-    GemmParams p{y, ldy, m, n, nsb, (n + kTileN - 1) / kTileN, accumulate};
-    if (mb == 32) launch<32>(wm, xm, p, st); else launch<64>(wm, xm, p, st);
+    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
+    if (ggml_type == B200_GGML_Q4_K) { if (mb == 32) launch<32, B200_GGML_Q4_K>(wm, xm, p, st); else launch<64, B200_GGML_Q4_K>(wm, xm, p, st); }
+    else { if (mb == 32) launch<32, B200_GGML_Q6_K>(wm, xm, p, st); else launch<64, B200_GGML_Q6_K>(wm, xm, p, st); }
     check_launch("qmatmul_tc");
+}
+
+void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
+                int accumulate, cudaStream_t st) {
+    qmatmul_tc_multi(x_f16, 1, &w, &y, &n, ldy, m, k, ggml_type, accumulate, st);
 }
 
 }  // namespace b200
