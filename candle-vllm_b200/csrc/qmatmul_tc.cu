@@ -27,6 +27,8 @@
 // dp4a; here activations are fp16 and accumulation fp32 (strictly closer to the fp32 target).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "qmatmul.cuh"
 
 namespace b200 {
@@ -35,23 +37,27 @@ namespace {
 
 constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
 constexpr int kSB = 256;             // weights per super-block
-constexpr int kDequantWarps = 8;
+constexpr int kDequantWarps = 16;     // 4 TMEM lane quadrants x 4 quarters of a super-block (64 weights per thread per unit)
 constexpr int kThreads = (kDequantWarps + 2) * 32;
 constexpr int kXSubBytes = 64 * 2;                      // 128-byte swizzled row
-constexpr int kColD = 0, kColA0 = 128, kColA1 = 256;    // TMEM columns (512 allocated)
+constexpr int kColD = 0, kColA = 128, kABufs = 3;        // TMEM columns (512 allocated): D accumulators [0,128), 3 A buffers of 128
 
 template <int kMB, int kType>   // batch rows padded to kMB (32 or 64) = UMMA N; GGML type of W
 struct Cfg {
     // bytes of one super-block as staged in shared memory: Q4_K 144; Q6_K a 240-byte window that starts at the
     // 210-byte block's address rounded down to 16 (TMA box starts must be 16-byte aligned)
+    // Independent accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on the accumulate
+    // dependency (~150 cycles each at N = 32, measured as a_free stalls); k-step ks goes to D[ks % kAcc] and the
+    // epilogue adds them up.  kAcc * kMB = 128 TMEM columns.
+    static constexpr int kAcc = 128 / kMB;
     static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : 240;
     static constexpr int kBlkGlobal = kType == B200_GGML_Q4_K ? 144 : 210;
     static constexpr int kWBytes = kTileN * kBlk;
     static constexpr int kStages = kMB == 32 ? (kType == B200_GGML_Q4_K ? 6 : 4) : (kType == B200_GGML_Q4_K ? 4 : 3);
     static constexpr int kXBytes = 4 * kMB * kXSubBytes;        // 4 sub-tiles of [kMB][64] fp16
     static constexpr int kStageBytes = (kXBytes + kWBytes + 1023) / 1024 * 1024;   // X first (1024-aligned), then W
-    static constexpr int kBars = kStages * kStageBytes;         // full[kStages] empty[kStages] a_ready[2] a_free[2] d_full d_empty
-    static constexpr int kTmemSlot = kBars + (2 * kStages + 6) * 8;
+    static constexpr int kBars = kStages * kStageBytes;         // full[kStages] empty[kStages] a_ready[3] a_free[3] d_full d_empty
+    static constexpr int kTmemSlot = kBars + (2 * kStages + 8) * 8;
     static constexpr int kTotal = kTmemSlot + 16;
     static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
@@ -85,6 +91,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// one elected lane of a converged warp (warp-uniform predicate source for the single-thread tcgen05 / TMA issue)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -117,6 +129,12 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
         "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -146,8 +164,12 @@ struct GemmParams {
     int m, nsb;                    // nsb = k / 256
     int n_tiles;                   // tiles over all segments
     int accumulate;
+    long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
+    int debug;                     // profiling aid (B200_GEMM_DEBUG): 1 = skip MMA issue, 2 = skip dequant, 4 = skip epilogue stores
 };
 __device__ __forceinline__ int seg_of_tile(const GemmParams& p, int tile) { return (tile >= p.tile_end[0]) + (tile >= p.tile_end[1]); }
+// first tile of segment sg (constant indices only: dynamic indexing would spill the parameter struct to local memory)
+__device__ __forceinline__ int seg_first_tile(const GemmParams& p, int sg) { return sg == 0 ? 0 : (sg == 1 ? p.tile_end[0] : p.tile_end[1]); }
 
 // 6-bit scale / min of sub-block J from the 12 packed bytes held in three 32-bit words (ggml get_scale_min_k4)
 template <int J>
@@ -163,8 +185,8 @@ __device__ __forceinline__ void scale_min(uint32_t s0, uint32_t s1, uint32_t s2,
 // (d*sc*2^18, -dmin*m) yields d*sc*q - dmin*m with a single rounding.  It needs d*sc*2^18 <= 65504
 // (sub-block scale < 0.25, i.e. weight range < 3.75 -- always true for LLM weights); otherwise the
 // exact two-step path (1024+q magic, HSUB2, HFMA2) is taken for that row.
-template <int kHf>
-__device__ __forceinline__ void dequant_q4k_half(const uint8_t* blk, uint32_t a_col) {
+template <int kC>        // kC = 32-byte chunk of qs: sub-blocks 2 kC (lo nibbles) and 2 kC + 1 (hi nibbles) -> TMEM columns [32 kC, 32 kC + 32)
+__device__ __forceinline__ void dequant_q4k_quarter(const uint8_t* blk, uint32_t a_col) {
     const uint4 hdr = *reinterpret_cast<const uint4*>(blk);              // d | dmin | scales[12]
     const __half2 dd = *reinterpret_cast<const __half2*>(&hdr.x);
     const float d = __low2float(dd);
@@ -172,53 +194,49 @@ __device__ __forceinline__ void dequant_q4k_half(const uint8_t* blk, uint32_t a_
     // warp-uniform so that the .aligned tcgen05.st below is reached convergently
     const bool fast = __all_sync(0xffffffffu, fabsf(d) * 63.f * 262144.f <= 65504.f);
     const float dk = fast ? d * 262144.f : d;
+    int sc_lo, m_lo, sc_hi, m_hi;
+    scale_min<2 * kC>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo);
+    scale_min<2 * kC + 1>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi);
+    const __half2 s_lo = __float2half2_rn(dk * (float)sc_lo), s_hi = __float2half2_rn(dk * (float)sc_hi);
+    const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
+    const uint4 qa = *reinterpret_cast<const uint4*>(blk + 16 + kC * 32);
+    const uint4 qb = *reinterpret_cast<const uint4*>(blk + 32 + kC * 32);
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+    uint32_t v[32];
+    if (fast) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        int sc_lo, m_lo, sc_hi, m_hi;
-        if (cc == 0) { scale_min<4 * kHf>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo); scale_min<4 * kHf + 1>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi); }
-        else { scale_min<4 * kHf + 2>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo); scale_min<4 * kHf + 3>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi); }
-        const __half2 s_lo = __float2half2_rn(dk * (float)sc_lo), s_hi = __float2half2_rn(dk * (float)sc_hi);
-        const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
-        const int c = 2 * kHf + cc;                                      // 32-byte chunk of qs: sub-blocks 2c (lo nibbles), 2c+1 (hi)
-        const uint4 qa = *reinterpret_cast<const uint4*>(blk + 16 + c * 32);
-        const uint4 qb = *reinterpret_cast<const uint4*>(blk + 32 + c * 32);
-        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-        uint32_t v[32];
-        if (fast) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t x = w[i];
-                uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
-                uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
-                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
-                const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
-                const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
-                const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
-                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
-                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
-                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
-                v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
-            }
-        } else {
-            const uint32_t magic = 0x64006400u;                          // half2(1024, 1024): (q | 0x6400) = 1024 + q exactly
-            const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t x = w[i];
-                uint32_t t0 = (x & 0x000f000fu) | magic, t1 = ((x >> 8) & 0x000f000fu) | magic;
-                uint32_t t2 = ((x >> 4) & 0x000f000fu) | magic, t3 = ((x >> 12) & 0x000f000fu) | magic;
-                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), s_lo, n_lo);
-                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), s_lo, n_lo);
-                const __half2 r2 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t2), k1024), s_hi, n_hi);
-                const __half2 r3 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t3), k1024), s_hi, n_hi);
-                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
-                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
-                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
-                v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t x = w[i];
+            uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
+            uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
+            const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
+            const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
+            const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
+            const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
+            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+            v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+            v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
         }
-        tc_st32(a_col + cc * 32, v);
+    } else {
+        const uint32_t magic = 0x64006400u;                          // half2(1024, 1024): (q | 0x6400) = 1024 + q exactly
+        const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t x = w[i];
+            uint32_t t0 = (x & 0x000f000fu) | magic, t1 = ((x >> 8) & 0x000f000fu) | magic;
+            uint32_t t2 = ((x >> 4) & 0x000f000fu) | magic, t3 = ((x >> 12) & 0x000f000fu) | magic;
+            const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), s_lo, n_lo);
+            const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), s_lo, n_lo);
+            const __half2 r2 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t2), k1024), s_hi, n_hi);
+            const __half2 r3 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t3), k1024), s_hi, n_hi);
+            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+            v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+            v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+        }
     }
+    tc_st32(a_col + kC * 32, v);
 }
 
 // Q6_K staging.  A block = ql[128] | qh[64] | scales i8[16] | d f16 = 210 bytes and is only 2-byte aligned
@@ -282,8 +300,8 @@ __device__ __forceinline__ void dequant_q6k_pair(const uint32_t (&ql)[8], uint32
     }
 }
 
-template <int kHf>
-__device__ __forceinline__ void dequant_q6k_half(const uint8_t* slot, int off, uint32_t a_col) {
+template <int kHf, int kGp>       // quarter = half kHf, groups (kGp, kGp + 2): 64 weights -> two 16-column TMEM stores
+__device__ __forceinline__ void dequant_q6k_quarter(const uint8_t* slot, int off, uint32_t a_col) {
     uint32_t t[57];
 #pragma unroll
     for (int c = 0; c < 14; ++c) {
@@ -299,10 +317,8 @@ __device__ __forceinline__ void dequant_q6k_half(const uint8_t* slot, int off, u
     realign<32 + 8 * kHf, 8>(t, wo, sh16, qh);
     const bool fast = __all_sync(0xffffffffu, fabsf(d) * 128.f * 1048576.f <= 65504.f);   // warp-uniform (see Q4_K)
     const float dk = fast ? d * 1048576.f : d;
-    realign<16 * kHf, 8>(t, wo, sh16, ql);
-    dequant_q6k_pair<0>(ql, a_col, qh, scw, dk, fast);
-    realign<16 * kHf + 8, 8>(t, wo, sh16, ql);
-    dequant_q6k_pair<1>(ql, a_col, qh, scw, dk, fast);
+    realign<16 * kHf + 8 * kGp, 8>(t, wo, sh16, ql);
+    dequant_q6k_pair<kGp>(ql, a_col + kHf * 64, qh, scw, dk, fast);
 }
 
 // =================================================================================================
@@ -319,13 +335,13 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     auto full_bar = [&](int s) { return bars + s * 8; };
     auto empty_bar = [&](int s) { return bars + (kStages + s) * 8; };
     auto a_ready = [&](int b) { return bars + (2 * kStages + b) * 8; };
-    auto a_free = [&](int b) { return bars + (2 * kStages + 2 + b) * 8; };
-    const uint32_t d_full = bars + (2 * kStages + 4) * 8, d_empty = bars + (2 * kStages + 5) * 8;
+    auto a_free = [&](int b) { return bars + (2 * kStages + kABufs + b) * 8; };
+    const uint32_t d_full = bars + (2 * kStages + 2 * kABufs) * 8, d_empty = bars + (2 * kStages + 2 * kABufs + 1) * 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::kTmemSlot);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(a_ready(b), kDequantWarps); mbar_init(a_free(b), 1); }
+        for (int b = 0; b < kABufs; ++b) { mbar_init(a_ready(b), kDequantWarps); mbar_init(a_free(b), 1); }
         mbar_init(d_full, 1);
         mbar_init(d_empty, kDequantWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -346,63 +362,82 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
 
     if (warp == kDequantWarps) {
         // ===================================== TMA PRODUCER =====================================
-        if (lane == 0) {
-            uint64_t pol_w, pol_x;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
-            int it = 0;
-            for (int64_t u = u0; u < u1; ++u, ++it) {
-                const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
-                const int s = it % kStages;
-                mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-                mbar_expect_tx(full_bar(s), C::kXBytes + C::kWBytes);
-                const uint32_t dst = smem_base + s * C::kStageBytes;
+        // warp-uniform control flow (addresses stay in uniform registers); one elected lane issues
+        const bool leader = elect_one();
+        uint64_t pol_w, pol_x;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
+        int it = 0;
+        for (int64_t u = u0; u < u1; ++u, ++it) {
+            const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
+            const int s = it % kStages;
+            mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+            if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 0] = clock64();
+            const int sg = seg_of_tile(p, tile);
+            const CUtensorMap* wm = sg == 0 ? &wmap0 : (sg == 1 ? &wmap1 : &wmap2);
+            const int ltile = tile - seg_first_tile(p, sg);
+            const uint32_t dst = smem_base + s * C::kStageBytes;
+            if (leader) {
+                mbar_expect_tx(full_bar(s), ((p.debug & 8) ? 0 : C::kXBytes) + ((p.debug & 16) ? 0 : C::kWBytes));
+                if (!(p.debug & 8)) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, full_bar(s), sb * kSB + q * 64, 0, pol_x);
+                    for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, full_bar(s), sb * kSB + q * 64, 0, pol_x);
+                }
                 // W box start (bytes): Q4_K blocks are 144 B (16-aligned); Q6_K blocks (210 B) start at the block address
                 // rounded down to 16 -- TMA box starts must be 16-byte aligned
-                const int sg = seg_of_tile(p, tile);
-                const CUtensorMap* wm = sg == 0 ? &wmap0 : (sg == 1 ? &wmap1 : &wmap2);
-                const int ltile = tile - (sg ? p.tile_end[sg - 1] : 0);
-                tma_load_2d(dst + C::kXBytes, wm, full_bar(s), kType == B200_GGML_Q4_K ? sb * 144 : ((sb * 210) & ~15), ltile * kTileN, pol_w);
+                if (!(p.debug & 16))
+                    tma_load_2d(dst + C::kXBytes, wm, full_bar(s), kType == B200_GGML_Q4_K ? sb * 144 : ((sb * 210) & ~15), ltile * kTileN, pol_w);
+                if ((p.debug & 24) == 24) mbar_arrive(full_bar(s));
             }
+            __syncwarp();
         }
     } else if (warp == kDequantWarps + 1) {
         // ======================================= MMA ISSUER ======================================
-        if (lane == 0) {
-            // instruction descriptor: D = f32, A = B = f16, both K-major, N = kMB, M = 128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(kMB >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
-            int it = 0, seg = 0;
-            for (int64_t u = u0; u < u1;) {
-                const int tile = (int)(u / p.nsb);
-                const int64_t tile_end = (int64_t)(tile + 1) * p.nsb;
-                const int64_t seg_end = tile_end < u1 ? tile_end : u1;
-                mbar_wait(d_empty, (seg & 1) ^ 1);                 // epilogue of the previous segment has drained D
+        // The whole warp runs the (warp-uniform) loop so descriptors / TMEM addresses live in uniform registers;
+        // one elected lane issues.  (With a single-lane loop every tcgen05.mma cost ~110 cycles of R2UR traffic.)
+        const bool leader = elect_one();
+        // instruction descriptor: D = f32, A = B = f16, both K-major, N = kMB, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(kMB >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+        int it = 0, seg = 0;
+        for (int64_t u = u0; u < u1;) {
+            const int tile = (int)(u / p.nsb);
+            const int64_t tile_end = (int64_t)(tile + 1) * p.nsb;
+            const int64_t seg_end = tile_end < u1 ? tile_end : u1;
+            mbar_wait(d_empty, (seg & 1) ^ 1);                 // epilogue of the previous segment has drained D
+            tc_fence_after();
+            bool first = true;
+            for (; u < seg_end; ++u, ++it) {
+                const int s = it % kStages, ab = it % kABufs;
+                mbar_wait(full_bar(s), (it / kStages) & 1);       // activations landed (TMA)
+                if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 1] = clock64();
+                mbar_wait(a_ready(ab), (it / kABufs) & 1);        // dequantised A tile is in TMEM
+                if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 2] = clock64();
                 tc_fence_after();
-                bool first = true;
-                for (; u < seg_end; ++u, ++it) {
-                    const int s = it % kStages, ab = it & 1;
-                    mbar_wait(full_bar(s), (it / kStages) & 1);       // activations landed (TMA)
-                    mbar_wait(a_ready(ab), (it >> 1) & 1);            // dequantised A tile is in TMEM
-                    tc_fence_after();
-                    const uint32_t a_t = tmem + (ab ? kColA1 : kColA0);
-                    const uint32_t xs = smem_base + s * C::kStageBytes;
+                const uint32_t a_t = tmem + kColA + ab * 128;
+                const uint64_t bd0 = make_b_desc(smem_base + s * C::kStageBytes);
+                if (leader) {
+                    if (!(p.debug & 1)) {
 #pragma unroll
-                    for (int ks = 0; ks < 16; ++ks) {
-                        const uint64_t bd = make_b_desc(xs + (ks >> 2) * kMB * kXSubBytes + (ks & 3) * 32);
-                        tc_mma_ts(tmem + kColD, a_t + ks * 8, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                        for (int ks = 0; ks < 16; ++ks) {
+                            // k-step ks: 64-wide sub-tile (ks / 4), 32 bytes per k-step inside its 128-byte swizzled rows
+                            const uint64_t bd = bd0 + (uint64_t)((((ks >> 2) * kMB * kXSubBytes) + (ks & 3) * 32) >> 4);
+                            tc_mma_ts(tmem + kColD + (ks % C::kAcc) * kMB, a_t + ks * 8, bd, idesc, (first && ks < C::kAcc) ? 0u : 1u);
+                        }
                     }
-                    first = false;
                     tc_commit(empty_bar(s));          // stage (W bytes + X slice) reusable once these MMAs retire
                     tc_commit(a_free(ab));            // and so is the A buffer
+                    if (p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 8 + 3] = clock64();
                 }
-                tc_commit(d_full);                    // accumulator of this segment complete
-                ++seg;
+                __syncwarp();
+                first = false;
             }
+            if (leader) tc_commit(d_full);            // accumulator of this segment complete
+            __syncwarp();
+            ++seg;
         }
     } else {
         // ================================ DEQUANT + EPILOGUE WARPS ================================
-        const int qd = warp & 3, hf = warp >> 2;           // TMEM lane quadrant; which half of the super-block
+        const int qd = warp & 3, qt = warp >> 2;           // TMEM lane quadrant; which quarter (64 weights) of the super-block
         const int row = qd * 32 + lane;                    // weight row within the tile = TMEM lane
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         int it = 0, seg = 0;
@@ -411,21 +446,35 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             const int64_t tile_begin = (int64_t)tile * p.nsb, tile_end = tile_begin + p.nsb;
             const int64_t seg_begin = u, seg_end = tile_end < u1 ? tile_end : u1;
             for (; u < seg_end; ++u, ++it) {
-                const int s = it % kStages, ab = it & 1;
+                const int s = it % kStages, ab = it % kABufs;
                 mbar_wait(full_bar(s), (it / kStages) & 1);
-                mbar_wait(a_free(ab), ((it >> 1) & 1) ^ 1);
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 4] = clock64();
+                mbar_wait(a_free(ab), ((it / kABufs) & 1) ^ 1);
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 5] = clock64();
                 tc_fence_after();
                 const uint8_t* blk = smem + s * C::kStageBytes + C::kXBytes + row * C::kBlk;
-                const uint32_t a_col = tmem + (ab ? kColA1 : kColA0) + lane_addr + hf * 64;
-                if constexpr (kType == B200_GGML_Q4_K) {
-                    if (hf == 0) dequant_q4k_half<0>(blk, a_col); else dequant_q4k_half<1>(blk, a_col);
+                const uint32_t a_col = tmem + kColA + ab * 128 + lane_addr;
+                if (p.debug & 2) {
+                } else if constexpr (kType == B200_GGML_Q4_K) {
+                    switch (qt) {
+                        case 0: dequant_q4k_quarter<0>(blk, a_col); break;
+                        case 1: dequant_q4k_quarter<1>(blk, a_col); break;
+                        case 2: dequant_q4k_quarter<2>(blk, a_col); break;
+                        default: dequant_q4k_quarter<3>(blk, a_col); break;
+                    }
                 } else {
                     const int off = ((int)(u - tile_begin) * 210) & 15;        // block offset inside the 16-byte aligned window
-                    if (hf == 0) dequant_q6k_half<0>(blk, off, a_col); else dequant_q6k_half<1>(blk, off, a_col);
+                    switch (qt) {
+                        case 0: dequant_q6k_quarter<0, 0>(blk, off, a_col); break;
+                        case 1: dequant_q6k_quarter<0, 1>(blk, off, a_col); break;
+                        case 2: dequant_q6k_quarter<1, 0>(blk, off, a_col); break;
+                        default: dequant_q6k_quarter<1, 1>(blk, off, a_col); break;
+                    }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
+                if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 6] = clock64();
                 if (lane == 0) mbar_arrive(a_ready(ab));
             }
             // ---- epilogue of the segment: D (TMEM) -> y ------------------------------------------------
@@ -433,24 +482,32 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             tc_fence_after();
             const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
             const int sg = seg_of_tile(p, tile);
-            const int n_idx = (tile - (sg ? p.tile_end[sg - 1] : 0)) * kTileN + row;
-            float* const ybase = p.y[sg];
-            const int n_rows = p.n[sg];
-            constexpr int kColsPerHalf = kMB / 2;                 // this warp's share of the batch columns
+            const int n_idx = (tile - seg_first_tile(p, sg)) * kTileN + row;
+            float* const ybase = sg == 0 ? p.y[0] : (sg == 1 ? p.y[1] : p.y[2]);
+            const int n_rows = sg == 0 ? p.n[0] : (sg == 1 ? p.n[1] : p.n[2]);
+            constexpr int kColsPerWarp = kMB / 4;                 // this warp's share of the batch columns (8 or 16)
 #pragma unroll
-            for (int c0 = 0; c0 < kColsPerHalf; c0 += 16) {
-                uint32_t acc[16];
-                tc_ld16(tmem + kColD + lane_addr + hf * kColsPerHalf + c0, acc);
+            for (int c0 = 0; c0 < kColsPerWarp; c0 += 8) {
+                uint32_t acc[8];
+                tc_ld8(tmem + kColD + lane_addr + qt * kColsPerWarp + c0, acc);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (n_idx < n_rows) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int mi = hf * kColsPerHalf + c0 + i;
+                for (int a = 1; a < C::kAcc; ++a) {            // fold the independent accumulators
+                    uint32_t more[8];
+                    tc_ld8(tmem + kColD + a * kMB + lane_addr + qt * kColsPerWarp + c0, more);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(more[i]));
+                }
+                if (n_idx < n_rows && !(p.debug & 4)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int mi = qt * kColsPerWarp + c0 + i;
                         if (mi < p.m) {
                             float* o = ybase + (int64_t)mi * p.ldy + n_idx;
                             const float val = __uint_as_float(acc[i]);
                             if (whole && !p.accumulate) *o = val;
-                            else atomicAdd(o, val);
+                            else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o), "f"(val) : "memory");
                         }
                     }
                 }
@@ -561,6 +618,8 @@ void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* 
         if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return; }
     }
     p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
+    { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    { static const char* tr = getenv("B200_GEMM_TRACE"); p.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 0)) : nullptr; }
     if (ggml_type == B200_GGML_Q4_K) { if (mb == 32) launch<32, B200_GGML_Q4_K>(wm, xm, p, st); else launch<64, B200_GGML_Q4_K>(wm, xm, p, st); }
     else { if (mb == 32) launch<32, B200_GGML_Q6_K>(wm, xm, p, st); else launch<64, B200_GGML_Q6_K>(wm, xm, p, st); }
     check_launch("qmatmul_tc");
