@@ -38,7 +38,7 @@ namespace {
 constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
 constexpr int kSB = 256;             // weights per super-block
 constexpr int kDequantWarps = 16;     // 4 TMEM lane quadrants x 4 quarters of a super-block (64 weights per thread per unit)
-constexpr int kThreads = (kDequantWarps + 2) * 32;
+constexpr int kThreads = (kDequantWarps + 3) * 32;     // + W producer, X producer, MMA issuer
 constexpr int kXSubBytes = 64 * 2;                      // 128-byte swizzled row
 constexpr int kColD = 0, kColA = 128, kABufs = 3;        // TMEM columns (512 allocated): D accumulators [0,128), 3 A buffers of 128
 
@@ -47,18 +47,23 @@ struct Cfg {
     // bytes of one super-block as staged in shared memory: Q4_K 144; Q6_K a 240-byte window that starts at the
     // 210-byte block's address rounded down to 16 (TMA box starts must be 16-byte aligned)
     // Independent accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on the accumulate
-    // dependency (~150 cycles each at N = 32, measured as a_free stalls); k-step ks goes to D[ks % kAcc] and the
-    // epilogue adds them up.  kAcc * kMB = 128 TMEM columns.
+    // dependency; k-step ks goes to D[ks % kAcc] and the epilogue adds them up.  kAcc * kMB = 128 TMEM columns.
     static constexpr int kAcc = 128 / kMB;
     static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : 240;
-    static constexpr int kBlkGlobal = kType == B200_GGML_Q4_K ? 144 : 210;
-    static constexpr int kWBytes = kTileN * kBlk;
-    static constexpr int kStages = kMB == 32 ? (kType == B200_GGML_Q4_K ? 6 : 4) : (kType == B200_GGML_Q4_K ? 4 : 3);
-    static constexpr int kXBytes = 4 * kMB * kXSubBytes;        // 4 sub-tiles of [kMB][64] fp16
-    static constexpr int kStageBytes = (kXBytes + kWBytes + 1023) / 1024 * 1024;   // X first (1024-aligned), then W
-    static constexpr int kBars = kStages * kStageBytes;         // full[kStages] empty[kStages] a_ready[3] a_free[3] d_full d_empty
-    static constexpr int kTmemSlot = kBars + (2 * kStages + 8) * 8;
+    static constexpr int kWBytes = kTileN * kBlk;                  // raw weights of one unit (18 KB / 30 KB)
+    static constexpr int kXBytes = 4 * kMB * kXSubBytes;           // 4 sub-tiles of [kMB][64] fp16 (16 KB / 32 KB)
+    // Two rings.  Raw weight bytes are dead as soon as the dequant warps have pulled them into registers, so the
+    // W ring is deep and recycles fast (more HBM reads in flight); the activation slices live until their MMAs
+    // retire and come from L2, so the X ring is shallow.
+    static constexpr int kXStages = kMB == 32 ? 4 : 2;
+    static constexpr int kWStages = (227 * 1024 - 1024 - kXStages * kXBytes) / kWBytes > 8 ? 8 : (227 * 1024 - 1024 - kXStages * kXBytes) / kWBytes;
+    static constexpr int kXOff = 0;                                // 1024-aligned (128-byte swizzle)
+    static constexpr int kWOff = kXStages * kXBytes;
+    static constexpr int kBars = kWOff + kWStages * kWBytes;       // w_full[kW] w_empty[kW] x_full[kX] x_empty[kX] a_ready[3] a_free[3] d_full d_empty
+    static constexpr int kNumBars = 2 * kWStages + 2 * kXStages + 2 * kABufs + 2;
+    static constexpr int kTmemSlot = kBars + kNumBars * 8;
     static constexpr int kTotal = kTmemSlot + 16;
+    static_assert(kWStages >= 3, "W ring too shallow");
     static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
@@ -186,58 +191,64 @@ __device__ __forceinline__ void scale_min(uint32_t s0, uint32_t s1, uint32_t s2,
 // (sub-block scale < 0.25, i.e. weight range < 3.75 -- always true for LLM weights); otherwise the
 // exact two-step path (1024+q magic, HSUB2, HFMA2) is taken for that row.
 template <int kC>        // kC = 32-byte chunk of qs: sub-blocks 2 kC (lo nibbles) and 2 kC + 1 (hi nibbles) -> TMEM columns [32 kC, 32 kC + 32)
-__device__ __forceinline__ void dequant_q4k_quarter(const uint8_t* blk, uint32_t a_col) {
-    const uint4 hdr = *reinterpret_cast<const uint4*>(blk);              // d | dmin | scales[12]
-    const __half2 dd = *reinterpret_cast<const __half2*>(&hdr.x);
-    const float d = __low2float(dd);
-    const float dmin = -__high2float(dd);
-    // warp-uniform so that the .aligned tcgen05.st below is reached convergently
-    const bool fast = __all_sync(0xffffffffu, fabsf(d) * 63.f * 262144.f <= 65504.f);
-    const float dk = fast ? d * 262144.f : d;
-    int sc_lo, m_lo, sc_hi, m_hi;
-    scale_min<2 * kC>(hdr.y, hdr.z, hdr.w, sc_lo, m_lo);
-    scale_min<2 * kC + 1>(hdr.y, hdr.z, hdr.w, sc_hi, m_hi);
-    const __half2 s_lo = __float2half2_rn(dk * (float)sc_lo), s_hi = __float2half2_rn(dk * (float)sc_hi);
-    const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
-    const uint4 qa = *reinterpret_cast<const uint4*>(blk + 16 + kC * 32);
-    const uint4 qb = *reinterpret_cast<const uint4*>(blk + 32 + kC * 32);
-    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-    uint32_t v[32];
-    if (fast) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t x = w[i];
-            uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
-            uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
-            const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
-            const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
-            const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
-            const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
-            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
-            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
-            v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
-            v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
-        }
-    } else {
-        const uint32_t magic = 0x64006400u;                          // half2(1024, 1024): (q | 0x6400) = 1024 + q exactly
-        const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t x = w[i];
-            uint32_t t0 = (x & 0x000f000fu) | magic, t1 = ((x >> 8) & 0x000f000fu) | magic;
-            uint32_t t2 = ((x >> 4) & 0x000f000fu) | magic, t3 = ((x >> 12) & 0x000f000fu) | magic;
-            const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), s_lo, n_lo);
-            const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), s_lo, n_lo);
-            const __half2 r2 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t2), k1024), s_hi, n_hi);
-            const __half2 r3 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t3), k1024), s_hi, n_hi);
-            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
-            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
-            v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
-            v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
-        }
+struct Q4KQuarter {
+    static constexpr int kRaw = 12;
+    static __device__ __forceinline__ void load(const uint8_t* blk, int, uint32_t (&raw)[kRaw]) {
+        const uint4 hdr = *reinterpret_cast<const uint4*>(blk);              // d | dmin | scales[12]
+        const uint4 qa = *reinterpret_cast<const uint4*>(blk + 16 + kC * 32);
+        const uint4 qb = *reinterpret_cast<const uint4*>(blk + 32 + kC * 32);
+        raw[0] = hdr.x; raw[1] = hdr.y; raw[2] = hdr.z; raw[3] = hdr.w;
+        raw[4] = qa.x; raw[5] = qa.y; raw[6] = qa.z; raw[7] = qa.w; raw[8] = qb.x; raw[9] = qb.y; raw[10] = qb.z; raw[11] = qb.w;
     }
-    tc_st32(a_col + kC * 32, v);
-}
+    static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], int, uint32_t a_col) {
+        const __half2 dd = *reinterpret_cast<const __half2*>(&raw[0]);
+        const float d = __low2float(dd);
+        const float dmin = -__high2float(dd);
+        // warp-uniform so that the .aligned tcgen05.st below is reached convergently
+        const bool fast = __all_sync(0xffffffffu, fabsf(d) * 63.f * 262144.f <= 65504.f);
+        const float dk = fast ? d * 262144.f : d;
+        int sc_lo, m_lo, sc_hi, m_hi;
+        scale_min<2 * kC>(raw[1], raw[2], raw[3], sc_lo, m_lo);
+        scale_min<2 * kC + 1>(raw[1], raw[2], raw[3], sc_hi, m_hi);
+        const __half2 s_lo = __float2half2_rn(dk * (float)sc_lo), s_hi = __float2half2_rn(dk * (float)sc_hi);
+        const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
+        uint32_t v[32];
+        if (fast) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = raw[4 + i];
+                uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u;      // lo nibbles of bytes (0,2) and (1,3)
+                uint32_t t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;      // hi nibbles of bytes (0,2) and (1,3)
+                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo);
+                const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
+                const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi);
+                const __half2 r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+                v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            }
+        } else {
+            const uint32_t magic = 0x64006400u;                          // half2(1024, 1024): (q | 0x6400) = 1024 + q exactly
+            const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = raw[4 + i];
+                uint32_t t0 = (x & 0x000f000fu) | magic, t1 = ((x >> 8) & 0x000f000fu) | magic;
+                uint32_t t2 = ((x >> 4) & 0x000f000fu) | magic, t3 = ((x >> 12) & 0x000f000fu) | magic;
+                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), s_lo, n_lo);
+                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), s_lo, n_lo);
+                const __half2 r2 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t2), k1024), s_hi, n_hi);
+                const __half2 r3 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t3), k1024), s_hi, n_hi);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+                v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
+                v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            }
+        }
+        tc_st32(a_col + kC * 32, v);
+    }
+};
 
 // Q6_K staging.  A block = ql[128] | qh[64] | scales i8[16] | d f16 = 210 bytes and is only 2-byte aligned
 // in memory, while a TMA box must START 16-byte aligned (probed on B200: an unaligned start raises "illegal
@@ -300,54 +311,85 @@ __device__ __forceinline__ void dequant_q6k_pair(const uint32_t (&ql)[8], uint32
     }
 }
 
-template <int kHf, int kGp>       // quarter = half kHf, groups (kGp, kGp + 2): 64 weights -> two 16-column TMEM stores
-__device__ __forceinline__ void dequant_q6k_quarter(const uint8_t* slot, int off, uint32_t a_col) {
-    uint32_t t[57];
+template <int kQ>       // quarter kQ: half kHf = kQ / 2, groups (kGp, kGp + 2) with kGp = kQ % 2: 64 weights -> two 16-column TMEM stores
+struct Q6KQuarter {
+    static constexpr int kHf = kQ >> 1, kGp = kQ & 1;
+    static constexpr int kRaw = 57;
+    static __device__ __forceinline__ void load(const uint8_t* slot, int, uint32_t (&t)[kRaw]) {
 #pragma unroll
-    for (int c = 0; c < 14; ++c) {
-        const uint4 v = *reinterpret_cast<const uint4*>(slot + 16 * c);
-        t[4 * c] = v.x; t[4 * c + 1] = v.y; t[4 * c + 2] = v.z; t[4 * c + 3] = v.w;
+        for (int c = 0; c < 14; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(slot + 16 * c);
+            t[4 * c] = v.x; t[4 * c + 1] = v.y; t[4 * c + 2] = v.z; t[4 * c + 3] = v.w;
+        }
+        t[56] = 0u;
     }
-    t[56] = 0u;
-    const int wo = off >> 2, sh16 = (off & 2) * 8;
-    uint32_t dw[1], scw[2], qh[8], ql[8];
-    realign<52, 1>(t, wo, sh16, dw);                                              // d (f16) in the low half of dw[0]
-    const float d = __half2float(__ushort_as_half((unsigned short)(dw[0] & 0xffffu)));
-    realign<48 + 2 * kHf, 2>(t, wo, sh16, scw);                                   // 8 int8 scales of this half
-    realign<32 + 8 * kHf, 8>(t, wo, sh16, qh);
-    const bool fast = __all_sync(0xffffffffu, fabsf(d) * 128.f * 1048576.f <= 65504.f);   // warp-uniform (see Q4_K)
-    const float dk = fast ? d * 1048576.f : d;
-    realign<16 * kHf + 8 * kGp, 8>(t, wo, sh16, ql);
-    dequant_q6k_pair<kGp>(ql, a_col + kHf * 64, qh, scw, dk, fast);
-}
+    static __device__ __forceinline__ void compute(const uint32_t (&t)[kRaw], int off, uint32_t a_col) {
+        const int wo = off >> 2, sh16 = (off & 2) * 8;
+        uint32_t dw[1], scw[2], qh[8], ql[8];
+        realign<52, 1>(t, wo, sh16, dw);                                              // d (f16) in the low half of dw[0]
+        const float d = __half2float(__ushort_as_half((unsigned short)(dw[0] & 0xffffu)));
+        realign<48 + 2 * kHf, 2>(t, wo, sh16, scw);                                   // 8 int8 scales of this half
+        realign<32 + 8 * kHf, 8>(t, wo, sh16, qh);
+        const bool fast = __all_sync(0xffffffffu, fabsf(d) * 128.f * 1048576.f <= 65504.f);   // warp-uniform (see Q4_K)
+        const float dk = fast ? d * 1048576.f : d;
+        realign<16 * kHf + 8 * kGp, 8>(t, wo, sh16, ql);
+        dequant_q6k_pair<kGp>(ql, a_col + kHf * 64, qh, scw, dk, fast);
+    }
+};
+
+template <int kType, int kQ> struct QuarterOf;
+template <int kQ> struct QuarterOf<B200_GGML_Q4_K, kQ> { using type = Q4KQuarter<kQ>; };
+template <int kQ> struct QuarterOf<B200_GGML_Q6_K, kQ> { using type = Q6KQuarter<kQ>; };
 
 // =================================================================================================
+// One dequant unit for quarter kQ: pull the raw bytes into registers, hand the W stage back to the producer at
+// once (the bytes are dead), then wait for a free A buffer, dequantise into TMEM and signal the MMA warp.
+template <int kType, int kQ>
+__device__ __forceinline__ void dequant_unit(const uint8_t* blk, int off, uint32_t a_col, uint32_t w_empty_bar,
+                                             uint32_t a_free_bar, uint32_t a_free_parity, uint32_t a_ready_bar, int lane, bool skip) {
+    using Q = typename QuarterOf<kType, kQ>::type;
+    uint32_t raw[Q::kRaw];
+    Q::load(blk, off, raw);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w_empty_bar);
+    mbar_wait(a_free_bar, a_free_parity);
+    tc_fence_after();
+    if (!skip) Q::compute(raw, off, a_col);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready_bar);
+}
+
 template <int kMB, int kType>
 __global__ void __launch_bounds__(kThreads, 1)
 qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_constant__ CUtensorMap wmap1,
                   const __grid_constant__ CUtensorMap wmap2, const __grid_constant__ CUtensorMap xmap, const GemmParams p) {
     using C = Cfg<kMB, kType>;
-    constexpr int kStages = C::kStages;
+    constexpr int kW = C::kWStages, kX = C::kXStages;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bars = smem_base + C::kBars;
-    auto full_bar = [&](int s) { return bars + s * 8; };
-    auto empty_bar = [&](int s) { return bars + (kStages + s) * 8; };
-    auto a_ready = [&](int b) { return bars + (2 * kStages + b) * 8; };
-    auto a_free = [&](int b) { return bars + (2 * kStages + kABufs + b) * 8; };
-    const uint32_t d_full = bars + (2 * kStages + 2 * kABufs) * 8, d_empty = bars + (2 * kStages + 2 * kABufs + 1) * 8;
+    auto w_full = [&](int s) { return bars + s * 8; };
+    auto w_empty = [&](int s) { return bars + (kW + s) * 8; };
+    auto x_full = [&](int s) { return bars + (2 * kW + s) * 8; };
+    auto x_empty = [&](int s) { return bars + (2 * kW + kX + s) * 8; };
+    auto a_ready = [&](int b) { return bars + (2 * kW + 2 * kX + b) * 8; };
+    auto a_free = [&](int b) { return bars + (2 * kW + 2 * kX + kABufs + b) * 8; };
+    const uint32_t d_full = bars + (2 * kW + 2 * kX + 2 * kABufs) * 8, d_empty = d_full + 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::kTmemSlot);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), kDequantWarps); }
+        for (int s = 0; s < kX; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
         for (int b = 0; b < kABufs; ++b) { mbar_init(a_ready(b), kDequantWarps); mbar_init(a_free(b), 1); }
         mbar_init(d_full, 1);
         mbar_init(d_empty, kDequantWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == kDequantWarps + 1) {      // MMA warp owns the TMEM allocation
+    if (warp == kDequantWarps + 2) {      // MMA warp owns the TMEM allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -361,37 +403,48 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == kDequantWarps) {
-        // ===================================== TMA PRODUCER =====================================
+        // ================================== W PRODUCER (HBM stream) ==============================
         // warp-uniform control flow (addresses stay in uniform registers); one elected lane issues
         const bool leader = elect_one();
-        uint64_t pol_w, pol_x;
+        uint64_t pol_w;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
         int it = 0;
         for (int64_t u = u0; u < u1; ++u, ++it) {
             const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
-            const int s = it % kStages;
-            mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+            const int s = it % kW;
+            mbar_wait(w_empty(s), ((it / kW) & 1) ^ 1);
             if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 0] = clock64();
             const int sg = seg_of_tile(p, tile);
             const CUtensorMap* wm = sg == 0 ? &wmap0 : (sg == 1 ? &wmap1 : &wmap2);
             const int ltile = tile - seg_first_tile(p, sg);
-            const uint32_t dst = smem_base + s * C::kStageBytes;
             if (leader) {
-                mbar_expect_tx(full_bar(s), ((p.debug & 8) ? 0 : C::kXBytes) + ((p.debug & 16) ? 0 : C::kWBytes));
-                if (!(p.debug & 8)) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, full_bar(s), sb * kSB + q * 64, 0, pol_x);
-                }
                 // W box start (bytes): Q4_K blocks are 144 B (16-aligned); Q6_K blocks (210 B) start at the block address
                 // rounded down to 16 -- TMA box starts must be 16-byte aligned
-                if (!(p.debug & 16))
-                    tma_load_2d(dst + C::kXBytes, wm, full_bar(s), kType == B200_GGML_Q4_K ? sb * 144 : ((sb * 210) & ~15), ltile * kTileN, pol_w);
-                if ((p.debug & 24) == 24) mbar_arrive(full_bar(s));
+                mbar_expect_tx(w_full(s), C::kWBytes);
+                tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : ((sb * 210) & ~15),
+                            ltile * kTileN, pol_w);
             }
             __syncwarp();
         }
     } else if (warp == kDequantWarps + 1) {
+        // ================================== X PRODUCER (L2 resident) =============================
+        const bool leader = elect_one();
+        uint64_t pol_x;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
+        int it = 0;
+        for (int64_t u = u0; u < u1; ++u, ++it) {
+            const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
+            const int s = it % kX;
+            mbar_wait(x_empty(s), ((it / kX) & 1) ^ 1);
+            if (leader) {
+                mbar_expect_tx(x_full(s), C::kXBytes);
+                const uint32_t dst = smem_base + C::kXOff + s * C::kXBytes;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, x_full(s), sb * kSB + q * 64, 0, pol_x);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kDequantWarps + 2) {
         // ======================================= MMA ISSUER ======================================
         // The whole warp runs the (warp-uniform) loop so descriptors / TMEM addresses live in uniform registers;
         // one elected lane issues.  (With a single-lane loop every tcgen05.mma cost ~110 cycles of R2UR traffic.)
@@ -407,14 +460,14 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             tc_fence_after();
             bool first = true;
             for (; u < seg_end; ++u, ++it) {
-                const int s = it % kStages, ab = it % kABufs;
-                mbar_wait(full_bar(s), (it / kStages) & 1);       // activations landed (TMA)
+                const int xs = it % kX, ab = it % kABufs;
+                mbar_wait(x_full(xs), (it / kX) & 1);             // activations landed (TMA)
                 if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 1] = clock64();
                 mbar_wait(a_ready(ab), (it / kABufs) & 1);        // dequantised A tile is in TMEM
                 if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 2] = clock64();
                 tc_fence_after();
                 const uint32_t a_t = tmem + kColA + ab * 128;
-                const uint64_t bd0 = make_b_desc(smem_base + s * C::kStageBytes);
+                const uint64_t bd0 = make_b_desc(smem_base + C::kXOff + xs * C::kXBytes);
                 if (leader) {
                     if (!(p.debug & 1)) {
 #pragma unroll
@@ -424,7 +477,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                             tc_mma_ts(tmem + kColD + (ks % C::kAcc) * kMB, a_t + ks * 8, bd, idesc, (first && ks < C::kAcc) ? 0u : 1u);
                         }
                     }
-                    tc_commit(empty_bar(s));          // stage (W bytes + X slice) reusable once these MMAs retire
+                    tc_commit(x_empty(xs));           // activation slice reusable once these MMAs retire
                     tc_commit(a_free(ab));            // and so is the A buffer
                     if (p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 8 + 3] = clock64();
                 }
@@ -446,36 +499,21 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             const int64_t tile_begin = (int64_t)tile * p.nsb, tile_end = tile_begin + p.nsb;
             const int64_t seg_begin = u, seg_end = tile_end < u1 ? tile_end : u1;
             for (; u < seg_end; ++u, ++it) {
-                const int s = it % kStages, ab = it % kABufs;
-                mbar_wait(full_bar(s), (it / kStages) & 1);
+                const int ws = it % kW, ab = it % kABufs;
+                mbar_wait(w_full(ws), (it / kW) & 1);
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 4] = clock64();
-                mbar_wait(a_free(ab), ((it / kABufs) & 1) ^ 1);
-                if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 5] = clock64();
-                tc_fence_after();
-                const uint8_t* blk = smem + s * C::kStageBytes + C::kXBytes + row * C::kBlk;
+                const uint8_t* blk = smem + C::kWOff + ws * C::kWBytes + row * C::kBlk;
                 const uint32_t a_col = tmem + kColA + ab * 128 + lane_addr;
-                if (p.debug & 2) {
-                } else if constexpr (kType == B200_GGML_Q4_K) {
-                    switch (qt) {
-                        case 0: dequant_q4k_quarter<0>(blk, a_col); break;
-                        case 1: dequant_q4k_quarter<1>(blk, a_col); break;
-                        case 2: dequant_q4k_quarter<2>(blk, a_col); break;
-                        default: dequant_q4k_quarter<3>(blk, a_col); break;
-                    }
-                } else {
-                    const int off = ((int)(u - tile_begin) * 210) & 15;        // block offset inside the 16-byte aligned window
-                    switch (qt) {
-                        case 0: dequant_q6k_quarter<0, 0>(blk, off, a_col); break;
-                        case 1: dequant_q6k_quarter<0, 1>(blk, off, a_col); break;
-                        case 2: dequant_q6k_quarter<1, 0>(blk, off, a_col); break;
-                        default: dequant_q6k_quarter<1, 1>(blk, off, a_col); break;
-                    }
+                const int off = kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15);   // Q6_K: block offset in its window
+                const uint32_t afp = ((it / kABufs) & 1) ^ 1;
+                const bool skip = (p.debug & 2) != 0;
+                switch (qt) {
+                    case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
+                    case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
+                    case 2: dequant_unit<kType, 2>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
+                    default: dequant_unit<kType, 3>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
                 }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 6] = clock64();
-                if (lane == 0) mbar_arrive(a_ready(ab));
             }
             // ---- epilogue of the segment: D (TMEM) -> y ------------------------------------------------
             mbar_wait(d_full, seg & 1);
@@ -522,7 +560,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     // ---- teardown ---------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == kDequantWarps + 1) {
+    if (warp == kDequantWarps + 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
