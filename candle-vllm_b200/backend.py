@@ -274,7 +274,7 @@ class PagedAttention:
 class QTensor:
     """GGML-quantised weight [n, k]: verbatim GGUF bytes on the device (candle ``QTensor``)."""
 
-    def __init__(self, data: torch.Tensor, ggml_type: int, shape):
+    def __init__(self, data: torch.Tensor, ggml_type: int, shape, allow_cpu: bool = False):
         n, k = int(shape[0]), int(shape[1])
         if ggml_type not in GgmlType.BLOCK:
             raise BackendError(f"unsupported ggml type {ggml_type}")
@@ -283,7 +283,8 @@ class QTensor:
             raise BackendError(f"k={k} is not a multiple of the block size {be}")
         if data.dtype != torch.uint8 or data.numel() != n * (k // be) * bb:
             raise BackendError(f"QTensor: expected {n * (k // be) * bb} bytes (u8), got {data.numel()} {data.dtype}")
-        self.data = _cuda(data, "QTensor data").contiguous()
+        # host-resident QTensors exist only for shard bookkeeping (tensor-parallel splitting); no op accepts them
+        self.data = (data if allow_cpu else _cuda(data, "QTensor data")).contiguous()
         self.ggml_type = ggml_type
         self.shape = (n, k)
 

@@ -202,6 +202,65 @@ argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int n)
     }
 }
 
+// tensor-parallel greedy sampling: pairs[row] = (max logit, global index) over this rank's vocab shard
+__global__ void __launch_bounds__(1024)
+argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int n, int index_offset) {
+    const int row = blockIdx.x;
+    const float* xr = x + (int64_t)row * n;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = xr[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+    __shared__ float sv[32];
+    __shared__ int si[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) pairs[row] = make_float2(best, __int_as_float((bi == 0x7fffffff ? 0 : bi) + index_offset));
+    }
+}
+
+// gathered [world][rows] pairs -> token ids (first maximal global index wins ties, like a full argmax)
+__global__ void argmax_reduce_pairs_kernel(const float2* __restrict__ gathered, int32_t* __restrict__ out, int rows, int world) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int r = 0; r < world; ++r) {
+        const float2 pr = gathered[(int64_t)r * rows + row];
+        const int idx = __float_as_int(pr.y);
+        if (pr.x > best || (pr.x == best && idx < bi)) { best = pr.x; bi = idx; }
+    }
+    out[row] = bi;
+}
+
+void argmax_pairs(const float* logits, void* pairs, int rows, int n, int index_offset, cudaStream_t st) {
+    argmax_pair_kernel<<<rows, 1024, 0, st>>>(logits, static_cast<float2*>(pairs), n, index_offset);
+    count_launch();
+    check_launch("argmax_pairs");
+}
+void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st) {
+    argmax_reduce_pairs_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(static_cast<const float2*>(gathered), out, rows, world);
+    count_launch();
+    check_launch("argmax_reduce_pairs");
+}
+
 static inline int ew_grid(int64_t n) {
     int64_t g = (n + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;

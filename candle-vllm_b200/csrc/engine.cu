@@ -23,7 +23,12 @@
 using namespace b200;
 
 extern "C" long long b200_total_kernel_launches(void);
-namespace b200 { void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st); }
+namespace b200 {
+void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st);
+void tp_allgather_bytes(void* comm, const void* src, void* dst, size_t bytes_per_rank, cudaStream_t st);
+void argmax_pairs(const float* logits, void* pairs, int rows, int n, int index_offset, cudaStream_t st);
+void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st);
+}
 
 struct b200_llama {
     b200_llama_config cfg;
@@ -45,6 +50,7 @@ struct b200_llama {
     float* x = nullptr; __half* xn = nullptr; float* qkv = nullptr; __nv_bfloat16* q16 = nullptr;
     __half* attn16 = nullptr; float* gate = nullptr; float* up = nullptr; __half* act16 = nullptr;
     float* partial = nullptr; float* logits = nullptr; int32_t* next_tokens = nullptr;
+    float* tp_pairs = nullptr; float* tp_gathered = nullptr;      // (max, index) per sequence: local, and gathered over ranks
     float* cos_t = nullptr; float* sin_t = nullptr;
     void* attn_ws = nullptr; size_t attn_ws_bytes = 0;
 
@@ -103,7 +109,8 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             const void* ws[3] = {w.wq, w.wk, w.wv};
             const int ts[3] = {w.tq, w.tk, w.tv}, ns[3] = {qd, kd, kd};
             float* ys[3] = {m->qkv, m->qkv + qd, m->qkv + qd + kd};
-            qmatmul_dispatch_multi(m->xn, 3, ws, ts, ys, ns, m->qkv_row, B, H, 1, st);
+            // accumulate = 0: whole tiles are plain stores, split tiles red.add into the zeroed buffer
+            qmatmul_dispatch_multi(m->xn, 3, ws, ts, ys, ns, m->qkv_row, B, H, 0, st);
         }
         // (also re-zeroes qkv: the split-K GEMMs accumulate into it)
         rope_and_cache_impl(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
@@ -125,7 +132,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             const void* ws[2] = {w.w1, w.w3};
             const int ts[2] = {w.t1, w.t3}, ns[2] = {m->ffn_l, m->ffn_l};
             float* ys[2] = {m->gate, m->up};
-            qmatmul_dispatch_multi(m->xn, 2, ws, ts, ys, ns, m->ffn_l, B, H, 1, st);
+            qmatmul_dispatch_multi(m->xn, 2, ws, ts, ys, ns, m->ffn_l, B, H, 0, st);
         }
         silu_mul_zero_src(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, s);      // act = silu(gate)*up; gate/up re-zeroed
         if (c.tp_world == 1) {
@@ -142,7 +149,14 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
         zero_f32_kernel<<<sm_count() * 2, 256, 0, st>>>(m->logits, (int64_t)B * m->vocab_l); count_launch();
     }
     qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
-    argmax_f32(m->logits, m->next_tokens, B, m->vocab_l, s);
+    if (c.tp_world == 1) {
+        argmax_f32(m->logits, m->next_tokens, B, m->vocab_l, s);
+    } else {
+        // vocab-parallel lm_head (distributed.rs:1632-1667): gather (max, global index) pairs instead of the logits
+        argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, c.tp_rank * m->vocab_l, st);
+        tp_allgather_bytes(m->comm, m->tp_pairs, m->tp_gathered, (size_t)B * 8, st);
+        argmax_reduce_pairs(m->tp_gathered, m->next_tokens, B, c.tp_world, st);
+    }
     return (int)(b200_total_kernel_launches() - n0);
 }
 
@@ -218,7 +232,7 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
               dmalloc(m->qkv, B * m->qkv_row) && dmalloc(m->q16, B * m->heads_l * c.head_dim) &&
               dmalloc(m->attn16, B * m->heads_l * c.head_dim) && dmalloc(m->gate, B * m->ffn_l) && dmalloc(m->up, B * m->ffn_l) &&
               dmalloc(m->act16, B * m->ffn_l) && dmalloc(m->partial, B * c.hidden) && dmalloc(m->logits, B * m->vocab_l) &&
-              dmalloc(m->next_tokens, B);
+              dmalloc(m->next_tokens, B) && dmalloc(m->tp_pairs, B * 2) && dmalloc(m->tp_gathered, B * 2 * c.tp_world);
     m->attn_ws_bytes = paged_attention_decode_workspace_bytes((int)B, m->heads_l, c.head_dim, c.max_blocks_per_seq, c.block_size);
     char* ws = nullptr;
     ok = ok && dmalloc(ws, m->attn_ws_bytes);
@@ -255,7 +269,7 @@ void b200_llama_destroy(b200_llama* m) {
     if (!m) return;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
     void* ptrs[] = {m->d_tokens, m->d_positions, m->d_slots, m->d_ctx, m->d_tables, m->x, m->xn, m->qkv, m->q16, m->attn16,
-                    m->gate, m->up, m->act16, m->partial, m->logits, m->next_tokens, m->cos_t, m->sin_t, m->attn_ws};
+                    m->gate, m->up, m->act16, m->partial, m->logits, m->next_tokens, m->cos_t, m->sin_t, m->attn_ws, m->tp_pairs, m->tp_gathered};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_next) cudaFreeHost(m->h_next);

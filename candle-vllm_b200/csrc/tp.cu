@@ -9,15 +9,26 @@
 namespace b200 {
 
 typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
 static nccl_allreduce_fn g_allreduce = nullptr;
+static nccl_allgather_fn g_allgather = nullptr;
 
 static bool resolve() {
-    if (g_allreduce) return true;
+    if (g_allreduce && g_allgather) return true;
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
-    void* f = h ? dlsym(h, "ncclAllReduce") : dlsym(RTLD_DEFAULT, "ncclAllReduce");
-    g_allreduce = reinterpret_cast<nccl_allreduce_fn>(f);
-    return g_allreduce != nullptr;
+    g_allreduce = reinterpret_cast<nccl_allreduce_fn>(h ? dlsym(h, "ncclAllReduce") : dlsym(RTLD_DEFAULT, "ncclAllReduce"));
+    g_allgather = reinterpret_cast<nccl_allgather_fn>(h ? dlsym(h, "ncclAllGather") : dlsym(RTLD_DEFAULT, "ncclAllGather"));
+    return g_allreduce != nullptr && g_allgather != nullptr;
+}
+
+// VocabParallelLinear + AllGather (/root/reference/src/openai/distributed.rs:1632-1667) reduced to what greedy
+// decoding needs: every rank contributes (max logit, global index) per sequence; gather 8 bytes per sequence.
+void tp_allgather_bytes(void* comm, const void* src, void* dst, size_t bytes_per_rank, cudaStream_t st) {
+    if (!comm) { set_error(kErrBadArg, "tp_allgather: no communicator"); return; }
+    if (!resolve()) { set_error(kErrUnsupported, "tp_allgather: ncclAllGather not found (libnccl.so.2 not loaded)"); return; }
+    const int rc = g_allgather(src, dst, bytes_per_rank, /*ncclInt8*/ 0, comm, st);
+    if (rc != 0) set_error(kErrCuda, "tp_allgather: ncclAllGather rc=%d", rc);
 }
 
 void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st) {

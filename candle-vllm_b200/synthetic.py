@@ -39,7 +39,7 @@ def random_q6k(gen, n: int, k: int, device) -> torch.Tensor:
 
 def random_qtensor(gen, ggml_type: int, n: int, k: int, device) -> QTensor:
     fn = {GgmlType.Q4_K: random_q4k, GgmlType.Q6_K: random_q6k}[ggml_type]
-    return QTensor(fn(gen, n, k, device), ggml_type, (n, k))
+    return QTensor(fn(gen, n, k, device), ggml_type, (n, k), allow_cpu=True)
 
 
 def shard_rows(w: QTensor, rank: int, world: int) -> QTensor:
@@ -48,7 +48,7 @@ def shard_rows(w: QTensor, rank: int, world: int) -> QTensor:
     be, bb = GgmlType.BLOCK[w.ggml_type]
     rows = w.data.reshape(n, (k // be) * bb)
     nl = n // world
-    return QTensor(rows[rank * nl:(rank + 1) * nl].contiguous().reshape(-1), w.ggml_type, (nl, k))
+    return QTensor(rows[rank * nl:(rank + 1) * nl].contiguous().reshape(-1), w.ggml_type, (nl, k), allow_cpu=True)
 
 
 def shard_cols(w: QTensor, rank: int, world: int) -> QTensor:
@@ -60,7 +60,7 @@ def shard_cols(w: QTensor, rank: int, world: int) -> QTensor:
         raise ValueError(f"k={k}: {nbk} blocks per row not divisible by world {world}")
     blocks = w.data.reshape(n, nbk, bb)
     bl = nbk // world
-    return QTensor(blocks[:, rank * bl:(rank + 1) * bl].contiguous().reshape(-1), w.ggml_type, (n, k // world))
+    return QTensor(blocks[:, rank * bl:(rank + 1) * bl].contiguous().reshape(-1), w.ggml_type, (n, k // world), allow_cpu=True)
 
 
 def make_weights(cfg: LlamaConfig, device="cuda", seed: int = 0, tp_rank: int = 0, tp_world: int = 1,

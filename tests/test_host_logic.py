@@ -83,16 +83,9 @@ def test_synthetic_blocks_are_valid_and_sharding_is_consistent():
     d6 = G.dequantize_weight(w6, G.GGML_TYPE_Q6_K, 8, 1024)
     assert np.isfinite(d6).all() and 0.005 < d6.std() < 0.05
     # raw-byte shards: dequant(shard) == slice(dequant(full))
-    class Q:    # QTensor without the CUDA requirement
-        def __init__(s, data, t, shape): s.data, s.ggml_type, s.shape = data, t, shape
-    real = synthetic.QTensor
-    synthetic.QTensor = Q
-    try:
-        full = Q(torch.from_numpy(w), G.GGML_TYPE_Q4_K, (8, 1024))
-        for r in range(2):
-            rs = synthetic.shard_rows(full, r, 2)
-            assert np.array_equal(G.dequantize_weight(rs.data.numpy(), 12, 4, 1024), deq[4 * r:4 * r + 4])
-            cs = synthetic.shard_cols(full, r, 2)
-            assert np.array_equal(G.dequantize_weight(cs.data.numpy(), 12, 8, 512), deq[:, 512 * r:512 * r + 512])
-    finally:
-        synthetic.QTensor = real
+    full = pkg.QTensor(torch.from_numpy(w), G.GGML_TYPE_Q4_K, (8, 1024), allow_cpu=True)
+    for r in range(2):
+        rs = synthetic.shard_rows(full, r, 2)
+        assert np.array_equal(G.dequantize_weight(rs.data.numpy(), 12, 4, 1024), deq[4 * r:4 * r + 4])
+        cs = synthetic.shard_cols(full, r, 2)
+        assert np.array_equal(G.dequantize_weight(cs.data.numpy(), 12, 8, 512), deq[:, 512 * r:512 * r + 512])

@@ -1,0 +1,117 @@
+"""Tensor-parallel path: world_size-2 gloo test of the host-side sharding logic on CPU (the oracle does the
+arithmetic), and a 2-GPU NCCL parity test of the decode engine (skipped without two B200s)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import candle_vllm_b200 as pkg
+from candle_vllm_b200 import synthetic
+from oracle import ggml_quants as G
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator(device="cpu"); gen.manual_seed(0)              # same stream on every rank
+        H, F, B = 512, 1024, 3
+        w_up = synthetic.random_qtensor(gen, pkg.GgmlType.Q4_K, F, H, "cpu")   # column parallel (split dim 0)
+        w_dn = synthetic.random_qtensor(gen, pkg.GgmlType.Q4_K, H, F, "cpu")   # row parallel (split dim 1) + all-reduce
+        x = torch.randn((B, H), generator=gen).numpy()
+        up_l = synthetic.shard_rows(w_up, rank, world)
+        dn_l = synthetic.shard_cols(w_dn, rank, world)
+        h_l = G.qmatmul_dequant(x, up_l.data.numpy(), 12, up_l.shape[0], H)                 # [B, F/world]
+        part = torch.from_numpy(G.qmatmul_dequant(h_l, dn_l.data.numpy(), 12, H, dn_l.shape[1]))
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)                                        # distributed.rs:696-710
+        full_h = G.qmatmul_dequant(x, w_up.data.numpy(), 12, F, H)
+        full = G.qmatmul_dequant(full_h, w_dn.data.numpy(), 12, H, F)
+        err = float(np.abs(part.numpy() - full).max() / np.abs(full).max())
+        # vocab-parallel greedy sampling: (max, global index) pairs gathered over ranks == full argmax
+        logits = torch.randn((B, 64), generator=gen)
+        Vl = 64 // world
+        loc = logits[:, rank * Vl:(rank + 1) * Vl]
+        pair = torch.stack([loc.max(dim=1).values, (loc.argmax(dim=1) + rank * Vl).float()], dim=1)
+        gathered = [torch.empty_like(pair) for _ in range(world)]
+        dist.all_gather(gathered, pair)
+        g = torch.stack(gathered)                       # [world, B, 2]
+        pick = g[g[:, :, 0].argmax(dim=0), torch.arange(B), 1].long()
+        ok = bool(torch.equal(pick, logits.argmax(dim=1)))
+        if rank == 0:
+            out.put((err, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp2_sharding_matches_unsharded_on_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    err, ok = q.get()
+    assert err < 1e-5 and ok
+
+
+def _nccl_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from candle_vllm_b200.distributed import Comm
+        comm = Comm(rank, world)
+        cfg = pkg.LlamaConfig(hidden=512, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=128, ffn=1024, vocab=768,
+                              max_pos=512, block_size=64, max_num_seqs=8, max_blocks_per_seq=8)
+        nb = 24
+        tables = synthetic.random_block_tables(4, 4, nb, seed=2)
+        lens, toks = [10, 64, 65, 200], [5, 9, 700, 33]
+
+        def run(tp_rank, tp_world, comm_handle):
+            w = synthetic.make_weights(cfg, dev, seed=0, tp_rank=tp_rank, tp_world=tp_world)
+            eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim, pkg.CacheConfig(cfg.block_size, nb), device=dev,
+                                  num_shards=tp_world)
+            synthetic.fill_kv_cache(eng.gpu_cache, seed=7)     # NOTE: same seed -> TP caches are NOT shards of the TP=1 cache;
+            for k, v in eng.gpu_cache:                          # start from empty context instead so results are comparable
+                k.zero_(); v.zero_()
+            model = pkg.GGUFLLaMa(cfg, w, eng.gpu_cache, tp_rank=tp_rank, tp_world=tp_world, nccl_comm=comm_handle)
+            outs, L, T = [], [1, 1, 1, 1], list(toks)
+            for _ in range(6):                                  # decode from an empty cache: context grows 1..6
+                nxt, _ = model.decode(pkg.prepare_decode(L, T, tables, cfg.block_size))
+                outs.append(nxt.copy()); T = [int(t) for t in nxt]; L = [x + 1 for x in L]
+            return np.stack(outs)
+
+        tp = run(rank, world, comm.handle.value)
+        if rank == 0:
+            ref = run(0, 1, None)
+            out.put(bool(np.array_equal(tp, ref)))
+        dist.barrier()
+        comm.destroy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_tp2_decode_matches_tp1_on_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(300)
+    assert all(p.exitcode == 0 for p in procs)
+    assert q.get()
