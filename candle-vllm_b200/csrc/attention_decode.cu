@@ -160,6 +160,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    pdl_wait();            // context_lens / q / KV written by the previous kernels
+    pdl_trigger();
     // chunk prefix over sequences from the DEVICE-side context lengths
     const int chunk_tokens = p.chunk_pages * kPage;
     for (int b = threadIdx.x; b < p.num_seqs; b += kThreads) {
@@ -357,6 +359,8 @@ __global__ void __launch_bounds__(kHeadDim)
 paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o, const float* __restrict__ part_ml,
                         const uint32_t* __restrict__ context_lens, unsigned int* __restrict__ counter, int num_heads,
                         int num_kv_heads, int group, int chunk_tokens, int max_chunks) {
+    pdl_wait();
+    pdl_trigger();
     const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
     if (head == 0 && b == 0 && d == 0) *counter = 0u;        // leave the work queue ready for the next launch
     const int h = head / group, r = head - h * group;
@@ -423,11 +427,11 @@ void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vma
     const int64_t max_items = (int64_t)a.num_seqs * a.num_kv_heads * p.max_chunks;
     const int64_t want = (max_items + kWarps - 1) / kWarps;
     const int grid = (int)(want < sm_count() ? want : sm_count());
-    kern<<<grid, kThreads, SmemLayout::kTotal, st>>>(kmap, vmap, p);
+    launch_pdl(kern, dim3(grid), dim3(kThreads), SmemLayout::kTotal, st, kmap, vmap, p);
     count_launch();
-    paged_attn_merge_kernel<T, TOut, kK4><<<dim3(a.num_heads, a.num_seqs), kHeadDim, 0, st>>>(
-        static_cast<TOut*>(a.out), p.part_o, p.part_ml, a.context_lens, p.counter, a.num_heads, a.num_kv_heads, kGroup,
-        p.chunk_pages * kPage, p.max_chunks);
+    launch_pdl(paged_attn_merge_kernel<T, TOut, kK4>, dim3(a.num_heads, a.num_seqs), dim3(kHeadDim), 0, st,
+               static_cast<TOut*>(a.out), (const float*)p.part_o, (const float*)p.part_ml, a.context_lens, p.counter, (int)a.num_heads,
+               (int)a.num_kv_heads, (int)kGroup, (int)(p.chunk_pages * kPage), (int)p.max_chunks);
     count_launch();
 }
 

@@ -29,6 +29,26 @@ enum ErrorCode { kErrBadArg = 1, kErrUnsupported = 2, kErrCuda = 3, kErrNoDevice
 
 static inline cudaStream_t as_stream(int64_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel on the decode path is launched with programmatic stream serialization allowed: its grid may start
+// (block scheduling, barrier init, TMEM alloc, even weight prefetch) while the previous kernel drains, and it
+// calls pdl_wait() before touching anything the previous kernel produced.  griddepcontrol.wait returns only when
+// the prerequisite grid has fully completed and flushed, so triggering early is always safe.  B200_PDL=0 disables.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- dtype conversion -------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -34,6 +34,8 @@ __device__ __forceinline__ void store4(TOut* o, int i, float a, float b, float c
 template <typename TOut, bool kK4 = false>
 __global__ void __launch_bounds__(256)
 rms_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, TOut* __restrict__ out, int n, float eps) {
+    pdl_wait();
+    pdl_trigger();
     constexpr int kMaxIt = 8;                             // rows up to 8192 columns stay in registers
     const int row = blockIdx.x;
     const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * n);
@@ -72,6 +74,8 @@ __global__ void fused_rope_f32_kernel(float* __restrict__ q, float* __restrict__
                                       const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                       const int64_t* __restrict__ positions, int num_heads, int num_kv_heads,
                                       int head_dim, int interleaved) {
+    pdl_wait();
+    pdl_trigger();
     const int t = blockIdx.x;
     const int half = head_dim >> 1;
     const int64_t pos = positions[t];
@@ -91,58 +95,62 @@ __global__ void fused_rope_f32_kernel(float* __restrict__ q, float* __restrict__
 // ---- fused: rope(q,k) + q -> 16-bit + k,v -> cache (flash layout) ----------------------------
 // qkv f32 [T, (h + 2 kvh) * hd] is the packed output of the fused QKV projection.
 template <typename T16, bool kFp8, bool kZeroSrc = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 rope_and_cache_kernel(float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
                       const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                       const int64_t* __restrict__ positions, const int64_t* __restrict__ slot_mapping,
                       int num_heads, int num_kv_heads, int head_dim, int interleaved) {
-    const int t = blockIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    // grid = (tokens, heads + 2 kv heads): one CTA per (token, head slot) so that even a 32-token decode batch fills the GPU
+    const int t = blockIdx.x, hs = blockIdx.y;
     const int half = head_dim >> 1;
     const int64_t pos = positions[t];
     const int64_t slot = slot_mapping[t];
     const int row = (num_heads + 2 * num_kv_heads) * head_dim;
-    float* src = qkv + (int64_t)t * row;
-    const int nrot = (num_heads + num_kv_heads) * half;
+    float* src = qkv + (int64_t)t * row + (int64_t)hs * head_dim;
     const int kvn = num_kv_heads * head_dim;
-    for (int i = threadIdx.x; i < nrot; i += blockDim.x) {
-        const int h = i / half, j = i % half;
-        const float c = cos_t[pos * half + j], s = sin_t[pos * half + j];
-        const int i0 = interleaved ? 2 * j : j, i1 = interleaved ? 2 * j + 1 : j + half;
-        const float a = src[h * head_dim + i0], b = src[h * head_dim + i1];
-        const float r0 = a * c - b * s, r1 = a * s + b * c;
-        if (h < num_heads) {
-            T16* o = q_out + ((int64_t)t * num_heads + h) * head_dim;
-            o[i0] = from_f32<T16>(r0);
-            o[i1] = from_f32<T16>(r1);
-        } else if (slot >= 0) {
-            const int64_t base = slot * kvn + (int64_t)(h - num_heads) * head_dim;
-            // reference: k -> model dtype first (attention.rs:971-975), then the cache write casts again
-            const float k0 = to_f32(from_f32<T16>(r0)), k1 = to_f32(from_f32<T16>(r1));
-            if constexpr (kFp8) {
-                static_cast<uint8_t*>(kc_)[base + i0] = f32_to_e4m3(k0);
-                static_cast<uint8_t*>(kc_)[base + i1] = f32_to_e4m3(k1);
-            } else {
-                static_cast<T16*>(kc_)[base + i0] = from_f32<T16>(r0);
-                static_cast<T16*>(kc_)[base + i1] = from_f32<T16>(r1);
+    if (hs < num_heads + num_kv_heads) {
+        // q or k head: rotate
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            const float c = cos_t[pos * half + j], s = sin_t[pos * half + j];
+            const int i0 = interleaved ? 2 * j : j, i1 = interleaved ? 2 * j + 1 : j + half;
+            const float a = src[i0], b = src[i1];
+            const float r0 = a * c - b * s, r1 = a * s + b * c;
+            if (hs < num_heads) {
+                T16* o = q_out + ((int64_t)t * num_heads + hs) * head_dim;
+                o[i0] = from_f32<T16>(r0);
+                o[i1] = from_f32<T16>(r1);
+            } else if (slot >= 0) {
+                const int64_t base = slot * kvn + (int64_t)(hs - num_heads) * head_dim;
+                // reference: k -> model dtype first (attention.rs:971-975), then the cache write casts again
+                if constexpr (kFp8) {
+                    static_cast<uint8_t*>(kc_)[base + i0] = f32_to_e4m3(to_f32(from_f32<T16>(r0)));
+                    static_cast<uint8_t*>(kc_)[base + i1] = f32_to_e4m3(to_f32(from_f32<T16>(r1)));
+                } else {
+                    static_cast<T16*>(kc_)[base + i0] = from_f32<T16>(r0);
+                    static_cast<T16*>(kc_)[base + i1] = from_f32<T16>(r1);
+                }
             }
         }
-    }
-    if (slot >= 0) {
-        const float* v = src + (num_heads + num_kv_heads) * head_dim;
-        (void)v;
-        for (int i = threadIdx.x; i < kvn; i += blockDim.x) {
-            if constexpr (kFp8) static_cast<uint8_t*>(vc_)[slot * kvn + i] = f32_to_e4m3(to_f32(from_f32<T16>(v[i])));
-            else static_cast<T16*>(vc_)[slot * kvn + i] = from_f32<T16>(v[i]);
+    } else if (slot >= 0) {
+        // v head: cast + cache write
+        const int64_t base = slot * kvn + (int64_t)(hs - num_heads - num_kv_heads) * head_dim;
+        for (int i = threadIdx.x; i < head_dim; i += blockDim.x) {
+            if constexpr (kFp8) static_cast<uint8_t*>(vc_)[base + i] = f32_to_e4m3(to_f32(from_f32<T16>(src[i])));
+            else static_cast<T16*>(vc_)[base + i] = from_f32<T16>(src[i]);
         }
     }
     if constexpr (kZeroSrc) {          // leave the split-K accumulator zeroed for the next layer's QKV GEMM
         __syncthreads();
-        for (int i = threadIdx.x; i < row; i += blockDim.x) src[i] = 0.f;
+        for (int i = threadIdx.x; i < head_dim; i += blockDim.x) src[i] = 0.f;
     }
 }
 
 template <typename TOut, bool kK4 = false, bool kZeroSrc = false>
 __global__ void silu_mul_kernel(float* __restrict__ g, float* __restrict__ u, TOut* __restrict__ out, int64_t n) {
+    pdl_wait();
+    pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float a = g[i];
         out[kK4 ? k4_index(i) : i] = from_f32<TOut>(a / (1.f + __expf(-a)) * u[i]);
@@ -151,17 +159,23 @@ __global__ void silu_mul_kernel(float* __restrict__ g, float* __restrict__ u, TO
 }
 
 __global__ void add_f32_kernel(float* __restrict__ x, const float* __restrict__ y, int64_t n) {
+    pdl_wait();
+    pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += y[i];
 }
 
 template <typename TS, typename TD, bool kK4 = false>
 __global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    pdl_wait();
+    pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         d[kK4 ? k4_index(i) : i] = from_f32<TD>(to_f32(s[i]));
 }
 
 __global__ void embedding_f32_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
                                      float* __restrict__ out, int dim) {
+    pdl_wait();
+    pdl_trigger();
     const int t = blockIdx.x;
     const float4* src = reinterpret_cast<const float4*>(table + ids[t] * (int64_t)dim);
     float4* dst = reinterpret_cast<float4*>(out + (int64_t)t * dim);
@@ -171,6 +185,8 @@ __global__ void embedding_f32_kernel(const float* __restrict__ table, const int6
 // argmax per row (first maximal index, like candle's argmax); one CTA per row.
 __global__ void __launch_bounds__(1024)
 argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int n) {
+    pdl_wait();
+    pdl_trigger();
     const int row = blockIdx.x;
     const float* xr = x + (int64_t)row * n;
     float best = -INFINITY;
@@ -205,6 +221,8 @@ argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int n)
 // tensor-parallel greedy sampling: pairs[row] = (max logit, global index) over this rank's vocab shard
 __global__ void __launch_bounds__(1024)
 argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int n, int index_offset) {
+    pdl_wait();
+    pdl_trigger();
     const int row = blockIdx.x;
     const float* xr = x + (int64_t)row * n;
     float best = -INFINITY;
@@ -238,6 +256,8 @@ argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int 
 
 // gathered [world][rows] pairs -> token ids (first maximal global index wins ties, like a full argmax)
 __global__ void argmax_reduce_pairs_kernel(const float2* __restrict__ gathered, int32_t* __restrict__ out, int rows, int world) {
+    pdl_wait();
+    pdl_trigger();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     float best = -INFINITY;
@@ -251,12 +271,12 @@ __global__ void argmax_reduce_pairs_kernel(const float2* __restrict__ gathered, 
 }
 
 void argmax_pairs(const float* logits, void* pairs, int rows, int n, int index_offset, cudaStream_t st) {
-    argmax_pair_kernel<<<rows, 1024, 0, st>>>(logits, static_cast<float2*>(pairs), n, index_offset);
+    launch_pdl(argmax_pair_kernel, dim3(rows), dim3(1024), 0, st, logits, static_cast<float2*>(pairs), n, index_offset);
     count_launch();
     check_launch("argmax_pairs");
 }
 void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st) {
-    argmax_reduce_pairs_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(static_cast<const float2*>(gathered), out, rows, world);
+    launch_pdl(argmax_reduce_pairs_kernel, dim3(ceil_div(rows, 128)), dim3(128), 0, st, static_cast<const float2*>(gathered), out, rows, world);
     count_launch();
     check_launch("argmax_reduce_pairs");
 }
@@ -279,10 +299,10 @@ void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int3
     B200_REQUIRE(x && weight && out && rows > 0 && n > 0, kErrBadArg, "rms_norm: bad arguments");
     B200_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)weight & 15) == 0 && ((uintptr_t)out & 15) == 0 && n % 4 == 0, kErrBadArg,
                  "rms_norm: x, weight, out must be 16-byte aligned and n %% 4 == 0");
-    if (out_dtype == B200_F32) rms_norm_kernel<float><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (float*)out, n, eps);
-    else if (out_dtype == B200_F16) rms_norm_kernel<__half><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);
-    else if (out_dtype == B200_F16_K4) rms_norm_kernel<__half, true><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__half*)out, n, eps);
-    else if (out_dtype == B200_BF16) rms_norm_kernel<__nv_bfloat16><<<rows, 256, 0, as_stream(stream)>>>(x, weight, (__nv_bfloat16*)out, n, eps);
+    if (out_dtype == B200_F32) launch_pdl(rms_norm_kernel<float, false>, dim3(rows), dim3(256), 0, as_stream(stream), x, weight, (float*)out, n, eps);
+    else if (out_dtype == B200_F16) launch_pdl(rms_norm_kernel<__half, false>, dim3(rows), dim3(256), 0, as_stream(stream), x, weight, (__half*)out, n, eps);
+    else if (out_dtype == B200_F16_K4) launch_pdl(rms_norm_kernel<__half, true>, dim3(rows), dim3(256), 0, as_stream(stream), x, weight, (__half*)out, n, eps);
+    else if (out_dtype == B200_BF16) launch_pdl(rms_norm_kernel<__nv_bfloat16, false>, dim3(rows), dim3(256), 0, as_stream(stream), x, weight, (__nv_bfloat16*)out, n, eps);
     else { set_error(kErrUnsupported, "rms_norm: out dtype %d", out_dtype); return; }
     count_launch();
     check_launch("rms_norm");
@@ -311,7 +331,7 @@ void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_c
     const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
     B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "rope_and_cache: cache dtype %d vs dtype %d", cache_dtype, dtype);
     cudaStream_t st = as_stream(stream);
-#define LAUNCH(T16, F8, Z) rope_and_cache_kernel<T16, F8, Z><<<num_tokens, 256, 0, st>>>(qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved)
+#define LAUNCH(T16, F8, Z) launch_pdl(rope_and_cache_kernel<T16, F8, Z>, dim3(num_tokens, num_heads + 2 * num_kv_heads), dim3(64), 0, st, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved)
 #define LAUNCH2(T16, F8) do { if (zero_src) LAUNCH(T16, F8, true); else LAUNCH(T16, F8, false); } while (0)
     if (dtype == B200_BF16) { if (fp8) LAUNCH2(__nv_bfloat16, true); else LAUNCH2(__nv_bfloat16, false); }
     else if (dtype == B200_F16) { if (fp8) LAUNCH2(__half, true); else LAUNCH2(__half, false); }
@@ -323,7 +343,7 @@ void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_c
 }
 
 void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, int64_t stream) {
-    silu_mul_kernel<__half, true, true><<<ew_grid(numel), 256, 0, as_stream(stream)>>>(gate, up, (__half*)out_f16_k4, numel);
+    launch_pdl(silu_mul_kernel<__half, true, true>, dim3(ew_grid(numel)), dim3(256), 0, as_stream(stream), gate, up, (__half*)out_f16_k4, numel);
     count_launch();
     check_launch("silu_mul");
 }
@@ -356,7 +376,7 @@ void silu_mul(const float* gate, const float* up, void* out, int64_t numel, int3
 void add_f32(float* x, const float* y, int64_t numel, int64_t stream) {
     if (numel == 0) return;
     B200_REQUIRE(x && y && numel > 0, kErrBadArg, "add_f32: bad arguments");
-    add_f32_kernel<<<ew_grid(numel), 256, 0, as_stream(stream)>>>(x, y, numel);
+    launch_pdl(add_f32_kernel, dim3(ew_grid(numel)), dim3(256), 0, as_stream(stream), x, y, numel);
     count_launch();
     check_launch("add_f32");
 }
@@ -380,7 +400,7 @@ void cast(const void* src, void* dst, int64_t numel, int32_t sd, int32_t dd, int
 void embedding_f32(const float* table, const int64_t* ids, float* out, int32_t num_tokens, int32_t dim, int64_t stream) {
     if (num_tokens == 0) return;
     B200_REQUIRE(table && ids && out && dim % 4 == 0, kErrBadArg, "embedding: bad arguments");
-    embedding_f32_kernel<<<num_tokens, 256, 0, as_stream(stream)>>>(table, ids, out, dim);
+    launch_pdl(embedding_f32_kernel, dim3(num_tokens), dim3(256), 0, as_stream(stream), table, ids, out, (int)dim);
     count_launch();
     check_launch("embedding");
 }
@@ -388,7 +408,7 @@ void embedding_f32(const float* table, const int64_t* ids, float* out, int32_t n
 void argmax_f32(const float* logits, int32_t* out, int32_t rows, int32_t n, int64_t stream) {
     if (rows == 0) return;
     B200_REQUIRE(logits && out && n > 0, kErrBadArg, "argmax: bad arguments");
-    argmax_f32_kernel<<<rows, 1024, 0, as_stream(stream)>>>(logits, out, n);
+    launch_pdl(argmax_f32_kernel, dim3(rows), dim3(1024), 0, as_stream(stream), logits, out, (int)n);
     count_launch();
     check_launch("argmax");
 }

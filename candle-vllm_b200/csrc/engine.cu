@@ -80,6 +80,8 @@ bool dmalloc(T*& p, size_t n) {
 __global__ void advance_metadata_kernel(int64_t* tokens, const int32_t* next_tokens, int64_t* positions,
                                         int64_t* slots, uint32_t* ctx, const uint32_t* tables,
                                         int num_seqs, int max_blocks, int block_size, int feed_tokens) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= num_seqs) return;
     if (feed_tokens) tokens[b] = next_tokens[b];
@@ -90,6 +92,8 @@ __global__ void advance_metadata_kernel(int64_t* tokens, const int32_t* next_tok
 }
 
 __global__ void zero_f32_kernel(float* p, int64_t n) {
+    pdl_wait();
+    pdl_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
@@ -122,7 +126,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             qmatmul_dispatch(m->attn16, w.wo, m->x, H, B, H, qd, w.to, 1, st);          // x += wo(attn)
         } else {
             // row-parallel: partial sums -> all-reduce -> residual add (distributed.rs:696-710)
-            zero_f32_kernel<<<64, 256, 0, st>>>(m->partial, (int64_t)B * H); count_launch();
+            launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->partial, (int64_t)B * H); count_launch();
             qmatmul_dispatch(m->attn16, w.wo, m->partial, H, B, H, qd, w.to, 1, st);
             tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);   // tp.cu (NCCL)
             add_f32(m->x, m->partial, (int64_t)B * H, s);
@@ -138,7 +142,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->act16, w.w2, m->x, H, B, H, m->ffn_l, w.t2, 1, st);     // x += w2(act)
         } else {
-            zero_f32_kernel<<<64, 256, 0, st>>>(m->partial, (int64_t)B * H); count_launch();
+            launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->partial, (int64_t)B * H); count_launch();
             qmatmul_dispatch(m->act16, w.w2, m->partial, H, B, H, m->ffn_l, w.t2, 1, st);
             tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);
             add_f32(m->x, m->partial, (int64_t)B * H, s);
@@ -146,7 +150,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
     }
     rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
     if (qmatmul_tc_supported(B, m->vocab_l, H, m->output_type) && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) {
-        zero_f32_kernel<<<sm_count() * 2, 256, 0, st>>>(m->logits, (int64_t)B * m->vocab_l); count_launch();
+        launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
     }
     qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
     if (c.tp_world == 1) {
@@ -350,9 +354,9 @@ void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance
     B200_REQUIRE(num_seqs > 0 && num_seqs <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_decode_resident: bad num_seqs");
     cudaStream_t st = as_stream(stream);
     if (advance) {
-        advance_metadata_kernel<<<ceil_div(num_seqs, 128), 128, 0, st>>>(m->d_tokens, m->next_tokens, m->d_positions, m->d_slots,
-                                                                        m->d_ctx, m->d_tables, num_seqs, m->cfg.max_blocks_per_seq,
-                                                                        m->cfg.block_size, 1);
+        launch_pdl(advance_metadata_kernel, dim3(ceil_div(num_seqs, 128)), dim3(128), 0, st, m->d_tokens, (const int32_t*)m->next_tokens,
+                   m->d_positions, m->d_slots, m->d_ctx, (const uint32_t*)m->d_tables, (int)num_seqs, (int)m->cfg.max_blocks_per_seq,
+                   (int)m->cfg.block_size, 1);
         m->launches += 1;
     }
     run_step(m, num_seqs, st);

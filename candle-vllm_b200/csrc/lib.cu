@@ -1,6 +1,7 @@
 // lib.cu -- library state: per-thread error record, launch counter, device probing.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -29,6 +30,11 @@ bool check_launch(const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const int on = [] { const char* e = getenv("B200_PDL"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
 
 int sm_count() {
     static int cached = -1;

@@ -28,6 +28,10 @@ void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* 
 void qmatmul_dispatch_multi(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
                             int64_t ldy, int m, int k, int accumulate, cudaStream_t st);
 
+// symmetric int4 (GPTQ, repacked by gptq_repack) x fp16 activations in K4 order -> 16-bit out; m <= 64, k % 256 == 0
+void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
+               cudaStream_t st);
+
 // picks tc or generic; y row stride ldy (elements)
 void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k,
                       int ggml_type, int accumulate, cudaStream_t st);

@@ -29,6 +29,8 @@ qmatmul_generic_kernel(const TX* __restrict__ x, const void* __restrict__ w_, fl
                        int64_t ldy, int m, int n, int k, int accumulate) {
     using Q = QType<kType>;
     using Block = typename Q::Block;
+    pdl_wait();
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowsPerCta + warp;
     if (row >= n) return;

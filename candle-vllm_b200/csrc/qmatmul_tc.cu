@@ -36,6 +36,7 @@ namespace b200 {
 namespace {
 
 constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
+constexpr int kTypeM4 = 1004;        // internal: symmetric int4 (GPTQ) in this library's repacked row-major layout (marlin_4bit_*)
 constexpr int kSB = 256;             // weights per super-block
 constexpr int kDequantWarps = 16;     // 4 TMEM lane quadrants x 4 quarters of a super-block (64 weights per thread per unit)
 constexpr int kThreads = (kDequantWarps + 3) * 32;     // + W producer, X producer, MMA issuer
@@ -49,7 +50,7 @@ struct Cfg {
     // Independent accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on the accumulate
     // dependency; k-step ks goes to D[ks % kAcc] and the epilogue adds them up.  kAcc * kMB = 128 TMEM columns.
     static constexpr int kAcc = 128 / kMB;
-    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : 240;
+    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : (kType == kTypeM4 ? 128 : 240);
     static constexpr int kWBytes = kTileN * kBlk;                  // raw weights of one unit (18 KB / 30 KB)
     static constexpr int kXBytes = 4 * kMB * kXSubBytes;           // 4 sub-tiles of [kMB][64] fp16 (16 KB / 32 KB)
     // Two rings.  Raw weight bytes are dead as soon as the dequant warps have pulled them into registers, so the
@@ -169,6 +170,10 @@ struct GemmParams {
     int m, nsb;                    // nsb = k / 256
     int n_tiles;                   // tiles over all segments
     int accumulate;
+    int out_dtype;                 // B200_F32 (GGUF paths) or B200_F16 / B200_BF16 (marlin: plain stores, whole tiles only)
+    int whole_tiles;               // 1: CTA ranges are whole tiles (no split-K, no atomics)
+    const void* scales;            // marlin: [K/g, N] in marlin-permuted order, dtype = out_dtype
+    int group_size, k;             // marlin
     long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
     int debug;                     // profiling aid (B200_GEMM_DEBUG): 1 = skip MMA issue, 2 = skip dequant, 4 = skip epilogue stores
 };
@@ -244,6 +249,67 @@ struct Q4KQuarter {
                 v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
                 v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2);
                 v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            }
+        }
+        tc_st32(a_col + kC * 32, v);
+    }
+};
+
+// Symmetric int4 (GPTQ) in the repacked layout written by gptq_repack(): per row, per 64-k chunk, 32 bytes whose low
+// nibbles are k = 0..31 and high nibbles k = 32..63 of the chunk -- the same nibble geometry as a Q4_K chunk, so the
+// subnormal-placement + HFMA2 trick applies unchanged: w = s*q - 8*s with one per-group scale s
+// (/root/reference/src/backend/gptq.rs:115-178 call site; scales arrive marlin-permuted, linear.rs:341-379).
+struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16; };
+__device__ __forceinline__ int marlin_scale_pos(int n, bool grouped) {
+    // inverse of marlin_permute_scales: position of original column n inside its permuted block
+    if (grouped) { const int b = n & 63; return (n & ~63) | (8 * (b & 7) + (b >> 3)); }
+    const int b = n & 31, i = (b & 7) >> 1, r = b - 2 * i;          // r = 8a + c, c in {0,1}
+    return (n & ~31) | (8 * i + 2 * (r >> 3) + (r & 1));
+}
+template <int kC>
+struct M4Quarter {
+    static constexpr int kRaw = 8;
+    static __device__ __forceinline__ void load(const uint8_t* blk, int, uint32_t (&raw)[kRaw]) {
+        const uint4 qa = *reinterpret_cast<const uint4*>(blk + kC * 32);
+        const uint4 qb = *reinterpret_cast<const uint4*>(blk + kC * 32 + 16);
+        raw[0] = qa.x; raw[1] = qa.y; raw[2] = qa.z; raw[3] = qa.w; raw[4] = qb.x; raw[5] = qb.y; raw[6] = qb.z; raw[7] = qb.w;
+    }
+    static __device__ __forceinline__ float scale_at(const M4Ctx& c, int k) {
+        const bool grouped = c.group_size > 0;
+        const int g = grouped ? k / c.group_size : 0;
+        const int64_t idx = (int64_t)g * c.n_total + marlin_scale_pos(c.n_idx, grouped);
+        return c.bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(c.scales)[idx]) : __half2float(static_cast<const __half*>(c.scales)[idx]);
+    }
+    static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
+        const float s0 = scale_at(c, c.k0 + kC * 64), s1 = scale_at(c, c.k0 + kC * 64 + 32);
+        const bool fast = __all_sync(0xffffffffu, fmaxf(fabsf(s0), fabsf(s1)) * 262144.f <= 65504.f);
+        const __half2 s_lo = __float2half2_rn(fast ? s0 * 262144.f : s0), s_hi = __float2half2_rn(fast ? s1 * 262144.f : s1);
+        const __half2 n_lo = __float2half2_rn(-8.f * s0), n_hi = __float2half2_rn(-8.f * s1);
+        uint32_t v[32];
+        if (fast) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = raw[i];
+                uint32_t t0 = (x << 6) & 0x03c003c0u, t1 = (x >> 2) & 0x03c003c0u, t2 = (x << 2) & 0x03c003c0u, t3 = (x >> 6) & 0x03c003c0u;
+                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), s_lo, n_lo), r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), s_lo, n_lo);
+                const __half2 r2 = __hfma2(*reinterpret_cast<__half2*>(&t2), s_hi, n_hi), r3 = __hfma2(*reinterpret_cast<__half2*>(&t3), s_hi, n_hi);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0); v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2); v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
+            }
+        } else {
+            const uint32_t magic = 0x64006400u;
+            const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t x = raw[i];
+                uint32_t t0 = (x & 0x000f000fu) | magic, t1 = ((x >> 8) & 0x000f000fu) | magic;
+                uint32_t t2 = ((x >> 4) & 0x000f000fu) | magic, t3 = ((x >> 12) & 0x000f000fu) | magic;
+                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), s_lo, n_lo);
+                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), s_lo, n_lo);
+                const __half2 r2 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t2), k1024), s_hi, n_hi);
+                const __half2 r3 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t3), k1024), s_hi, n_hi);
+                v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0); v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+                v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2); v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
             }
         }
         tc_st32(a_col + kC * 32, v);
@@ -340,13 +406,15 @@ struct Q6KQuarter {
 template <int kType, int kQ> struct QuarterOf;
 template <int kQ> struct QuarterOf<B200_GGML_Q4_K, kQ> { using type = Q4KQuarter<kQ>; };
 template <int kQ> struct QuarterOf<B200_GGML_Q6_K, kQ> { using type = Q6KQuarter<kQ>; };
+template <int kQ> struct QuarterOf<kTypeM4, kQ> { using type = M4Quarter<kQ>; };
 
 // =================================================================================================
 // One dequant unit for quarter kQ: pull the raw bytes into registers, hand the W stage back to the producer at
 // once (the bytes are dead), then wait for a free A buffer, dequantise into TMEM and signal the MMA warp.
 template <int kType, int kQ>
 __device__ __forceinline__ void dequant_unit(const uint8_t* blk, int off, uint32_t a_col, uint32_t w_empty_bar,
-                                             uint32_t a_free_bar, uint32_t a_free_parity, uint32_t a_ready_bar, int lane, bool skip) {
+                                             uint32_t a_free_bar, uint32_t a_free_parity, uint32_t a_ready_bar, int lane, bool skip,
+                                             const M4Ctx& mc) {
     using Q = typename QuarterOf<kType, kQ>::type;
     uint32_t raw[Q::kRaw];
     Q::load(blk, off, raw);
@@ -354,7 +422,9 @@ __device__ __forceinline__ void dequant_unit(const uint8_t* blk, int off, uint32
     if (lane == 0) mbar_arrive(w_empty_bar);
     mbar_wait(a_free_bar, a_free_parity);
     tc_fence_after();
-    if (!skip) Q::compute(raw, off, a_col);
+    if (!skip) {
+        if constexpr (kType == kTypeM4) Q::compute(raw, mc, a_col); else Q::compute(raw, off, a_col);
+    }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     __syncwarp();
@@ -397,10 +467,12 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_trigger();         // the next kernel may start its own prologue; it waits for our completion before reading
 
     // ---- stream-K range of this CTA over the flattened (tile, super-block) space -----------------
     const int64_t total = (int64_t)p.n_tiles * p.nsb;
-    const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int64_t u0 = p.whole_tiles ? ((int64_t)p.n_tiles * blockIdx.x / gridDim.x) * p.nsb : total * blockIdx.x / gridDim.x;
+    const int64_t u1 = p.whole_tiles ? ((int64_t)p.n_tiles * (blockIdx.x + 1) / gridDim.x) * p.nsb : total * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == kDequantWarps) {
         // ================================== W PRODUCER (HBM stream) ==============================
@@ -421,13 +493,14 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 // W box start (bytes): Q4_K blocks are 144 B (16-aligned); Q6_K blocks (210 B) start at the block address
                 // rounded down to 16 -- TMA box starts must be 16-byte aligned
                 mbar_expect_tx(w_full(s), C::kWBytes);
-                tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : ((sb * 210) & ~15),
+                tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : (kType == kTypeM4 ? sb * 128 : ((sb * 210) & ~15)),
                             ltile * kTileN, pol_w);
             }
             __syncwarp();
         }
     } else if (warp == kDequantWarps + 1) {
         // ================================== X PRODUCER (L2 resident) =============================
+        pdl_wait();        // activations come from the previous kernel (the weight stream above does not wait: weights are static)
         const bool leader = elect_one();
         uint64_t pol_x;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
@@ -491,6 +564,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     } else {
         // ================================ DEQUANT + EPILOGUE WARPS ================================
         const int qd = warp & 3, qt = warp >> 2;           // TMEM lane quadrant; which quarter (64 weights) of the super-block
+        bool waited = false;
         const int row = qd * 32 + lane;                    // weight row within the tile = TMEM lane
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         int it = 0, seg = 0;
@@ -507,15 +581,18 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const int off = kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15);   // Q6_K: block offset in its window
                 const uint32_t afp = ((it / kABufs) & 1) ^ 1;
                 const bool skip = (p.debug & 2) != 0;
+                const M4Ctx mc{p.scales, p.n[0], p.group_size, (int)(u - tile_begin) * kSB, tile * kTileN + row < p.n[0] ? tile * kTileN + row : 0,
+                               p.out_dtype == B200_BF16};
                 switch (qt) {
-                    case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
-                    case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
-                    case 2: dequant_unit<kType, 2>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
-                    default: dequant_unit<kType, 3>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip); break;
+                    case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
+                    case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
+                    case 2: dequant_unit<kType, 2>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
+                    default: dequant_unit<kType, 3>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                 }
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 6] = clock64();
             }
             // ---- epilogue of the segment: D (TMEM) -> y ------------------------------------------------
+            if (!waited) { pdl_wait(); waited = true; }       // y may still be in use by earlier kernels
             mbar_wait(d_full, seg & 1);
             tc_fence_after();
             const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
@@ -544,7 +621,11 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                         if (mi < p.m) {
                             float* o = ybase + (int64_t)mi * p.ldy + n_idx;
                             const float val = __uint_as_float(acc[i]);
-                            if (whole && !p.accumulate) *o = val;
+                            if (p.out_dtype != B200_F32) {          // marlin: 16-bit output, whole tiles only
+                                const int64_t oi = (int64_t)mi * p.ldy + n_idx;
+                                if (p.out_dtype == B200_BF16) reinterpret_cast<__nv_bfloat16*>(ybase)[oi] = __float2bfloat16_rn(val);
+                                else reinterpret_cast<__half*>(ybase)[oi] = __float2half_rn(val);
+                            } else if (whole && !p.accumulate) *o = val;
                             else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o), "f"(val) : "memory");
                         }
                     }
@@ -586,20 +667,20 @@ void launch(const CUtensorMap* wm, const CUtensorMap& xm, const GemmParams& p, c
     auto kern = qmatmul_tc_kernel<kMB, kType>;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kMB, kType>::kTotal); attr = true; }
-    const int64_t total = (int64_t)p.n_tiles * p.nsb;
+    const int64_t total = p.whole_tiles ? p.n_tiles : (int64_t)p.n_tiles * p.nsb;
     int grid = sm_count();
     if (total < grid) grid = (int)total;
-    kern<<<grid, kThreads, Cfg<kMB, kType>::kTotal, st>>>(wm[0], wm[1], wm[2], xm, p);
+    launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg<kMB, kType>::kTotal, st, wm[0], wm[1], wm[2], xm, p);
     count_launch();
 }
 
 bool make_w_map(CUtensorMap* wm, const void* w, int n, int nsb, int ggml_type) {
     EncodeTiledFn enc = encode_fn();
-    const bool q4 = ggml_type == B200_GGML_Q4_K;
-    // byte tensor [n][nsb * block]; box {144, 128} (Q4_K) or {240, 128} (Q6_K: 210-byte block + alignment slack)
-    const cuuint64_t dims[2] = {(cuuint64_t)nsb * (q4 ? 144 : 210), (cuuint64_t)n};
-    const cuuint64_t strides[1] = {(cuuint64_t)nsb * (q4 ? 144 : 210)};
-    const cuuint32_t box[2] = {(cuuint32_t)(q4 ? 144 : 240), (cuuint32_t)kTileN};
+    const bool q4 = ggml_type == B200_GGML_Q4_K, m4 = ggml_type == kTypeM4;
+    // byte tensor [n][nsb * block]; box {144, 128} (Q4_K), {128, 128} (int4) or {240, 128} (Q6_K: 210-byte block + alignment slack)
+    const cuuint64_t dims[2] = {(cuuint64_t)nsb * (q4 ? 144 : (m4 ? 128 : 210)), (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)nsb * (q4 ? 144 : (m4 ? 128 : 210))};
+    const cuuint32_t box[2] = {(cuuint32_t)(q4 ? 144 : (m4 ? 128 : 240)), (cuuint32_t)kTileN};
     const cuuint32_t es[2] = {1, 1};
     const CUresult r = enc(wm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -655,12 +736,40 @@ void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return; }
     }
-    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
+    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate; p.out_dtype = B200_F32; p.whole_tiles = 0;
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     { static const char* tr = getenv("B200_GEMM_TRACE"); p.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 0)) : nullptr; }
     if (ggml_type == B200_GGML_Q4_K) { if (mb == 32) launch<32, B200_GGML_Q4_K>(wm, xm, p, st); else launch<64, B200_GGML_Q4_K>(wm, xm, p, st); }
     else { if (mb == 32) launch<32, B200_GGML_Q6_K>(wm, xm, p, st); else launch<64, B200_GGML_Q6_K>(wm, xm, p, st); }
     check_launch("qmatmul_tc");
+}
+
+// symmetric int4 x fp16 (marlin_4bit_*): w in the gptq_repack() layout, scales marlin-permuted, 16-bit output
+void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
+               cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error(kErrCuda, "marlin: cuTensorMapEncodeTiled unavailable"); return; }
+    const int nsb = k / 256;
+    const int mb = m <= 32 ? 32 : 64;
+    CUtensorMap wm[kMaxSeg], xm;
+    for (int i = 0; i < kMaxSeg; ++i) if (!make_w_map(&wm[i], w, n, nsb, kTypeM4)) return;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
+        const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+        const cuuint32_t box[2] = {64, (cuuint32_t)mb};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16_k4), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "marlin: activation tensor map failed (%d)", (int)r); return; }
+    }
+    GemmParams p{};
+    const int tiles = (n + kTileN - 1) / kTileN;
+    for (int i = 0; i < kMaxSeg; ++i) { p.y[i] = static_cast<float*>(out); p.n[i] = n; p.tile_end[i] = i == 0 ? tiles : 0x7fffffff; }
+    p.ldy = n; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = 0; p.out_dtype = out_dtype; p.whole_tiles = 1;
+    p.scales = scales; p.group_size = group_size; p.k = k;
+    if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st);
+    check_launch("marlin_tc");
 }
 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,

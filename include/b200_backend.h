@@ -135,6 +135,31 @@ void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32
 /* QTensor::dequantize: W -> f32 [n,k] (linear.rs:808-842 forward_via_dequant) */
 void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggml_type, int64_t stream);
 
+/* ---- K7 / K9: GPTQ -> Marlin int4 weight-only GEMM -- replaces attention_rs::kernels::ffi::{gptq_repack,
+ * marlin_4bit_f16, marlin_4bit_bf16, marlin_awq_4bit_*, awq_repack, gemm_half_q_half_alt} with the reference's exact
+ * signatures (/root/reference/src/backend/gptq.rs:115-197, :313-332).
+ * gptq_repack: qweight u32 [k_packed = K/8, n] (8 nibbles along K per word) -> same word count in this library's
+ *   private int4 layout (the reference reshapes the result to [K/16, 2n], gptq.rs:283-297; only marlin_4bit_* reads it).
+ * marlin_4bit_{f16,bf16}: out[m,n] = x[m,k] . ((q - 8) * scale)^T; scales [k/group, n] in the order produced by the
+ *   reference's marlin_permute_scales (/root/reference/src/openai/models/linear.rs:354-379); qzeros ignored (symmetric),
+ *   g_idx must be NULL; group_size 64 / 128 / -1; m <= 64; k % 256 == 0; n % 64 == 0.  `workspace` (n zeroed u32 of
+ *   locks in Marlin) is unused.  The fp16 copy of x lives in a library-owned scratch buffer, grown outside stream
+ *   capture or handed over once with b200_set_scratch().
+ * AWQ / act-order entry points exist but record an "unsupported" error in this round. */
+void gptq_repack(const void* in, void* out, int32_t k_packed, int32_t n, int64_t stream);
+void awq_repack(const void* in, void* out, int32_t k, int32_t n_packed, int32_t bits, int64_t stream);
+void marlin_4bit_f16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx,
+                     void* out, int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream);
+void marlin_4bit_bf16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx,
+                      void* out, int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream);
+void marlin_awq_4bit_f16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx,
+                         void* out, int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream);
+void marlin_awq_4bit_bf16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx,
+                          void* out, int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream);
+void gemm_half_q_half_alt(const void* x, const uint32_t* qweight, const uint32_t* qzeros, const void* scales,
+                          const int32_t* g_idx, void* out, int32_t m, int32_t n, int32_t k, int32_t bits, int64_t stream);
+void b200_set_scratch(void* device_ptr, size_t bytes);
+
 /* ---- K15 / K21: the elementwise ops between the big ones ------------------------------------
  * rms_norm: candle_nn::ops::rms_norm (layers/qrmsnorm.rs:28-31).  out_dtype F32 or F16. */
 void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int32_t n, float eps,

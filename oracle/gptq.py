@@ -1,0 +1,66 @@
+"""GPTQ / Marlin int4 weight-only GEMM restated in numpy.
+
+Oracle (test infrastructure) -- see ``oracle/__init__.py``.  Formats and host-side transforms follow the
+reference: qweight u32 [K/8, N], 8 nibbles along K per word, LSB first
+(/root/reference/src/openai/models/linear.rs:225-242), scales [K/g, N]; symmetric 4-bit only, group
+size 64 / 128 / -1, no act-order (linear.rs:319-325).  ``marlin_permute_scales`` restates
+linear.rs:341-379; its permutation tables are pinned against the reference's own Python
+(examples/convert_awq_marlin.py:8-17) through tests/golden/marlin_perms.json.  The Marlin kernel itself
+(attention-rs) is not in the tree: w = (q - 8) * scale is the published GPTQ-sym/Marlin convention.
+PARITY UNPINNED for the GEMM values (no reference fixtures).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def get_scale_perms():
+    """linear.rs:341-352 / examples/convert_awq_marlin.py:8-17."""
+    scale_perm = []
+    for i in range(8):
+        scale_perm.extend([i + 8 * j for j in range(8)])
+    scale_perm_single = []
+    for i in range(4):
+        scale_perm_single.extend([2 * i + j for j in [0, 1, 8, 9, 16, 17, 24, 25]])
+    return scale_perm, scale_perm_single
+
+
+def pack_gptq(q: np.ndarray) -> np.ndarray:
+    """q u8 [K, N] in 0..15 -> qweight u32 [K/8, N]; nibble i of word (kp, n) = q[8 kp + i, n]."""
+    K, N = q.shape
+    q = q.astype(np.uint32).reshape(K // 8, 8, N)
+    out = np.zeros((K // 8, N), np.uint32)
+    for i in range(8):
+        out |= q[:, i, :] << np.uint32(4 * i)
+    return out
+
+
+def unpack_gptq(qweight: np.ndarray) -> np.ndarray:
+    Kp, N = qweight.shape
+    q = np.empty((Kp, 8, N), np.uint8)
+    for i in range(8):
+        q[:, i, :] = (qweight >> np.uint32(4 * i)) & 0xF
+    return q.reshape(Kp * 8, N)
+
+
+def marlin_permute_scales(s: np.ndarray, size_k: int, size_n: int, group_size: int) -> np.ndarray:
+    """linear.rs:354-379."""
+    scale_perm, scale_perm_single = get_scale_perms()
+    if group_size != -1 and group_size < size_k:
+        s = s.reshape(-1, len(scale_perm))[:, scale_perm]
+    else:
+        s = s.reshape(-1, len(scale_perm_single))[:, scale_perm_single]
+    return np.ascontiguousarray(s.reshape(-1, size_n))
+
+
+def dequant_gptq(qweight: np.ndarray, scales: np.ndarray, group_size: int) -> np.ndarray:
+    """-> W f64 [N, K] with W[n, k] = (q[k, n] - 8) * scales[k // g, n]  (scales in ORIGINAL order)."""
+    q = unpack_gptq(qweight).astype(np.float64)
+    K, N = q.shape
+    g = K if group_size == -1 else group_size
+    s = np.repeat(np.asarray(scales, np.float64), g, axis=0)[:K]
+    return ((q - 8.0) * s).T
+
+
+def gptq_matmul(x: np.ndarray, qweight: np.ndarray, scales: np.ndarray, group_size: int) -> np.ndarray:
+    return (np.asarray(x, np.float64) @ dequant_gptq(qweight, scales, group_size).T).astype(np.float32)

@@ -56,3 +56,21 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def marlin_perms():
+    """tests/golden/marlin_perms.json: the scale permutation tables produced by EXECUTING the reference's own
+    Python (`get_scale_perms`, /root/reference/examples/convert_awq_marlin.py:8-17; the function source is
+    extracted with `ast` because the module imports safetensors)."""
+    import ast
+    src = open("/root/reference/examples/convert_awq_marlin.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_scale_perms"][0]
+    ns = {"List": list}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref", "exec"), ns)
+    sp, sps = ns["get_scale_perms"]()
+    with open(os.path.join(HERE, "marlin_perms.json"), "w") as f:
+        json.dump({"scale_perm": sp, "scale_perm_single": sps, "source": "examples/convert_awq_marlin.py:8-17 (executed)"}, f)
+
+
+if __name__ == "__main__" and os.path.exists("/root/reference/examples/convert_awq_marlin.py"):
+    marlin_perms()
