@@ -259,7 +259,7 @@ struct Q4KQuarter {
 // nibbles are k = 0..31 and high nibbles k = 32..63 of the chunk -- the same nibble geometry as a Q4_K chunk, so the
 // subnormal-placement + HFMA2 trick applies unchanged: w = s*q - 8*s with one per-group scale s
 // (/root/reference/src/backend/gptq.rs:115-178 call site; scales arrive marlin-permuted, linear.rs:341-379).
-struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16; };
+struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg; };
 __device__ __forceinline__ int marlin_scale_pos(int n, bool grouped) {
     // inverse of marlin_permute_scales: position of original column n inside its permuted block
     if (grouped) { const int b = n & 63; return (n & ~63) | (8 * (b & 7) + (b >> 3)); }
@@ -418,6 +418,10 @@ __device__ __forceinline__ void dequant_unit(const uint8_t* blk, int off, uint32
     using Q = typename QuarterOf<kType, kQ>::type;
     uint32_t raw[Q::kRaw];
     Q::load(blk, off, raw);
+    // Cross-proxy WAR: our generic-proxy reads (LDS) must be ordered before the TMA (async proxy) refill that the
+    // arrive below unblocks.  Without this fence the int4 path read refilled stages (observed on B200: units whose
+    // a_free wait is long got the NEXT round's bytes); mbarrier release/acquire alone does not order the two proxies.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(w_empty_bar);
     mbar_wait(a_free_bar, a_free_parity);
@@ -582,7 +586,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const uint32_t afp = ((it / kABufs) & 1) ^ 1;
                 const bool skip = (p.debug & 2) != 0;
                 const M4Ctx mc{p.scales, p.n[0], p.group_size, (int)(u - tile_begin) * kSB, tile * kTileN + row < p.n[0] ? tile * kTileN + row : 0,
-                               p.out_dtype == B200_BF16};
+                               p.out_dtype == B200_BF16, p.debug};
                 switch (qt) {
                     case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                     case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
@@ -768,6 +772,7 @@ void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* ou
     for (int i = 0; i < kMaxSeg; ++i) { p.y[i] = static_cast<float*>(out); p.n[i] = n; p.tile_end[i] = i == 0 ? tiles : 0x7fffffff; }
     p.ldy = n; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = 0; p.out_dtype = out_dtype; p.whole_tiles = 1;
     p.scales = scales; p.group_size = group_size; p.k = k;
+    { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st);
     check_launch("marlin_tc");
 }
