@@ -322,7 +322,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
     if cfg.num_layers != 32:
         line["invalid"] = "debug run with fewer layers"
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         tps, t_step, info = cpu_decode_sample(B, args.ctx, args.cpu_seconds)
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, **info}
     print(json.dumps(line), flush=True)
