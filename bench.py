@@ -280,14 +280,15 @@ def run_b200(args):
     nxt = model.read_next_tokens(B)
     h2d = B * (8 + 8 + 8 + 4) + B * blocks_per_seq * 4
     d2h = B * 4
+    tables_np = np.asarray(tables, np.int32)              # rectangular tables: prepare_decode's vectorised path
     for _ in range(min(W, 3)):
-        prep = pkg.prepare_decode([cur] * B, [int(t) for t in nxt], tables, bs)
+        prep = pkg.prepare_decode(np.full(B, cur), nxt, tables_np, bs)
         nxt, _ = model.decode(prep); cur += 1
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(K):
-        prep = pkg.prepare_decode([cur] * B, [int(t) for t in nxt], tables, bs)     # host: block tables, slots
+        prep = pkg.prepare_decode(np.full(B, cur), nxt, tables_np, bs)              # host: block tables, slots
         nxt, _ = model.decode(prep); cur += 1                                       # H2D + replay + D2H + sync
     e1.record(stream)
     barrier()

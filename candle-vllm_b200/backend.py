@@ -347,6 +347,28 @@ class QMatMul:
         check("QMatMul.forward")
         return y.reshape(*lead, n)
 
+    def forward_slabs(self, x: torch.Tensor) -> torch.Tensor:
+        """Atomic-free form the fused decode layer uses (``qmatmul_f16act_slabs``): returns ``[S, m, n]`` partial sums whose
+        sum over S is the product; S = 1 when no tile is split.  Bitwise deterministic."""
+        _cuda(x, "x"); require_device()
+        n, k = self.w.shape
+        if x.dim() != 2 or x.shape[-1] != k:
+            raise BackendError(f"QMatMul: shape mismatch, x {tuple(x.shape)} vs weight {self.w.shape}")
+        L = lib()
+        m = x.shape[0]
+        L.qmatmul_slab_count.restype = C.c_int32
+        L.qmatmul_f16act_slabs.restype = C.c_int32
+        s_max = int(L.qmatmul_slab_count(C.c_int32(m), C.c_int32(n), C.c_int32(k), C.c_int32(self.w.ggml_type)))
+        y = torch.full((max(s_max, 1), m, n), float("nan"), dtype=torch.float32, device=x.device)    # every element must be overwritten
+        with torch.cuda.device(x.device):
+            x2 = x.contiguous().half()
+            xk4 = torch.empty_like(x2)
+            L.cast(_ptr(x2), _ptr(xk4), C.c_int64(x2.numel()), C.c_int32(DType.F16), C.c_int32(DType.F16_K4), _stream(x.device))
+            got = int(L.qmatmul_f16act_slabs(_ptr(xk4), _ptr(self.w.data), _ptr(y), C.c_int32(y.shape[0]), C.c_int32(m), C.c_int32(n),
+                                             C.c_int32(k), C.c_int32(self.w.ggml_type), _stream(x.device)))
+        check("QMatMul.forward_slabs")
+        return y[:got]
+
 
 # ---------------------------------------------------------------------------------------------
 # small ops

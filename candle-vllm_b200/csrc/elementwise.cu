@@ -218,16 +218,19 @@ argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int n)
     }
 }
 
-// tensor-parallel greedy sampling: pairs[row] = (max logit, global index) over this rank's vocab shard
-__global__ void __launch_bounds__(1024)
+// stage 1 of greedy sampling: pairs[chunk][row] = (max logit, global index) over column chunk blockIdx.y of this rank's vocab
+// shard.  Stage 2 (argmax_reduce_pairs_kernel) reduces over chunks -- and, tensor-parallel, over the ranks' gathered pairs.
+__global__ void __launch_bounds__(256)
 argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int n, int index_offset) {
     pdl_wait();
     pdl_trigger();
-    const int row = blockIdx.x;
+    const int row = blockIdx.x, rows = gridDim.x;
+    const int per = (((n + (int)gridDim.y - 1) / (int)gridDim.y) + 3) & ~3;
+    const int c0 = blockIdx.y * per, c1 = min(n, c0 + per);
     const float* xr = x + (int64_t)row * n;
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
         const float v = xr[i];
         if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
@@ -250,7 +253,8 @@ argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int 
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (threadIdx.x == 0) pairs[row] = make_float2(best, __int_as_float((bi == 0x7fffffff ? 0 : bi) + index_offset));
+        // an empty chunk reports (-inf, INT_MAX): it loses every comparison in stage 2
+        if (threadIdx.x == 0) pairs[(int64_t)blockIdx.y * rows + row] = make_float2(best, __int_as_float(bi == 0x7fffffff ? bi : bi + index_offset));
     }
 }
 
@@ -267,11 +271,11 @@ __global__ void argmax_reduce_pairs_kernel(const float2* __restrict__ gathered, 
         const int idx = __float_as_int(pr.y);
         if (pr.x > best || (pr.x == best && idx < bi)) { best = pr.x; bi = idx; }
     }
-    out[row] = bi;
+    out[row] = bi == 0x7fffffff ? 0 : bi;
 }
 
-void argmax_pairs(const float* logits, void* pairs, int rows, int n, int index_offset, cudaStream_t st) {
-    launch_pdl(argmax_pair_kernel, dim3(rows), dim3(1024), 0, st, logits, static_cast<float2*>(pairs), n, index_offset);
+void argmax_pairs(const float* logits, void* pairs, int rows, int n, int chunks, int index_offset, cudaStream_t st) {
+    launch_pdl(argmax_pair_kernel, dim3(rows, chunks), dim3(256), 0, st, logits, static_cast<float2*>(pairs), n, index_offset);
     count_launch();
     check_launch("argmax_pairs");
 }

@@ -26,7 +26,7 @@ extern "C" long long b200_total_kernel_launches(void);
 namespace b200 {
 void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st);
 void tp_allgather_bytes(void* comm, const void* src, void* dst, size_t bytes_per_rank, cudaStream_t st);
-void argmax_pairs(const float* logits, void* pairs, int rows, int n, int index_offset, cudaStream_t st);
+void argmax_pairs(const float* logits, void* pairs, int rows, int n, int chunks, int index_offset, cudaStream_t st);
 void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st);
 }
 
@@ -45,6 +45,7 @@ struct b200_llama {
     int heads_l, kv_l, ffn_l, vocab_l, qkv_row;
 
     // static device buffers (graph.rs: static input buffers sized for max batch)
+    char* d_meta = nullptr;                                      // one slab: tokens | positions | slots | ctx | tables
     int64_t* d_tokens = nullptr; int64_t* d_positions = nullptr; int64_t* d_slots = nullptr;
     uint32_t* d_ctx = nullptr; uint32_t* d_tables = nullptr;
     float* x = nullptr; __half* xn = nullptr; float* qkv = nullptr; __nv_bfloat16* q16 = nullptr;
@@ -104,6 +105,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
     const int H = c.hidden, hd = c.head_dim;
     const int qd = m->heads_l * hd, kd = m->kv_l * hd;
     const long long n0 = b200_total_kernel_launches();
+    constexpr int kArgmaxChunks = 16;
     embedding_f32(m->tok_embeddings, m->d_tokens, m->x, B, H, s);
     for (int l = 0; l < c.num_layers; ++l) {
         const b200_llama_layer& w = m->layers[l];
@@ -153,13 +155,14 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
         launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
     }
     qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
+    // greedy sampling in two stages; vocab-parallel lm_head (distributed.rs:1632-1667): gather (max, global index) pairs
+    // instead of the logits
+    argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, kArgmaxChunks, c.tp_rank * m->vocab_l, st);
     if (c.tp_world == 1) {
-        argmax_f32(m->logits, m->next_tokens, B, m->vocab_l, s);
+        argmax_reduce_pairs(m->tp_pairs, m->next_tokens, B, kArgmaxChunks, st);
     } else {
-        // vocab-parallel lm_head (distributed.rs:1632-1667): gather (max, global index) pairs instead of the logits
-        argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, c.tp_rank * m->vocab_l, st);
-        tp_allgather_bytes(m->comm, m->tp_pairs, m->tp_gathered, (size_t)B * 8, st);
-        argmax_reduce_pairs(m->tp_gathered, m->next_tokens, B, c.tp_world, st);
+        tp_allgather_bytes(m->comm, m->tp_pairs, m->tp_gathered, (size_t)B * kArgmaxChunks * 8, st);
+        argmax_reduce_pairs(m->tp_gathered, m->next_tokens, B, c.tp_world * kArgmaxChunks, st);
     }
     return (int)(b200_total_kernel_launches() - n0);
 }
@@ -231,12 +234,20 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
     m->vocab_l = c.vocab / c.tp_world;
     m->qkv_row = (m->heads_l + 2 * m->kv_l) * c.head_dim;
     const size_t B = c.max_num_seqs;
-    bool ok = dmalloc(m->d_tokens, B) && dmalloc(m->d_positions, B) && dmalloc(m->d_slots, B) && dmalloc(m->d_ctx, B) &&
-              dmalloc(m->d_tables, B * c.max_blocks_per_seq) && dmalloc(m->x, B * c.hidden) && dmalloc(m->xn, B * c.hidden) &&
+    constexpr size_t kChunks = 16;
+    // step metadata lives in ONE device slab with the layout of the pinned staging slab: one H2D copy per step
+    const size_t Bp = (B + 3) & ~(size_t)3;
+    m->stage_bytes = Bp * (8 + 8 + 8 + 4) + B * c.max_blocks_per_seq * 4 + 64;
+    bool ok = dmalloc(m->d_meta, m->stage_bytes);
+    if (ok) {
+        m->d_tokens = reinterpret_cast<int64_t*>(m->d_meta); m->d_positions = m->d_tokens + Bp; m->d_slots = m->d_positions + Bp;
+        m->d_ctx = reinterpret_cast<uint32_t*>(m->d_slots + Bp); m->d_tables = m->d_ctx + Bp;
+    }
+    ok = ok && dmalloc(m->x, B * c.hidden) && dmalloc(m->xn, B * c.hidden) &&
               dmalloc(m->qkv, B * m->qkv_row) && dmalloc(m->q16, B * m->heads_l * c.head_dim) &&
               dmalloc(m->attn16, B * m->heads_l * c.head_dim) && dmalloc(m->gate, B * m->ffn_l) && dmalloc(m->up, B * m->ffn_l) &&
               dmalloc(m->act16, B * m->ffn_l) && dmalloc(m->partial, B * c.hidden) && dmalloc(m->logits, B * m->vocab_l) &&
-              dmalloc(m->next_tokens, B) && dmalloc(m->tp_pairs, B * 2) && dmalloc(m->tp_gathered, B * 2 * c.tp_world);
+              dmalloc(m->next_tokens, B) && dmalloc(m->tp_pairs, B * 2 * kChunks) && dmalloc(m->tp_gathered, B * 2 * kChunks * c.tp_world);
     m->attn_ws_bytes = paged_attention_decode_workspace_bytes((int)B, m->heads_l, c.head_dim, c.max_blocks_per_seq, c.block_size);
     char* ws = nullptr;
     ok = ok && dmalloc(ws, m->attn_ws_bytes);
@@ -257,7 +268,6 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
         cudaMemcpy(m->cos_t, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(m->sin_t, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
     }
-    m->stage_bytes = B * (8 + 8 + 8 + 4) + B * c.max_blocks_per_seq * 4 + 64;
     ok = ok && cudaMallocHost((void**)&m->h_stage, m->stage_bytes) == cudaSuccess &&
          cudaMallocHost((void**)&m->h_next, B * 4) == cudaSuccess;
     if (!ok) {
@@ -272,7 +282,7 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
 void b200_llama_destroy(b200_llama* m) {
     if (!m) return;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
-    void* ptrs[] = {m->d_tokens, m->d_positions, m->d_slots, m->d_ctx, m->d_tables, m->x, m->xn, m->qkv, m->q16, m->attn16,
+    void* ptrs[] = {m->d_meta, m->x, m->xn, m->qkv, m->q16, m->attn16,
                     m->gate, m->up, m->act16, m->partial, m->logits, m->next_tokens, m->cos_t, m->sin_t, m->attn_ws, m->tp_pairs, m->tp_gathered};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->h_stage) cudaFreeHost(m->h_stage);
@@ -318,24 +328,21 @@ void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* pos
                  "b200_llama_decode: block table width %d out of (0, %d]", table_width, c.max_blocks_per_seq);
     cudaStream_t st = as_stream(stream);
     const int B = num_seqs, W = c.max_blocks_per_seq;
-    // stage into pinned memory; block tables are re-padded with zeros to the static width (graph.rs:732-738)
-    char* p = m->h_stage;
-    int64_t* h_tok = (int64_t*)p; p += 8 * B;
-    int64_t* h_pos = (int64_t*)p; p += 8 * B;
-    int64_t* h_slot = (int64_t*)p; p += 8 * B;
-    uint32_t* h_ctx = (uint32_t*)p; p += 4 * B;
-    uint32_t* h_tab = (uint32_t*)p;
+    // stage into pinned memory (same layout as the device slab); block tables are re-padded with zeros to the static
+    // width (graph.rs:732-738)
+    const size_t Bp = ((size_t)c.max_num_seqs + 3) & ~(size_t)3;
+    int64_t* h_tok = (int64_t*)m->h_stage;
+    int64_t* h_pos = h_tok + Bp;
+    int64_t* h_slot = h_pos + Bp;
+    uint32_t* h_ctx = (uint32_t*)(h_slot + Bp);
+    uint32_t* h_tab = h_ctx + Bp;
     for (int b = 0; b < B; ++b) {
         B200_REQUIRE(tokens[b] < (uint32_t)c.vocab, kErrBadArg, "b200_llama_decode: token id %u >= vocab", tokens[b]);
         B200_REQUIRE(positions[b] >= 0 && positions[b] < c.max_pos, kErrBadArg, "b200_llama_decode: position out of range");
         h_tok[b] = tokens[b]; h_pos[b] = positions[b]; h_slot[b] = slot_mapping[b]; h_ctx[b] = context_lens[b];
         for (int j = 0; j < W; ++j) h_tab[(size_t)b * W + j] = j < table_width ? block_tables[(size_t)b * table_width + j] : 0u;
     }
-    cudaMemcpyAsync(m->d_tokens, h_tok, 8 * B, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(m->d_positions, h_pos, 8 * B, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(m->d_slots, h_slot, 8 * B, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(m->d_ctx, h_ctx, 4 * B, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(m->d_tables, h_tab, (size_t)4 * B * W, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(m->d_meta, m->h_stage, (size_t)((char*)(h_tab + (size_t)B * W) - m->h_stage), cudaMemcpyHostToDevice, st);
     run_step(m, B, st);
     if (logits_host) cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->vocab_l * 4, cudaMemcpyDeviceToHost, st);
     if (next_tokens_host) {

@@ -22,11 +22,19 @@ void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
                 int accumulate, cudaStream_t st);
 
-// several weight matrices (same type / k) on one activation in one launch; falls back to separate launches
-void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
-                      int ggml_type, int accumulate, cudaStream_t st);
+// several weight matrices (same type / k) on one activation in one launch.  slabs_avail > 0 selects slab mode: split tiles
+// write partial sums to y[i] + s * slab_stride, s < (return value); the caller's consumer adds the slabs up.
+int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
+                     int ggml_type, int accumulate, int slabs_avail, int64_t slab_stride, cudaStream_t st);
+int qmatmul_tc_slab_count(int64_t n_tiles, int nsb);
+// legacy (accumulating) form; falls back to separate launches
 void qmatmul_dispatch_multi(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
                             int64_t ldy, int m, int k, int accumulate, cudaStream_t st);
+// slab form: returns how many slabs hold partial sums (1 when the product went to slab 0 whole); never reads y
+int qmatmul_dispatch_slabs(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
+                           int64_t ldy, int m, int k, int slabs_avail, int64_t slab_stride, cudaStream_t st);
+// slabs qmatmul_dispatch_slabs may need for these shapes
+int qmatmul_slabs_needed(int nseg, const int* n, const int* types, int m, int k);
 
 // symmetric int4 (GPTQ, repacked by gptq_repack) x fp16 activations in K4 order -> 16-bit out; m <= 64, k % 256 == 0
 void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,

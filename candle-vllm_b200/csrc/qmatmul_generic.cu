@@ -101,12 +101,30 @@ void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, i
     else qmatmul_generic(x_f16, true, w, y, ldy, m, n, k, ggml_type, accumulate, st);
 }
 
-void qmatmul_dispatch_multi(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
-                            int64_t ldy, int m, int k, int accumulate, cudaStream_t st) {
+static bool can_fuse(int nseg, const int* types, const int* n, int m, int k) {
     bool fuse = nseg >= 1 && nseg <= 3;
     for (int i = 0; i < nseg && fuse; ++i) fuse = types[i] == types[0] && qmatmul_tc_supported(m, n[i], k, types[i]);
-    if (fuse) { qmatmul_tc_multi(x_f16, nseg, w, y, n, ldy, m, k, types[0], accumulate, st); return; }
+    return fuse;
+}
+
+void qmatmul_dispatch_multi(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
+                            int64_t ldy, int m, int k, int accumulate, cudaStream_t st) {
+    if (can_fuse(nseg, types, n, m, k)) { qmatmul_tc_multi(x_f16, nseg, w, y, n, ldy, m, k, types[0], accumulate, 0, 0, st); return; }
     for (int i = 0; i < nseg; ++i) qmatmul_dispatch(x_f16, w[i], y[i], ldy, m, n[i], k, types[i], accumulate, st);
+}
+
+int qmatmul_slabs_needed(int nseg, const int* n, const int* types, int m, int k) {
+    if (!can_fuse(nseg, types, n, m, k)) return 1;
+    int64_t tiles = 0;
+    for (int i = 0; i < nseg; ++i) tiles += (n[i] + 127) / 128;
+    return qmatmul_tc_slab_count(tiles, k / 256);
+}
+
+int qmatmul_dispatch_slabs(const void* x_f16, int nseg, const void* const* w, const int* types, float* const* y, const int* n,
+                           int64_t ldy, int m, int k, int slabs_avail, int64_t slab_stride, cudaStream_t st) {
+    if (can_fuse(nseg, types, n, m, k)) return qmatmul_tc_multi(x_f16, nseg, w, y, n, ldy, m, k, types[0], 0, slabs_avail, slab_stride, st);
+    for (int i = 0; i < nseg; ++i) qmatmul_generic(x_f16, true, w[i], y[i], ldy, m, n[i], k, types[i], 0, st);   // whole product -> slab 0
+    return 1;
 }
 
 }  // namespace b200
@@ -136,6 +154,19 @@ void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32
     if (!accumulate && qmatmul_tc_supported(m, n, k, ggml_type) && qmatmul_tc_needs_zeroed_output(n, k))
         cudaMemsetAsync(y, 0, (size_t)m * n * sizeof(float), as_stream(stream));
     qmatmul_dispatch(x_f16, w, y, n, m, n, k, ggml_type, accumulate, as_stream(stream));
+}
+
+int32_t qmatmul_slab_count(int32_t m, int32_t n, int32_t k, int32_t ggml_type) {
+    if (m <= 0 || n <= 0 || k <= 0) return 0;
+    return qmatmul_slabs_needed(1, &n, &ggml_type, m, k);
+}
+
+int32_t qmatmul_f16act_slabs(const void* x_f16, const void* w, float* y_slabs, int32_t slabs_avail, int32_t m, int32_t n,
+                             int32_t k, int32_t ggml_type, int64_t stream) {
+    if (m == 0 || n == 0) return 0;
+    if (!qmm_check("qmatmul_f16act_slabs", x_f16, w, y_slabs, m, n, k, ggml_type)) return 0;
+    if (slabs_avail < 1) { set_error(kErrBadArg, "qmatmul_f16act_slabs: slabs_avail = %d", slabs_avail); return 0; }
+    return qmatmul_dispatch_slabs(x_f16, 1, &w, &ggml_type, &y_slabs, &n, n, m, k, slabs_avail, (int64_t)m * n, as_stream(stream));
 }
 
 void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, int32_t k,

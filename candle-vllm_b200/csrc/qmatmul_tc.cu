@@ -172,6 +172,8 @@ struct GemmParams {
     int accumulate;
     int out_dtype;                 // B200_F32 (GGUF paths) or B200_F16 / B200_BF16 (marlin: plain stores, whole tiles only)
     int whole_tiles;               // 1: CTA ranges are whole tiles (no split-K, no atomics)
+    int slabs;                     // > 0: split tiles write their partial sums to DISTINCT slabs (plain stores, no atomics, no
+    int64_t slab_stride;           //      pre-zeroed output): slab s of segment sg starts at y[sg] + s * slab_stride; the consumer sums
     const void* scales;            // marlin: [K/g, N] in marlin-permuted order, dtype = out_dtype
     int group_size, k;             // marlin
     long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
@@ -341,34 +343,46 @@ __device__ __forceinline__ void realign(const uint32_t (&t)[57], int wo, int sh1
 template <int kGp>      // kGp = 0: groups 0 (lo nibble) and 2 (hi nibble) from ql[0..31]; kGp = 1: groups 1, 3
 __device__ __forceinline__ void dequant_q6k_pair(const uint32_t (&ql)[8], uint32_t a_col, const uint32_t (&qh)[8],
                                                  const uint32_t (&scw)[2], float dk, bool fast) {
+    // `fast` is warp-uniform; the two paths are separate straight-line blocks (a per-word branch interleaves them in the
+    // instruction stream and the kernel then stalls on instruction fetch: ncu showed stall_no_inst on every line)
 #pragma unroll
     for (int hi = 0; hi < 2; ++hi) {
         const int g = kGp + 2 * hi;             // group index 0..3 within the half
-        uint32_t v[16];
+        __half2 sh[2], nh[2];                   // scale / offset of the two 16-weight sub-groups
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int sidx = 2 * g + (i >> 2);                                  // scale index within this half
-            const int sc = (int)(int8_t)(((sidx < 4 ? scw[0] : scw[1]) >> (8 * (sidx & 3))) & 0xff);
-            const float s = dk * (float)sc;
-            const uint32_t lw = hi ? (ql[i] >> 4) : ql[i];                      // nibbles now at bits 0-3 of every byte
-            const uint32_t hw = qh[i] >> (2 * g);                               // 2 high bits now at bits 0-1 of every byte
-            const __half2 sh = __float2half2_rn(s);
-            if (fast) {
-                const __half2 nh = __float2half2_rn(-32.f * (__low2float(sh) * (1.f / 1048576.f)));   // q = 32 -> exactly 0
-                uint32_t t0 = ((lw << 4) & 0x00f000f0u) | ((hw << 8) & 0x03000300u);    // bytes (0,2)
-                uint32_t t1 = ((lw >> 4) & 0x00f000f0u) | (hw & 0x03000300u);           // bytes (1,3)
-                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), sh, nh);
-                const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), sh, nh);
+        for (int j = 0; j < 2; ++j) {
+            const int sidx = 2 * g + j;
+            const int sc = (int)(int8_t)((scw[sidx >> 2] >> (8 * (sidx & 3))) & 0xff);
+            sh[j] = __float2half2_rn(dk * (float)sc);
+            // q = 32 must give exactly 0: the offset is derived from the ROUNDED scale
+            nh[j] = __float2half2_rn(-32.f * (fast ? __low2float(sh[j]) * (1.f / 1048576.f) : __low2float(sh[j])));
+        }
+        uint32_t v[16];
+        if (fast) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                // 6-bit value -> fp16 mantissa bits 4-9 (= q * 2^-20): low nibble at bits 4-7, the two qh bits at bits 8-9
+                const uint32_t l0 = hi ? ql[i] : (ql[i] << 4);                    // bytes (0,2)
+                const uint32_t l1 = hi ? (ql[i] >> 8) : (ql[i] >> 4);             // bytes (1,3)
+                const uint32_t h0 = qh[i] << (8 - 2 * g), h1 = qh[i] >> (2 * g);
+                uint32_t t0 = (l0 & 0x00f000f0u) | (h0 & 0x03000300u);
+                uint32_t t1 = (l1 & 0x00f000f0u) | (h1 & 0x03000300u);
+                const __half2 r0 = __hfma2(*reinterpret_cast<__half2*>(&t0), sh[i >> 2], nh[i >> 2]);
+                const __half2 r1 = __hfma2(*reinterpret_cast<__half2*>(&t1), sh[i >> 2], nh[i >> 2]);
                 v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
                 v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
-            } else {
-                const __half2 nh = __float2half2_rn(-32.f * __low2float(sh));
-                const uint32_t magic = 0x64006400u;
-                const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+            }
+        } else {
+            const uint32_t magic = 0x64006400u;
+            const __half2 k1024 = *reinterpret_cast<const __half2*>(&magic);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t lw = hi ? (ql[i] >> 4) : ql[i];                      // nibbles now at bits 0-3 of every byte
+                const uint32_t hw = qh[i] >> (2 * g);                               // 2 high bits now at bits 0-1 of every byte
                 uint32_t t0 = (lw & 0x000f000fu) | ((hw << 4) & 0x00300030u) | magic;
                 uint32_t t1 = ((lw >> 8) & 0x000f000fu) | ((hw >> 4) & 0x00300030u) | magic;
-                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), sh, nh);
-                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), sh, nh);
+                const __half2 r0 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t0), k1024), sh[i >> 2], nh[i >> 2]);
+                const __half2 r1 = __hfma2(__hsub2(*reinterpret_cast<__half2*>(&t1), k1024), sh[i >> 2], nh[i >> 2]);
                 v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
                 v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
             }
@@ -602,7 +616,13 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
             const int sg = seg_of_tile(p, tile);
             const int n_idx = (tile - seg_first_tile(p, sg)) * kTileN + row;
-            float* const ybase = sg == 0 ? p.y[0] : (sg == 1 ? p.y[1] : p.y[2]);
+            float* ybase = sg == 0 ? p.y[0] : (sg == 1 ? p.y[1] : p.y[2]);
+            // slab mode: the k-th CTA that works on a tile writes slab k.  CTA b owns units [total*b/grid, total*(b+1)/grid),
+            // so the owner of unit u is ((u+1)*grid - 1) / total and only a CTA's first segment can start inside a tile.
+            int ordinal = 0;
+            if (p.slabs > 0 && seg_begin != tile_begin) ordinal = (int)blockIdx.x - (int)(((tile_begin + 1) * gridDim.x - 1) / total);
+            if (p.slabs > 0) ybase += (int64_t)ordinal * p.slab_stride;
+            const int zero_slabs = (p.slabs > 0 && seg_end == tile_end) ? p.slabs - 1 - ordinal : 0;   // slabs nobody else writes
             const int n_rows = sg == 0 ? p.n[0] : (sg == 1 ? p.n[1] : p.n[2]);
             constexpr int kColsPerWarp = kMB / 4;                 // this warp's share of the batch columns (8 or 16)
 #pragma unroll
@@ -629,6 +649,9 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                                 const int64_t oi = (int64_t)mi * p.ldy + n_idx;
                                 if (p.out_dtype == B200_BF16) reinterpret_cast<__nv_bfloat16*>(ybase)[oi] = __float2bfloat16_rn(val);
                                 else reinterpret_cast<__half*>(ybase)[oi] = __float2half_rn(val);
+                            } else if (p.slabs > 0) {
+                                *o = val;
+                                for (int z = 1; z <= zero_slabs; ++z) o[(int64_t)z * p.slab_stride] = 0.f;
                             } else if (whole && !p.accumulate) *o = val;
                             else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(o), "f"(val) : "memory");
                         }
@@ -666,14 +689,21 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// CTAs of a launch.  Slab mode keeps >= nsb/8 units per CTA so that at most 9 CTAs (= slabs) ever share one tile.
+int gemm_grid(int64_t n_tiles, int nsb, bool whole_tiles, bool slab_mode) {
+    const int64_t total = whole_tiles ? n_tiles : n_tiles * nsb;
+    int64_t grid = sm_count();
+    if (total < grid) grid = total;
+    if (slab_mode && !whole_tiles && n_tiles * 8 < grid) grid = n_tiles * 8;
+    return (int)grid;
+}
+
 template <int kMB, int kType>
 void launch(const CUtensorMap* wm, const CUtensorMap& xm, const GemmParams& p, cudaStream_t st) {
     auto kern = qmatmul_tc_kernel<kMB, kType>;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kMB, kType>::kTotal); attr = true; }
-    const int64_t total = p.whole_tiles ? p.n_tiles : (int64_t)p.n_tiles * p.nsb;
-    int grid = sm_count();
-    if (total < grid) grid = (int)total;
+    const int grid = gemm_grid(p.n_tiles, p.nsb, p.whole_tiles != 0, p.slabs > 0);
     launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg<kMB, kType>::kTotal, st, wm[0], wm[1], wm[2], xm, p);
     count_launch();
 }
@@ -701,23 +731,42 @@ bool qmatmul_tc_supported(int m, int n, int k, int ggml_type) {
     return false;
 }
 
+// Decomposition: with many tiles per SM every CTA gets whole tiles (no split); otherwise stream-K over (tile, super-block).
+static bool use_whole_tiles(int64_t n_tiles) { return n_tiles >= 4 * (int64_t)sm_count(); }
+
 // true when some output tile is produced by more than one CTA (or accumulate): y must then hold the
 // addend (zeros for a plain product) before the launch
 bool qmatmul_tc_needs_zeroed_output(int n, int k) {
     const int64_t n_tiles = (n + kTileN - 1) / kTileN, nsb = k / 256, total = n_tiles * nsb;
+    if (use_whole_tiles(n_tiles)) return false;
     const int64_t grid = total < sm_count() ? total : sm_count();
     for (int64_t c = 1; c < grid; ++c)
         if ((total * c / grid) % nsb != 0) return true;
     return false;
 }
 
-// up to kMaxSeg weight matrices (same type, same k) applied to one activation in one launch
-void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
-                      int ggml_type, int accumulate, cudaStream_t st) {
+// slab mode: how many slabs the decomposition writes for n_tiles tiles of nsb super-blocks (max CTAs sharing one tile)
+int qmatmul_tc_slab_count(int64_t n_tiles, int nsb) {
+    if (n_tiles <= 0 || nsb <= 0 || use_whole_tiles(n_tiles)) return 1;
+    const int64_t total = n_tiles * nsb, grid = gemm_grid(n_tiles, nsb, false, true);
+    int mx = 1;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const int64_t first = ((t * nsb + 1) * grid - 1) / total, last = ((t + 1) * nsb * grid - 1) / total;
+        if ((int)(last - first + 1) > mx) mx = (int)(last - first + 1);
+    }
+    return mx;
+}
+
+// up to kMaxSeg weight matrices (same type, same k) applied to one activation in one launch.
+// slabs_avail = 0: y receives the product (split tiles red.add into it: see qmatmul_tc_needs_zeroed_output).
+// slabs_avail > 0: split tiles store their partial sums to distinct slabs y[sg] + s * slab_stride (plain stores, nothing to
+// pre-zero, bitwise deterministic); returns the number of slabs the consumer has to add up.
+int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
+                     int ggml_type, int accumulate, int slabs_avail, int64_t slab_stride, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
-    if (!enc) { set_error(kErrCuda, "qmatmul: cuTensorMapEncodeTiled unavailable"); return; }
-    if (nseg < 1 || nseg > kMaxSeg) { set_error(kErrBadArg, "qmatmul: %d segments (max %d)", nseg, kMaxSeg); return; }
-    if ((uintptr_t)x_f16 & 15) { set_error(kErrBadArg, "qmatmul: x must be 16-byte aligned"); return; }
+    if (!enc) { set_error(kErrCuda, "qmatmul: cuTensorMapEncodeTiled unavailable"); return 0; }
+    if (nseg < 1 || nseg > kMaxSeg) { set_error(kErrBadArg, "qmatmul: %d segments (max %d)", nseg, kMaxSeg); return 0; }
+    if ((uintptr_t)x_f16 & 15) { set_error(kErrBadArg, "qmatmul: x must be 16-byte aligned"); return 0; }
     const int nsb = k / 256;
     const int mb = m <= 32 ? 32 : 64;
     CUtensorMap wm[kMaxSeg], xm;
@@ -725,8 +774,8 @@ void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* 
     int tiles = 0;
     for (int i = 0; i < kMaxSeg; ++i) {
         const int j = i < nseg ? i : nseg - 1;               // unused slots alias the last segment
-        if ((uintptr_t)w[j] & 15) { set_error(kErrBadArg, "qmatmul: w must be 16-byte aligned"); return; }
-        if (!make_w_map(&wm[i], w[j], n[j], nsb, ggml_type)) return;
+        if ((uintptr_t)w[j] & 15) { set_error(kErrBadArg, "qmatmul: w must be 16-byte aligned"); return 0; }
+        if (!make_w_map(&wm[i], w[j], n[j], nsb, ggml_type)) return 0;
         if (i < nseg) tiles += (n[i] + kTileN - 1) / kTileN;
         p.y[i] = y[j]; p.n[i] = n[j]; p.tile_end[i] = i < nseg ? tiles : 0x7fffffff;
     }
@@ -738,14 +787,22 @@ void qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* 
         CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return; }
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return 0; }
     }
-    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate; p.out_dtype = B200_F32; p.whole_tiles = 0;
+    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate; p.out_dtype = B200_F32;
+    p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
+    if (slabs_avail > 0) {
+        p.slabs = qmatmul_tc_slab_count(tiles, nsb);
+        p.slab_stride = slab_stride;
+        p.accumulate = 0;
+        if (p.slabs > slabs_avail) { set_error(kErrBadArg, "qmatmul: %d slabs needed, %d provided", p.slabs, slabs_avail); return 0; }
+    }
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     { static const char* tr = getenv("B200_GEMM_TRACE"); p.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 0)) : nullptr; }
     if (ggml_type == B200_GGML_Q4_K) { if (mb == 32) launch<32, B200_GGML_Q4_K>(wm, xm, p, st); else launch<64, B200_GGML_Q4_K>(wm, xm, p, st); }
     else { if (mb == 32) launch<32, B200_GGML_Q6_K>(wm, xm, p, st); else launch<64, B200_GGML_Q6_K>(wm, xm, p, st); }
     check_launch("qmatmul_tc");
+    return p.slabs;
 }
 
 // symmetric int4 x fp16 (marlin_4bit_*): w in the gptq_repack() layout, scales marlin-permuted, 16-bit output
@@ -779,7 +836,7 @@ void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* ou
 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
                 int accumulate, cudaStream_t st) {
-    qmatmul_tc_multi(x_f16, 1, &w, &y, &n, ldy, m, k, ggml_type, accumulate, st);
+    qmatmul_tc_multi(x_f16, 1, &w, &y, &n, ldy, m, k, ggml_type, accumulate, 0, 0, st);
 }
 
 }  // namespace b200

@@ -40,7 +40,11 @@ def _pad_tables(tables: List[List[int]]) -> np.ndarray:
 
 def prepare_decode(seq_lens: Sequence[int], last_tokens: Sequence[int], block_tables: Sequence[Sequence[int]],
                    block_size: int) -> dict:
-    """inputs.rs:376-454,552-568.  seq_lens include the token being decoded."""
+    """inputs.rs:376-454,552-568.  seq_lens include the token being decoded.  ``block_tables`` may be a list of per-sequence
+    lists (ragged, like ``Sequence::block_table``) or a rectangular integer ndarray [B, width] whose rows are valid up to
+    each sequence's used-block count -- the latter takes a vectorised path with identical results."""
+    if isinstance(block_tables, np.ndarray) and block_tables.ndim == 2:
+        return _prepare_decode_rect(np.asarray(seq_lens, np.int64), np.asarray(last_tokens), block_tables, block_size)
     tokens, positions, slots, ctx, tabs = [], [], [], [], []
     for L, tok, table in zip(seq_lens, last_tokens, block_tables):
         pos = L - 1
@@ -50,6 +54,24 @@ def prepare_decode(seq_lens: Sequence[int], last_tokens: Sequence[int], block_ta
     return dict(is_prefill=False, tokens=np.asarray(tokens, np.uint32), positions=np.asarray(positions, np.int64),
                 slot_mapping=np.asarray(slots, np.int64), context_lens=np.asarray(ctx, np.int32),
                 block_tables=_pad_tables(tabs), max_context_len=int(max(ctx)))
+
+
+def _prepare_decode_rect(lens: np.ndarray, toks: np.ndarray, tables: np.ndarray, block_size: int) -> dict:
+    B, width = tables.shape
+    if lens.shape != (B,) or toks.shape != (B,):
+        raise BackendError(f"prepare_decode: {B} block tables for {lens.shape[0]} sequences / {toks.shape[0]} tokens")
+    pos = lens - 1
+    bi = pos // block_size
+    if (bi >= width).any() or (pos < 0).any():
+        b = int(np.argmax((bi >= width) | (pos < 0)))
+        raise BackendError(f"Block table is too small (completion)! start_pos={int(pos[b])} block_size={block_size} table_len={width}")
+    rows = np.arange(B)
+    slots = tables[rows, bi].astype(np.int64) * block_size + pos % block_size
+    used = np.minimum((lens + block_size - 1) // block_size, width)          # used_blocks_for_len
+    w = max(1, int(used.max()))
+    tabs = np.where(np.arange(w)[None, :] < used[:, None], tables[:, :w], 0).astype(np.int32)
+    return dict(is_prefill=False, tokens=toks.astype(np.uint32), positions=pos.astype(np.int64), slot_mapping=slots,
+                context_lens=lens.astype(np.int32), block_tables=tabs, max_context_len=int(lens.max()))
 
 
 def prepare_prompt(prompts: Sequence[Sequence[int]], block_tables: Sequence[Sequence[int]], block_size: int,

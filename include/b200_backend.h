@@ -132,6 +132,15 @@ void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, 
  * When accumulate == 0 and the product is split over K, y is zero-filled first (contiguous y only). */
 void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32_t n, int32_t k,
                     int32_t ggml_type, int32_t accumulate, int64_t stream);
+/* Atomic-free, bitwise-deterministic form used by the fused decode layer: when the product of a small-n matrix is split
+ * over K between SMs, every SM that shares a 128-row tile stores its partial sum to its own slab instead of red.add-ing
+ * into y.  y_slabs = [slabs][m][n] f32 (slab stride m*n); returns the number of slabs S <= slabs_avail that now hold
+ * partial sums (every element of slabs 0..S-1 is written, nothing needs pre-zeroing); the product is their sum, which the
+ * consumer kernel (RMSNorm, RoPE, SiLU) folds into its own load.  qmatmul_slab_count() gives the S this (n, k) needs.
+ * Returns 0 and records an error on bad arguments. */
+int32_t qmatmul_slab_count(int32_t m, int32_t n, int32_t k, int32_t ggml_type);
+int32_t qmatmul_f16act_slabs(const void* x_f16, const void* w, float* y_slabs, int32_t slabs_avail, int32_t m, int32_t n,
+                             int32_t k, int32_t ggml_type, int64_t stream);
 /* QTensor::dequantize: W -> f32 [n,k] (linear.rs:808-842 forward_via_dequant) */
 void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggml_type, int64_t stream);
 

@@ -89,3 +89,23 @@ def test_synthetic_blocks_are_valid_and_sharding_is_consistent():
         assert np.array_equal(G.dequantize_weight(rs.data.numpy(), 12, 4, 1024), deq[4 * r:4 * r + 4])
         cs = synthetic.shard_cols(full, r, 2)
         assert np.array_equal(G.dequantize_weight(cs.data.numpy(), 12, 8, 512), deq[:, 512 * r:512 * r + 512])
+
+
+def test_prepare_decode_rectangular_tables_match_ragged_path():
+    """ndarray block tables take a vectorised path; results (values and dtypes) equal the per-sequence loop."""
+    from candle_vllm_b200 import inputs
+    rng = np.random.default_rng(11)
+    B, bs, width = 9, 16, 12
+    tabs = rng.integers(0, 500, (B, width)).astype(np.int32)
+    for base in (1, 15, 16, 17, 100, bs * width - B):
+        lens = [base + i for i in range(B)]
+        toks = [int(t) for t in rng.integers(0, 1000, B)]
+        a = inputs.prepare_decode(lens, toks, tabs.tolist(), bs)
+        b = inputs.prepare_decode(np.asarray(lens), np.asarray(toks), tabs, bs)
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+            if hasattr(a[k], "dtype"):
+                assert a[k].dtype == b[k].dtype, k
+    with pytest.raises(inputs.BackendError, match="Block table is too small"):
+        inputs.prepare_decode(np.full(B, bs * width + 1), np.zeros(B, np.int64), tabs, bs)

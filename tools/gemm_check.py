@@ -47,7 +47,15 @@ if reps:
     yb = torch.zeros((m, n), dtype=torch.float32, device="cuda")
     with torch.cuda.stream(st):
         L.cast(C.c_void_p(xh.data_ptr()), C.c_void_p(xk4.data_ptr()), C.c_int64(xh.numel()), C.c_int32(DType.F16), C.c_int32(DType.F16_K4), C.c_int64(st.cuda_stream))
+        slabs = int(os.environ.get("B200_SLABS", "0"))
+        L.qmatmul_slab_count.restype = C.c_int32
+        ns = int(L.qmatmul_slab_count(C.c_int32(m), C.c_int32(n), C.c_int32(k), C.c_int32(t)))
+        ysl = torch.empty((max(ns, 1), m, n), dtype=torch.float32, device="cuda")
         def call(i):
+            if slabs:
+                L.qmatmul_f16act_slabs(C.c_void_p(xk4.data_ptr()), C.c_void_p(ws[i % Lw].data.data_ptr()), C.c_void_p(ysl.data_ptr()), C.c_int32(ysl.shape[0]),
+                                       C.c_int32(m), C.c_int32(n), C.c_int32(k), C.c_int32(t), C.c_int64(st.cuda_stream))
+                return
             L.qmatmul_f16act(C.c_void_p(xk4.data_ptr()), C.c_void_p(ws[i % Lw].data.data_ptr()), C.c_void_p(yb.data_ptr()), C.c_int32(m), C.c_int32(n),
                              C.c_int32(k), C.c_int32(t), C.c_int32(1), C.c_int64(st.cuda_stream))
         for i in range(3): call(i)
@@ -60,4 +68,4 @@ if reps:
         e0.record(st); gr.replay(); e1.record(st); st.synchronize()
     ms = e0.elapsed_time(e1) / reps
     byts = w.data.numel()
-    print(f"  graph of {reps} GEMM launches: {ms*1e3:.2f} us/launch, {byts/ms/1e6:.1f} GB/s weight stream (debug={os.environ.get('B200_GEMM_DEBUG','0')})")
+    print(f"  graph of {reps} GEMM launches: {ms*1e3:.2f} us/launch, {byts/ms/1e6:.1f} GB/s weight stream (debug={os.environ.get('B200_GEMM_DEBUG','0')}, slabs={ns if slabs else 0})")
