@@ -48,8 +48,9 @@ struct Cfg {
     // bytes of one super-block as staged in shared memory: Q4_K 144; Q6_K a 240-byte window that starts at the
     // 210-byte block's address rounded down to 16 (TMA box starts must be 16-byte aligned)
     // Independent accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on the accumulate
-    // dependency; k-step ks goes to D[ks % kAcc] and the epilogue adds them up.  kAcc * kMB = 128 TMEM columns.
-    static constexpr int kAcc = 128 / kMB;
+    // dependency; k-step ks goes to D[ks % kAcc] and the epilogue adds them up.  Two suffice (the dequant side sets the
+    // pace) and keep the epilogue's TMEM reads (64 B/clk) short: kAcc * kMB <= 128 TMEM columns.
+    static constexpr int kAcc = 2;
     static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : (kType == kTypeM4 ? 128 : 240);
     static constexpr int kWBytes = kTileN * kBlk;                  // raw weights of one unit (18 KB / 30 KB)
     static constexpr int kXBytes = 4 * kMB * kXSubBytes;           // 4 sub-tiles of [kMB][64] fp16 (16 KB / 32 KB)
@@ -191,6 +192,20 @@ __device__ __forceinline__ void scale_min(uint32_t s0, uint32_t s1, uint32_t s2,
     else { sc = (byte(J + 4) & 0xF) | ((byte(J - 4) >> 6) << 4); mn = (byte(J + 4) >> 4) | ((byte(J) >> 6) << 4); }
 }
 
+// the two 6-bit scales and mins of sub-blocks 2kC and 2kC+1, packed as (lo | hi << 16) integers
+template <int kC>
+__device__ __forceinline__ void scale_min_pair(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t& sc2, uint32_t& mn2) {
+    constexpr uint32_t sel = (kC & 1) ? 0x4342u : 0x4140u;       // bytes (2,3) or (0,1) of a word -> low bytes of the two halves
+    if constexpr (kC < 2) {          // j < 4: sc = q[j] & 63, m = q[j + 4] & 63
+        sc2 = __byte_perm(s0, 0u, sel) & 0x003f003fu;
+        mn2 = __byte_perm(s1, 0u, sel) & 0x003f003fu;
+    } else {                         // j >= 4: sc = (q[j+4] & 0xF) | ((q[j-4] >> 6) << 4), m = (q[j+4] >> 4) | ((q[j] >> 6) << 4)
+        const uint32_t a = __byte_perm(s2, 0u, sel), hs = __byte_perm(s0, 0u, sel), hm = __byte_perm(s1, 0u, sel);
+        sc2 = (a & 0x000f000fu) | ((hs >> 2) & 0x00300030u);
+        mn2 = ((a >> 4) & 0x000f000fu) | ((hm >> 2) & 0x00300030u);
+    }
+}
+
 // Dequantise sub-blocks 4*kHf .. 4*kHf+3 (128 weights) of this thread's Q4_K block into fp16 and store
 // them to 64 TMEM columns (two weights per 32-bit column; K4 order inside each group of four).
 // Fast path: the nibble is dropped into fp16 mantissa bits 6-9 (a subnormal = q * 2^-18) and ONE HFMA2 with
@@ -208,17 +223,22 @@ struct Q4KQuarter {
         raw[4] = qa.x; raw[5] = qa.y; raw[6] = qa.z; raw[7] = qa.w; raw[8] = qb.x; raw[9] = qb.y; raw[10] = qb.z; raw[11] = qb.w;
     }
     static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], int, uint32_t a_col) {
-        const __half2 dd = *reinterpret_cast<const __half2*>(&raw[0]);
+        const __half2 dd = *reinterpret_cast<const __half2*>(&raw[0]);          // (d, dmin)
         const float d = __low2float(dd);
-        const float dmin = -__high2float(dd);
         // warp-uniform so that the .aligned tcgen05.st below is reached convergently
         const bool fast = __all_sync(0xffffffffu, fabsf(d) * 63.f * 262144.f <= 65504.f);
-        const float dk = fast ? d * 262144.f : d;
-        int sc_lo, m_lo, sc_hi, m_hi;
-        scale_min<2 * kC>(raw[1], raw[2], raw[3], sc_lo, m_lo);
-        scale_min<2 * kC + 1>(raw[1], raw[2], raw[3], sc_hi, m_hi);
-        const __half2 s_lo = __float2half2_rn(dk * (float)sc_lo), s_hi = __float2half2_rn(dk * (float)sc_hi);
-        const __half2 n_lo = __float2half2_rn(dmin * (float)m_lo), n_hi = __float2half2_rn(dmin * (float)m_hi);
+        const __half2 dk = __float2half2_rn(fast ? d * 262144.f : d);            // exact: power-of-two scaling inside the fp16 range
+        const __half2 ndmin = __hneg2(__high2half2(dd));
+        // 6-bit scales / mins of sub-blocks 2kC (low half) and 2kC+1 (high half) as exact fp16 integers via the 1024+q
+        // magic; one HMUL2 each then rounds d*sc and dmin*m exactly like the fp32 product followed by a cast would
+        uint32_t sc2, mn2;
+        scale_min_pair<kC>(raw[1], raw[2], raw[3], sc2, mn2);
+        const uint32_t magic1024 = 0x64006400u;
+        const __half2 h1024 = *reinterpret_cast<const __half2*>(&magic1024);
+        sc2 |= magic1024; mn2 |= magic1024;
+        const __half2 S = __hmul2(dk, __hsub2(*reinterpret_cast<__half2*>(&sc2), h1024));
+        const __half2 N = __hmul2(ndmin, __hsub2(*reinterpret_cast<__half2*>(&mn2), h1024));
+        const __half2 s_lo = __low2half2(S), s_hi = __high2half2(S), n_lo = __low2half2(N), n_hi = __high2half2(N);
         uint32_t v[32];
         if (fast) {
 #pragma unroll
@@ -468,6 +488,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     const uint32_t d_full = bars + (2 * kW + 2 * kX + 2 * kABufs) * 8, d_empty = d_full + 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + C::kTmemSlot);
 
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[32 * 8 + 0] = clock64();       // kernel entry
     if (threadIdx.x == 0) {
         for (int s = 0; s < kW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), kDequantWarps); }
         for (int s = 0; s < kX; ++s) { mbar_init(x_full(s), 1); mbar_init(x_empty(s), 1); }
@@ -485,12 +506,16 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[32 * 8 + 1] = clock64();       // barriers + TMEM ready
     pdl_trigger();         // the next kernel may start its own prologue; it waits for our completion before reading
 
     // ---- stream-K range of this CTA over the flattened (tile, super-block) space -----------------
-    const int64_t total = (int64_t)p.n_tiles * p.nsb;
-    const int64_t u0 = p.whole_tiles ? ((int64_t)p.n_tiles * blockIdx.x / gridDim.x) * p.nsb : total * blockIdx.x / gridDim.x;
-    const int64_t u1 = p.whole_tiles ? ((int64_t)p.n_tiles * (blockIdx.x + 1) / gridDim.x) * p.nsb : total * (blockIdx.x + 1) / gridDim.x;
+    // (32-bit on purpose: 64-bit integer division costs ~500 cycles each on the SM and sat on the critical path of every
+    // launch; the host guarantees total * gridDim.x < 2^31)
+    const uint32_t total = (uint32_t)p.n_tiles * (uint32_t)p.nsb, nsb = (uint32_t)p.nsb;
+    const uint32_t u0 = p.whole_tiles ? ((uint32_t)p.n_tiles * blockIdx.x / gridDim.x) * nsb : total * blockIdx.x / gridDim.x;
+    const uint32_t u1 = p.whole_tiles ? ((uint32_t)p.n_tiles * (blockIdx.x + 1) / gridDim.x) * nsb : total * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t tile0 = u0 / nsb, sb0 = u0 - tile0 * nsb;          // first unit of this CTA
 
     if (warp == kDequantWarps) {
         // ================================== W PRODUCER (HBM stream) ==============================
@@ -499,8 +524,8 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         uint64_t pol_w;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
         int it = 0;
-        for (int64_t u = u0; u < u1; ++u, ++it) {
-            const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
+        int tile = (int)tile0, sb = (int)sb0;
+        for (uint32_t u = u0; u < u1; ++u, ++it) {
             const int s = it % kW;
             mbar_wait(w_empty(s), ((it / kW) & 1) ^ 1);
             if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 0] = clock64();
@@ -515,6 +540,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                             ltile * kTileN, pol_w);
             }
             __syncwarp();
+            if (++sb == (int)nsb) { sb = 0; ++tile; }
         }
     } else if (warp == kDequantWarps + 1) {
         // ================================== X PRODUCER (L2 resident) =============================
@@ -523,8 +549,8 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         uint64_t pol_x;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
         int it = 0;
-        for (int64_t u = u0; u < u1; ++u, ++it) {
-            const int tile = (int)(u / p.nsb), sb = (int)(u - (int64_t)tile * p.nsb);
+        int sb = (int)sb0;
+        for (uint32_t u = u0; u < u1; ++u, ++it) {
             const int s = it % kX;
             mbar_wait(x_empty(s), ((it / kX) & 1) ^ 1);
             if (leader) {
@@ -534,6 +560,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, x_full(s), sb * kSB + q * 64, 0, pol_x);
             }
             __syncwarp();
+            if (++sb == (int)nsb) sb = 0;
         }
     } else if (warp == kDequantWarps + 2) {
         // ======================================= MMA ISSUER ======================================
@@ -543,10 +570,10 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         // instruction descriptor: D = f32, A = B = f16, both K-major, N = kMB, M = 128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(kMB >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
         int it = 0, seg = 0;
-        for (int64_t u = u0; u < u1;) {
-            const int tile = (int)(u / p.nsb);
-            const int64_t tile_end = (int64_t)(tile + 1) * p.nsb;
-            const int64_t seg_end = tile_end < u1 ? tile_end : u1;
+        uint32_t tile = tile0;
+        for (uint32_t u = u0; u < u1; ++tile) {
+            const uint32_t tile_end = (tile + 1) * nsb;
+            const uint32_t seg_end = tile_end < u1 ? tile_end : u1;
             mbar_wait(d_empty, (seg & 1) ^ 1);                 // epilogue of the previous segment has drained D
             tc_fence_after();
             bool first = true;
@@ -586,18 +613,19 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         const int row = qd * 32 + lane;                    // weight row within the tile = TMEM lane
         const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
         int it = 0, seg = 0;
-        for (int64_t u = u0; u < u1;) {
-            const int tile = (int)(u / p.nsb);
-            const int64_t tile_begin = (int64_t)tile * p.nsb, tile_end = tile_begin + p.nsb;
-            const int64_t seg_begin = u, seg_end = tile_end < u1 ? tile_end : u1;
+        int ws = 0, ab = 0;                                // ring positions and phases kept as running state (no div / mod per unit)
+        uint32_t wph = 0, aph = 0;
+        int tile = (int)tile0;
+        for (uint32_t u = u0; u < u1; ++tile) {
+            const uint32_t tile_begin = (uint32_t)tile * nsb, tile_end = tile_begin + nsb;
+            const uint32_t seg_begin = u, seg_end = tile_end < u1 ? tile_end : u1;
             for (; u < seg_end; ++u, ++it) {
-                const int ws = it % kW, ab = it % kABufs;
-                mbar_wait(w_full(ws), (it / kW) & 1);
+                mbar_wait(w_full(ws), wph);
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 4] = clock64();
                 const uint8_t* blk = smem + C::kWOff + ws * C::kWBytes + row * C::kBlk;
                 const uint32_t a_col = tmem + kColA + ab * 128 + lane_addr;
                 const int off = kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15);   // Q6_K: block offset in its window
-                const uint32_t afp = ((it / kABufs) & 1) ^ 1;
+                const uint32_t afp = aph ^ 1;
                 const bool skip = (p.debug & 2) != 0;
                 const M4Ctx mc{p.scales, p.n[0], p.group_size, (int)(u - tile_begin) * kSB, tile * kTileN + row < p.n[0] ? tile * kTileN + row : 0,
                                p.out_dtype == B200_BF16, p.debug};
@@ -608,11 +636,15 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                     default: dequant_unit<kType, 3>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                 }
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 6] = clock64();
+                if (++ws == kW) { ws = 0; wph ^= 1; }
+                if (++ab == kABufs) { ab = 0; aph ^= 1; }
             }
             // ---- epilogue of the segment: D (TMEM) -> y ------------------------------------------------
             if (!waited) { pdl_wait(); waited = true; }       // y may still be in use by earlier kernels
+            if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && seg < 3) p.trace[32 * 8 + 2 + 2 * seg] = clock64();   // dequant of the segment done
             mbar_wait(d_full, seg & 1);
             tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && seg < 3) p.trace[32 * 8 + 3 + 2 * seg] = clock64();   // accumulator complete
             const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
             const int sg = seg_of_tile(p, tile);
             const int n_idx = (tile - seg_first_tile(p, sg)) * kTileN + row;
@@ -620,7 +652,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             // slab mode: the k-th CTA that works on a tile writes slab k.  CTA b owns units [total*b/grid, total*(b+1)/grid),
             // so the owner of unit u is ((u+1)*grid - 1) / total and only a CTA's first segment can start inside a tile.
             int ordinal = 0;
-            if (p.slabs > 0 && seg_begin != tile_begin) ordinal = (int)blockIdx.x - (int)(((tile_begin + 1) * gridDim.x - 1) / total);
+            if (p.slabs > 0 && seg_begin != tile_begin) ordinal = (int)blockIdx.x - (int)(((tile_begin + 1) * gridDim.x - 1) / total);   // 32-bit, see above
             if (p.slabs > 0) ybase += (int64_t)ordinal * p.slab_stride;
             const int zero_slabs = (p.slabs > 0 && seg_end == tile_end) ? p.slabs - 1 - ordinal : 0;   // slabs nobody else writes
             const int n_rows = sg == 0 ? p.n[0] : (sg == 1 ? p.n[1] : p.n[2]);
@@ -666,8 +698,10 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     }
 
     // ---- teardown ---------------------------------------------------------------------------------
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[33 * 8 + 0] = clock64();           // this warp's last epilogue done
     tc_fence_before();
     __syncthreads();
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[33 * 8 + 1] = clock64();           // all roles done
     if (warp == kDequantWarps + 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -726,6 +760,7 @@ bool make_w_map(CUtensorMap* wm, const void* w, int n, int nsb, int ggml_type) {
 
 bool qmatmul_tc_supported(int m, int n, int k, int ggml_type) {
     if (m < 1 || m > 64 || n < 1 || k < 256 || k % 256) return false;
+    if ((int64_t)((n + kTileN - 1) / kTileN + 2) * (k / 256) * sm_count() >= (int64_t)1 << 30) return false;   // kernel uses 32-bit unit arithmetic
     if (ggml_type == B200_GGML_Q4_K) return true;                         // row pitch (k/256)*144 is always a multiple of 16
     if (ggml_type == B200_GGML_Q6_K) return ((int64_t)(k / 256) * 210) % 16 == 0;   // TMA row pitch: k % 2048 == 0
     return false;
@@ -789,6 +824,7 @@ int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* c
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return 0; }
     }
+    if ((int64_t)tiles * nsb * sm_count() >= (int64_t)1 << 31) { set_error(kErrUnsupported, "qmatmul: %d tiles x %d super-blocks exceed the 32-bit unit range", tiles, nsb); return 0; }
     p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate; p.out_dtype = B200_F32;
     p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
     if (slabs_avail > 0) {

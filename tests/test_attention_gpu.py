@@ -149,3 +149,30 @@ def test_attention_argument_errors():
         attn.forward(q.bfloat16()[:, :4], None, None, None, kc, kc, meta)   # head count mismatch
     with pytest.raises(pkg.BackendError):
         pkg.PagedAttention(6, 128, 0.1, 4)
+
+
+def test_decode_repeatable_on_one_workspace():
+    """The work-queue head lives in the caller's workspace and is re-armed by the merge kernel: 200 back-to-back launches
+    on ONE workspace, with changing context lengths (1 .. many chunks, one empty context), must all match the first-launch
+    result bit for bit (the split merge folds chunks in a fixed order) and the oracle."""
+    rng = np.random.default_rng(21)
+    B, H, kvh, hd, bs = 16, 32, 8, 128, 64
+    ctxs = [[1 + (37 * b * (r + 1)) % 2900 for b in range(B)] for r in range(4)]
+    ctxs[1][3] = 0                                            # an empty context attends to nothing -> zeros
+    nb = 16 * 46 + 3
+    q, kc, vc, kn, vn, bt = _mk(rng, B, H, kvh, hd, bs, nb, [2900] * B)
+    attn = pkg.PagedAttention(H, hd, hd ** -0.5, kvh)
+    first = {}
+    for it in range(200):
+        r = it % 4
+        meta = pkg.InputMetadata(False, torch.zeros(0, dtype=torch.int64, device=DEV), torch.from_numpy(bt).to(DEV),
+                                 torch.tensor(ctxs[r], dtype=torch.int32, device=DEV))
+        out = attn.forward(q, None, None, None, kc, vc, meta)
+        if r not in first:
+            first[r] = out.clone()
+            ref = OA.paged_attention_decode(q.float().cpu().numpy(), kn, vn, bt, ctxs[r], hd ** -0.5)
+            _check(out, ref)
+            if r == 1:
+                assert float(out[3].abs().max()) == 0.0
+        else:
+            assert torch.equal(out, first[r]), f"launch {it} differs from launch {r}"

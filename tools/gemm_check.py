@@ -10,7 +10,7 @@ from candle_vllm_b200 import synthetic
 
 if os.environ.get("B200_TRACE"):
     import torch as _t
-    _trace = _t.zeros(32 * 8, dtype=_t.int64, device="cuda")
+    _trace = _t.zeros(34 * 8, dtype=_t.int64, device="cuda")
     os.environ["B200_GEMM_TRACE"] = str(_trace.data_ptr())
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
@@ -28,12 +28,17 @@ ref = (x.half().float().double() @ wd.double().T).float()      # fp16-rounded ac
 ref32 = (x.double() @ wd.double().T).float()
 rel = ((y - ref).norm() / ref.norm()).item()
 rel32 = ((y - ref32).norm() / ref32.norm()).item()
-if os.environ.get("B200_TRACE"):
-    tr = _trace.cpu().numpy().reshape(32, 8)
+def show_trace(tag):
+    if not os.environ.get("B200_TRACE"): return
+    tr = _trace.cpu().numpy().reshape(34, 8)
     t0 = tr[tr > 0].min()
-    print("unit: prod_empty_ok | mma_full_ok mma_aready_ok mma_committed | deq_full_ok deq_afree_ok deq_done   (cycles since first stamp)")
+    print(f"[{tag}] unit: prod_empty_ok | mma_full_ok mma_aready_ok mma_committed | deq_full_ok deq_afree_ok deq_done   (cycles since first stamp)")
     for i in range(16):
-        print(i, [int(v - t0) if v > 0 else -1 for v in tr[i, :7]])
+        if (tr[i] > 0).any(): print(i, [int(v - t0) if v > 0 else -1 for v in tr[i, :7]])
+    print("kernel: entry, setup_done, (seg dequant_done, acc_complete) x3:", [int(v - t0) if v > 0 else -1 for v in tr[32]])
+    print("kernel: last_epilogue_done, all_roles_done:", [int(v - t0) if v > 0 else -1 for v in tr[33, :2]])
+    _trace.zero_()
+show_trace("cold first launch")
 print(f"m={m} n={n} k={k} type={t}: rel-fro vs fp16-act ref {rel:.3e}, vs f32 ref {rel32:.3e}, max|y|={y.abs().max().item():.3f}")
 if reps:
     import ctypes as C
@@ -69,3 +74,4 @@ if reps:
     ms = e0.elapsed_time(e1) / reps
     byts = w.data.numel()
     print(f"  graph of {reps} GEMM launches: {ms*1e3:.2f} us/launch, {byts/ms/1e6:.1f} GB/s weight stream (debug={os.environ.get('B200_GEMM_DEBUG','0')}, slabs={ns if slabs else 0})")
+    show_trace("last launch of the warm graph")
