@@ -371,6 +371,94 @@ class QMatMul:
 
 
 # ---------------------------------------------------------------------------------------------
+# weight-only low-precision float linears (LnFp8 / LnNvfp4 / LnMxfp4, linear.rs:1190-1221, :1913-1943, :1717-1757)
+# ---------------------------------------------------------------------------------------------
+def _lin_io(x: torch.Tensor, n: int, k: int, bias, who: str):
+    _cuda(x, "x"); require_device()
+    if x.dtype not in (torch.float16, torch.bfloat16):
+        raise BackendError(f"{who}: activations must be f16 or bf16 (the reference casts f32 inputs to bf16, linear.rs:1719-1724)")
+    if x.shape[-1] != k:
+        raise BackendError(f"{who}: shape mismatch, x {tuple(x.shape)} vs weight [{n}, {k}]")
+    if bias is not None and (bias.dtype != x.dtype or bias.numel() != n):
+        raise BackendError(f"{who}: bias must be [{n}] of the activation dtype")
+    x2 = x.reshape(-1, k).contiguous()
+    out = torch.empty((x2.shape[0], n), dtype=x.dtype, device=x.device)
+    return x2, out
+
+
+class LnFp8:
+    """Block-scaled FP8 linear: ``weight`` e4m3 (torch.float8_e4m3fn or u8) [N, K], ``weight_scale`` f32
+    [ceil(N/by), ceil(K/bx)] (linear.rs:944-973); ``forward`` = ``fp8_matmul`` (+ bias)."""
+
+    def __init__(self, weight: torch.Tensor, weight_scale: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 weight_block_size=(128, 128)):
+        if len(weight_block_size) != 2:
+            raise BackendError("LnFp8: weight_block_size must have 2 elements")          # linear.rs:949-951
+        self.weight = _cuda(weight, "weight").contiguous().view(torch.uint8)
+        self.by, self.bx = int(weight_block_size[0]), int(weight_block_size[1])
+        n, k = self.weight.shape
+        want = ((n + self.by - 1) // self.by, (k + self.bx - 1) // self.bx)
+        if tuple(weight_scale.shape) != want or weight_scale.dtype != torch.float32:
+            raise BackendError(f"LnFp8: weight_scale must be f32 {want}, got {tuple(weight_scale.shape)} {weight_scale.dtype}")
+        self.weight_scale = _cuda(weight_scale, "weight_scale").contiguous()
+        self.bias = bias
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, k = self.weight.shape
+        x2, out = _lin_io(x, n, k, self.bias, "LnFp8")
+        with torch.cuda.device(x.device):
+            lib().fp8_matmul(_ptr(x2), _ptr(self.weight), _ptr(self.weight_scale), _ptr(self.bias), _ptr(out), C.c_int32(x2.shape[0]),
+                             C.c_int32(n), C.c_int32(k), C.c_int32(self.by), C.c_int32(self.bx), C.c_int32(_dt(x2)), _stream(x.device))
+        check("LnFp8.forward")
+        return out.reshape(*x.shape[:-1], n)
+
+
+class LnNvfp4:
+    """NVFP4 linear: ``blocks`` u8 [N, K/2], ``scales`` e4m3 [N, K/16], ``global_scale`` as stored by the reference
+    (the reciprocal of weight_global_scale, or weight_scale_2; linear.rs:1829-1853).  ``input_scale`` is accepted and ignored."""
+
+    def __init__(self, blocks: torch.Tensor, scales: torch.Tensor, global_scale: float = 1.0, input_scale: float = 1.0,
+                 bias: Optional[torch.Tensor] = None):
+        self.blocks = _cuda(blocks, "blocks").contiguous().view(torch.uint8)
+        self.scales = _cuda(scales, "scales").contiguous().view(torch.uint8)
+        n, k2 = self.blocks.shape
+        if tuple(self.scales.shape) != (n, k2 // 8):
+            raise BackendError(f"LnNvfp4: scales must be [{n}, {k2 // 8}], got {tuple(self.scales.shape)}")
+        self.global_scale, self.input_scale, self.bias = float(global_scale), float(input_scale), bias
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, k = self.blocks.shape[0], self.blocks.shape[1] * 2
+        x2, out = _lin_io(x, n, k, self.bias, "LnNvfp4")
+        with torch.cuda.device(x.device):
+            lib().nvfp4_matmul(_ptr(x2), _ptr(self.blocks), _ptr(self.scales), C.c_float(self.global_scale), C.c_float(self.input_scale),
+                               _ptr(self.bias), _ptr(out), C.c_int32(x2.shape[0]), C.c_int32(n), C.c_int32(k), C.c_int32(_dt(x2)),
+                               _stream(x.device))
+        check("LnNvfp4.forward")
+        return out.reshape(*x.shape[:-1], n)
+
+
+class LnMxfp4:
+    """MXFP4 linear: ``blocks`` u8 [N, K/2], ``scales`` e8m0 [N, K/32] (linear.rs:1686-1700)."""
+
+    def __init__(self, blocks: torch.Tensor, scales: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        self.blocks = _cuda(blocks, "blocks").contiguous().view(torch.uint8)
+        self.scales = _cuda(scales, "scales").contiguous().view(torch.uint8)
+        n, k2 = self.blocks.shape
+        if tuple(self.scales.shape) != (n, k2 // 16):
+            raise BackendError(f"LnMxfp4: scales must be [{n}, {k2 // 16}], got {tuple(self.scales.shape)}")
+        self.bias = bias
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, k = self.blocks.shape[0], self.blocks.shape[1] * 2
+        x2, out = _lin_io(x, n, k, self.bias, "LnMxfp4")
+        with torch.cuda.device(x.device):
+            lib().mxfp4_matmul(_ptr(x2), _ptr(self.blocks), _ptr(self.scales), _ptr(self.bias), _ptr(out), C.c_int32(x2.shape[0]),
+                               C.c_int32(n), C.c_int32(k), C.c_int32(_dt(x2)), _stream(x.device))
+        check("LnMxfp4.forward")
+        return out.reshape(*x.shape[:-1], n)
+
+
+# ---------------------------------------------------------------------------------------------
 # small ops
 # ---------------------------------------------------------------------------------------------
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, out_dtype=torch.float32) -> torch.Tensor:

@@ -367,13 +367,31 @@ paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o
     const int ctx = (int)context_lens[b];
     const int nchunks = (ctx + chunk_tokens - 1) / chunk_tokens;
     const int64_t base = ((int64_t)b * num_kv_heads + h) * max_chunks;
-    float M = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) M = fmaxf(M, part_ml[((base + c) * group + r) * 2]);
-    float acc = 0.f, L = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-        const float w = exp2f(part_ml[((base + c) * group + r) * 2] - M);
-        acc += w * part_o[((base + c) * group + r) * kHeadDim + d];
-        L += w * part_ml[((base + c) * group + r) * 2 + 1];
+    // batches of 8 chunks with all loads of a batch in flight together (the kernel is pure L2 latency), folded online
+    constexpr int kU = 8;
+    float M = -INFINITY, acc = 0.f, L = 0.f;
+    for (int c0 = 0; c0 < nchunks; c0 += kU) {
+        float2 ml[kU];
+        float o[kU];
+#pragma unroll
+        for (int i = 0; i < kU; ++i) {
+            const bool ok = c0 + i < nchunks;
+            const int64_t slot = (base + (ok ? c0 + i : c0)) * group + r;
+            ml[i] = *reinterpret_cast<const float2*>(part_ml + slot * 2);
+            o[i] = part_o[slot * kHeadDim + d];
+            if (!ok) { ml[i] = make_float2(-INFINITY, 0.f); o[i] = 0.f; }
+        }
+        float bm = M;
+#pragma unroll
+        for (int i = 0; i < kU; ++i) bm = fmaxf(bm, ml[i].x);
+        const float corr = exp2f(M - bm);            // first batch: exp2(-inf) = 0 on zero accumulators
+        acc *= corr; L *= corr; M = bm;
+#pragma unroll
+        for (int i = 0; i < kU; ++i) {
+            const float w = exp2f(ml[i].x - M);      // padding: exp2(-inf) = 0
+            acc += w * o[i];
+            L += w * ml[i].y;
+        }
     }
     const float res = nchunks > 0 && L > 0.f ? acc / L : 0.f;
     out[((int64_t)b * num_heads + head) * kHeadDim + (kK4 ? (int)k4_index(d) : d)] = from_f32<TOut>(to_f32(from_f32<T>(res)));

@@ -32,7 +32,7 @@ __global__ void gptq_repack_kernel(const uint32_t* __restrict__ in, uint32_t* __
 // activation scratch (fp16, K4 order): the reference ABI has no slot for it (its `workspace` is N words of locks),
 // so the library owns one buffer per device, grown outside stream capture (the reference warms every shape up
 // eagerly before capturing, graph.rs:471-661) or provided once with b200_set_scratch().
-static void* g_scratch = nullptr;
+static void* g_scratch = nullptr;      // (fp16 activation copy + fp32 partial-sum slabs of the 16-bit-output GEMMs)
 static size_t g_scratch_bytes = 0;
 static bool g_scratch_owned = false;
 
@@ -63,10 +63,12 @@ static void marlin_4bit(const void* x, const void* qweight, const void* scales, 
     B200_REQUIRE(k % 256 == 0 && n % 64 == 0, kErrUnsupported, "marlin_4bit: k %% 256 and n %% 64 must be 0 (k=%d n=%d)", k, n);
     B200_REQUIRE(m <= 64, kErrUnsupported, "marlin_4bit: m = %d > 64 (decode batches only in this round)", m);
     cudaStream_t st = as_stream(stream);
-    void* xs = get_scratch((size_t)m * k * 2, st);
+    // scratch: fp16 K4 copy of x, then the fp32 partial-sum slabs of the stream-K GEMM
+    const size_t x_bytes = ((size_t)m * k * 2 + 255) & ~(size_t)255;
+    char* xs = static_cast<char*>(get_scratch(x_bytes + (size_t)wq16_slabs(n, k) * m * n * 4, st));
     if (!xs) return;
     cast(x, xs, (int64_t)m * k, dtype, B200_F16_K4, stream);
-    marlin_tc(xs, qweight, scales, out, dtype, m, n, k, group_size, st);
+    marlin_tc(xs, qweight, scales, out, dtype, m, n, k, group_size, reinterpret_cast<float*>(xs + x_bytes), st);
 }
 
 }  // namespace b200

@@ -36,9 +36,18 @@ int qmatmul_dispatch_slabs(const void* x_f16, int nseg, const void* const* w, co
 // slabs qmatmul_dispatch_slabs may need for these shapes
 int qmatmul_slabs_needed(int nseg, const int* n, const int* types, int m, int k);
 
-// symmetric int4 (GPTQ, repacked by gptq_repack) x fp16 activations in K4 order -> 16-bit out; m <= 64, k % 256 == 0
+// 16-bit-output weight-only GEMMs on the tcgen05 pipeline: fp32 partial-sum slabs ([wq16_slabs][m][n] f32, caller scratch)
+// + a finishing pass.  m <= 64, k % 256 == 0.
+int wq16_slabs(int n, int k);
+// symmetric int4 (GPTQ, repacked by gptq_repack) x fp16 activations in K4 order
 void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
-               cudaStream_t st);
+               float* slabs, cudaStream_t st);
+// e4m3 [n,k] with f32 scale per [by, bx] tile x fp16 activations in natural order
+bool fp8_tc_supported(int m, int n, int k, int by, int bx);
+void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void* bias, void* out, int out_dtype, int m, int n, int k,
+                int by, int bx, float* slabs, float* norm /* 2 floats, device */, cudaStream_t st);
+// library-owned scratch (marlin_api.cu): grown outside stream capture or set once with b200_set_scratch()
+void* get_scratch(size_t bytes, cudaStream_t st);
 
 // picks tc or generic; y row stride ldy (elements)
 void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k,

@@ -37,6 +37,7 @@ namespace {
 
 constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
 constexpr int kTypeM4 = 1004;        // internal: symmetric int4 (GPTQ) in this library's repacked row-major layout (marlin_4bit_*)
+constexpr int kTypeF8 = 1008;        // internal: e4m3 weights [N,K] with one f32 scale per [by, bx] tile (fp8_matmul)
 constexpr int kSB = 256;             // weights per super-block
 constexpr int kDequantWarps = 16;     // 4 TMEM lane quadrants x 4 quarters of a super-block (64 weights per thread per unit)
 constexpr int kThreads = (kDequantWarps + 3) * 32;     // + W producer, X producer, MMA issuer
@@ -51,7 +52,7 @@ struct Cfg {
     // dependency; k-step ks goes to D[ks % kAcc] and the epilogue adds them up.  Two suffice (the dequant side sets the
     // pace) and keep the epilogue's TMEM reads (64 B/clk) short: kAcc * kMB <= 128 TMEM columns.
     static constexpr int kAcc = 2;
-    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : (kType == kTypeM4 ? 128 : 240);
+    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : (kType == kTypeM4 ? 128 : (kType == kTypeF8 ? 256 : 240));
     static constexpr int kWBytes = kTileN * kBlk;                  // raw weights of one unit (18 KB / 30 KB)
     static constexpr int kXBytes = 4 * kMB * kXSubBytes;           // 4 sub-tiles of [kMB][64] fp16 (16 KB / 32 KB)
     // Two rings.  Raw weight bytes are dead as soon as the dequant warps have pulled them into registers, so the
@@ -171,12 +172,13 @@ struct GemmParams {
     int m, nsb;                    // nsb = k / 256
     int n_tiles;                   // tiles over all segments
     int accumulate;
-    int out_dtype;                 // B200_F32 (GGUF paths) or B200_F16 / B200_BF16 (marlin: plain stores, whole tiles only)
     int whole_tiles;               // 1: CTA ranges are whole tiles (no split-K, no atomics)
     int slabs;                     // > 0: split tiles write their partial sums to DISTINCT slabs (plain stores, no atomics, no
     int64_t slab_stride;           //      pre-zeroed output): slab s of segment sg starts at y[sg] + s * slab_stride; the consumer sums
-    const void* scales;            // marlin: [K/g, N] in marlin-permuted order, dtype = out_dtype
-    int group_size, k;             // marlin
+    const void* scales;            // marlin: [K/g, N] in marlin-permuted order (f16 / bf16: scale_bf16); fp8: f32 [N/by, K/bx]
+    int group_size, k;             // marlin group size / fp8 bx
+    int scale_bf16, scale_by, scale_sk;
+    const float* norm;             // fp8: {2^p, 2^-p} range shift of the tile scales (device)
     long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
     int debug;                     // profiling aid (B200_GEMM_DEBUG): 1 = skip MMA issue, 2 = skip dequant, 4 = skip epilogue stores
 };
@@ -281,7 +283,7 @@ struct Q4KQuarter {
 // nibbles are k = 0..31 and high nibbles k = 32..63 of the chunk -- the same nibble geometry as a Q4_K chunk, so the
 // subnormal-placement + HFMA2 trick applies unchanged: w = s*q - 8*s with one per-group scale s
 // (/root/reference/src/backend/gptq.rs:115-178 call site; scales arrive marlin-permuted, linear.rs:341-379).
-struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg; };
+struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg, by, sk; const float* norm; };   // by / sk: fp8 scale-tile rows, scale columns; norm: fp8 range shift
 __device__ __forceinline__ int marlin_scale_pos(int n, bool grouped) {
     // inverse of marlin_permute_scales: position of original column n inside its permuted block
     if (grouped) { const int b = n & 63; return (n & ~63) | (8 * (b & 7) + (b >> 3)); }
@@ -333,6 +335,39 @@ struct M4Quarter {
                 v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0); v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
                 v[16 + 2 * i] = *reinterpret_cast<const uint32_t*>(&r2); v[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r3);
             }
+        }
+        tc_st32(a_col + kC * 32, v);
+    }
+};
+
+// Block-scaled FP8 (fp8_matmul): a unit is 128 rows x 256 e4m3 bytes, staged as two {128 B x 128 rows} TMA boxes with the
+// 128-byte swizzle (a plain 256-byte row pitch would put a warp's 16-byte reads 8 deep on the same banks).  Quarter kC =
+// 64 bytes of this thread's row; cvt.rn.f16x2.e4m3x2 expands two weights per instruction, one HMUL2 applies the tile scale
+// (group_size = bx must be a multiple of 64 so a quarter sees one scale).  Natural k order: the activation copy is plain fp16.
+template <int kC>
+struct F8Quarter {
+    static constexpr int kRaw = 16;
+    static __device__ __forceinline__ void load(const uint8_t* stage, int row, uint32_t (&raw)[kRaw]) {
+        const uint8_t* base = stage + (kC >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + ((((kC & 1) * 4 + i) ^ (row & 7)) << 4));
+            raw[4 * i] = v.x; raw[4 * i + 1] = v.y; raw[4 * i + 2] = v.z; raw[4 * i + 3] = v.w;
+        }
+    }
+    static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
+        // norm[0] = power of two that moves the largest tile scale to [32, 64): scaled weights then sit in fp16's normal
+        // range whatever the checkpoint's scale magnitude (DeepSeek-style scales are ~1e-4); the finishing pass undoes it
+        const float sc = static_cast<const float*>(c.scales)[(int64_t)(c.n_idx / c.by) * c.sk + (c.k0 + kC * 64) / c.group_size] * __ldg(c.norm);
+        const __half2 S = __float2half2_rn(sc);
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(raw[i] & 0xffffu), __NV_E4M3);
+            const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(raw[i] >> 16), __NV_E4M3);
+            const __half2 r0 = __hmul2(__half2(lo), S), r1 = __hmul2(__half2(hi), S);
+            v[2 * i] = *reinterpret_cast<const uint32_t*>(&r0);
+            v[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
         }
         tc_st32(a_col + kC * 32, v);
     }
@@ -441,6 +476,7 @@ template <int kType, int kQ> struct QuarterOf;
 template <int kQ> struct QuarterOf<B200_GGML_Q4_K, kQ> { using type = Q4KQuarter<kQ>; };
 template <int kQ> struct QuarterOf<B200_GGML_Q6_K, kQ> { using type = Q6KQuarter<kQ>; };
 template <int kQ> struct QuarterOf<kTypeM4, kQ> { using type = M4Quarter<kQ>; };
+template <int kQ> struct QuarterOf<kTypeF8, kQ> { using type = F8Quarter<kQ>; };
 
 // =================================================================================================
 // One dequant unit for quarter kQ: pull the raw bytes into registers, hand the W stage back to the producer at
@@ -461,7 +497,7 @@ __device__ __forceinline__ void dequant_unit(const uint8_t* blk, int off, uint32
     mbar_wait(a_free_bar, a_free_parity);
     tc_fence_after();
     if (!skip) {
-        if constexpr (kType == kTypeM4) Q::compute(raw, mc, a_col); else Q::compute(raw, off, a_col);
+        if constexpr (kType == kTypeM4 || kType == kTypeF8) Q::compute(raw, mc, a_col); else Q::compute(raw, off, a_col);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
@@ -536,6 +572,10 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 // W box start (bytes): Q4_K blocks are 144 B (16-aligned); Q6_K blocks (210 B) start at the block address
                 // rounded down to 16 -- TMA box starts must be 16-byte aligned
                 mbar_expect_tx(w_full(s), C::kWBytes);
+                if constexpr (kType == kTypeF8) {       // two 128-byte-swizzled boxes per unit
+                    tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), sb * 256, ltile * kTileN, pol_w);
+                    tma_load_2d(smem_base + C::kWOff + s * C::kWBytes + 16384, wm, w_full(s), sb * 256 + 128, ltile * kTileN, pol_w);
+                } else
                 tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : (kType == kTypeM4 ? sb * 128 : ((sb * 210) & ~15)),
                             ltile * kTileN, pol_w);
             }
@@ -622,13 +662,13 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             for (; u < seg_end; ++u, ++it) {
                 mbar_wait(w_full(ws), wph);
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 4] = clock64();
-                const uint8_t* blk = smem + C::kWOff + ws * C::kWBytes + row * C::kBlk;
+                const uint8_t* blk = smem + C::kWOff + ws * C::kWBytes + (kType == kTypeF8 ? 0 : row * C::kBlk);    // fp8: stage base (swizzled rows)
                 const uint32_t a_col = tmem + kColA + ab * 128 + lane_addr;
-                const int off = kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15);   // Q6_K: block offset in its window
+                const int off = kType == kTypeF8 ? row : (kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15));   // Q6_K: block offset in its window
                 const uint32_t afp = aph ^ 1;
                 const bool skip = (p.debug & 2) != 0;
                 const M4Ctx mc{p.scales, p.n[0], p.group_size, (int)(u - tile_begin) * kSB, tile * kTileN + row < p.n[0] ? tile * kTileN + row : 0,
-                               p.out_dtype == B200_BF16, p.debug};
+                               p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm};
                 switch (qt) {
                     case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                     case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
@@ -677,11 +717,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                         if (mi < p.m) {
                             float* o = ybase + (int64_t)mi * p.ldy + n_idx;
                             const float val = __uint_as_float(acc[i]);
-                            if (p.out_dtype != B200_F32) {          // marlin: 16-bit output, whole tiles only
-                                const int64_t oi = (int64_t)mi * p.ldy + n_idx;
-                                if (p.out_dtype == B200_BF16) reinterpret_cast<__nv_bfloat16*>(ybase)[oi] = __float2bfloat16_rn(val);
-                                else reinterpret_cast<__half*>(ybase)[oi] = __float2half_rn(val);
-                            } else if (p.slabs > 0) {
+                            if (p.slabs > 0) {
                                 *o = val;
                                 for (int z = 1; z <= zero_slabs; ++z) o[(int64_t)z * p.slab_stride] = 0.f;
                             } else if (whole && !p.accumulate) *o = val;
@@ -744,16 +780,59 @@ void launch(const CUtensorMap* wm, const CUtensorMap& xm, const GemmParams& p, c
 
 bool make_w_map(CUtensorMap* wm, const void* w, int n, int nsb, int ggml_type) {
     EncodeTiledFn enc = encode_fn();
-    const bool q4 = ggml_type == B200_GGML_Q4_K, m4 = ggml_type == kTypeM4;
-    // byte tensor [n][nsb * block]; box {144, 128} (Q4_K), {128, 128} (int4) or {240, 128} (Q6_K: 210-byte block + alignment slack)
-    const cuuint64_t dims[2] = {(cuuint64_t)nsb * (q4 ? 144 : (m4 ? 128 : 210)), (cuuint64_t)n};
-    const cuuint64_t strides[1] = {(cuuint64_t)nsb * (q4 ? 144 : (m4 ? 128 : 210))};
-    const cuuint32_t box[2] = {(cuuint32_t)(q4 ? 144 : (m4 ? 128 : 240)), (cuuint32_t)kTileN};
+    const bool q4 = ggml_type == B200_GGML_Q4_K, m4 = ggml_type == kTypeM4, f8 = ggml_type == kTypeF8;
+    // byte tensor [n][nsb * block]; box {144, 128} (Q4_K), {128, 128} (int4; fp8 with the 128-byte swizzle, two per unit) or
+    // {240, 128} (Q6_K: 210-byte block + alignment slack)
+    const cuuint64_t pitch = (cuuint64_t)nsb * (q4 ? 144 : (m4 ? 128 : (f8 ? 256 : 210)));
+    const cuuint64_t dims[2] = {pitch, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)(q4 ? 144 : ((m4 || f8) ? 128 : 240)), (cuuint32_t)kTileN};
     const cuuint32_t es[2] = {1, 1};
     const CUresult r = enc(wm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           f8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: weight tensor map failed (%d)", (int)r); return false; }
     return true;
+}
+
+// fp8: norm = {2^p, 2^-p} with max|scale| * 2^p in [32, 64)
+__global__ void fp8_scale_norm_kernel(const float* __restrict__ scale, int64_t count, float* __restrict__ norm) {
+    pdl_wait();
+    pdl_trigger();
+    float mx = 0.f;
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) mx = fmaxf(mx, fabsf(scale[i]));
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+        int e = 0;
+        if (mx > 0.f && mx < 3.0e38f) { frexpf(mx, &e); e = 6 - e; }           // mx = f * 2^e', f in [0.5, 1): mx * 2^(6 - e') in [32, 64)
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        norm[0] = ldexpf(1.f, e); norm[1] = ldexpf(1.f, -e);
+    }
+}
+
+// out[m,n] (f16 / bf16) = sum of the fp32 slabs (+ bias): the finishing pass of the 16-bit-output GEMMs below
+template <typename T>
+__global__ void finish_slabs_kernel(const float* __restrict__ slabs, int n_slabs, int64_t slab_stride, const T* __restrict__ bias,
+                                    T* __restrict__ out, int64_t total, int n, const float* __restrict__ norm) {
+    pdl_wait();
+    pdl_trigger();
+    const float post = norm ? norm[1] : 1.f;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (int64_t)gridDim.x * blockDim.x * 4) {
+        float4 a = *reinterpret_cast<const float4*>(slabs + i);
+        for (int sl = 1; sl < n_slabs; ++sl) {
+            const float4 b = *reinterpret_cast<const float4*>(slabs + sl * slab_stride + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        a.x *= post; a.y *= post; a.z *= post; a.w *= post;
+        if (bias) { const int c = (int)(i % n); a.x += to_f32(bias[c]); a.y += to_f32(bias[c + 1]); a.z += to_f32(bias[c + 2]); a.w += to_f32(bias[c + 3]); }
+        T o[4] = {from_f32<T>(a.x), from_f32<T>(a.y), from_f32<T>(a.z), from_f32<T>(a.w)};
+        *reinterpret_cast<uint2*>(out + i) = *reinterpret_cast<const uint2*>(o);
+    }
 }
 
 }  // namespace
@@ -825,7 +904,7 @@ int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* c
         if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: activation tensor map failed (%d)", (int)r); return 0; }
     }
     if ((int64_t)tiles * nsb * sm_count() >= (int64_t)1 << 31) { set_error(kErrUnsupported, "qmatmul: %d tiles x %d super-blocks exceed the 32-bit unit range", tiles, nsb); return 0; }
-    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate; p.out_dtype = B200_F32;
+    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
     p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
     if (slabs_avail > 0) {
         p.slabs = qmatmul_tc_slab_count(tiles, nsb);
@@ -841,33 +920,71 @@ int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* c
     return p.slabs;
 }
 
-// symmetric int4 x fp16 (marlin_4bit_*): w in the gptq_repack() layout, scales marlin-permuted, 16-bit output
-void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
-               cudaStream_t st) {
+// ---- weight-only GEMMs with 16-bit output (marlin_4bit_*, fp8_matmul) ----------------------------------------------
+// stream-K over all SMs with fp32 partial-sum slabs in the caller's scratch, then one small finishing pass that adds the
+// slabs (and the bias) and rounds once to f16 / bf16.  scratch = [S][m][n] f32, S = wq16_slabs(n, k).
+int wq16_slabs(int n, int k) { return qmatmul_tc_slab_count((n + kTileN - 1) / kTileN, k / 256); }
+
+static void wq16_launch(int kind, const void* x_f16, const void* w, const void* scales, int scale_bf16, int group_or_bx, int by, int sk,
+                        const float* norm, const void* bias, void* out, int out_dtype, int m, int n, int k, float* slabs, cudaStream_t st,
+                        const char* who) {
     EncodeTiledFn enc = encode_fn();
-    if (!enc) { set_error(kErrCuda, "marlin: cuTensorMapEncodeTiled unavailable"); return; }
+    if (!enc) { set_error(kErrCuda, "%s: cuTensorMapEncodeTiled unavailable", who); return; }
+    if (((uintptr_t)x_f16 | (uintptr_t)w) & 15) { set_error(kErrBadArg, "%s: x and weights must be 16-byte aligned", who); return; }
     const int nsb = k / 256;
     const int mb = m <= 32 ? 32 : 64;
     CUtensorMap wm[kMaxSeg], xm;
-    for (int i = 0; i < kMaxSeg; ++i) if (!make_w_map(&wm[i], w, n, nsb, kTypeM4)) return;
+    for (int i = 0; i < kMaxSeg; ++i) if (!make_w_map(&wm[i], w, n, nsb, kind)) return;
     {
         const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
         const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
         const cuuint32_t box[2] = {64, (cuuint32_t)mb};
         const cuuint32_t es[2] = {1, 1};
-        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16_k4), dims, strides, box, es,
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "marlin: activation tensor map failed (%d)", (int)r); return; }
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "%s: activation tensor map failed (%d)", who, (int)r); return; }
     }
     GemmParams p{};
     const int tiles = (n + kTileN - 1) / kTileN;
-    for (int i = 0; i < kMaxSeg; ++i) { p.y[i] = static_cast<float*>(out); p.n[i] = n; p.tile_end[i] = i == 0 ? tiles : 0x7fffffff; }
-    p.ldy = n; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = 0; p.out_dtype = out_dtype; p.whole_tiles = 1;
-    p.scales = scales; p.group_size = group_size; p.k = k;
+    for (int i = 0; i < kMaxSeg; ++i) { p.y[i] = slabs; p.n[i] = n; p.tile_end[i] = i == 0 ? tiles : 0x7fffffff; }
+    p.ldy = n; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = 0;
+    p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
+    p.slabs = qmatmul_tc_slab_count(tiles, nsb);
+    p.slab_stride = (int64_t)m * n;
+    p.scales = scales; p.group_size = group_or_bx; p.k = k; p.scale_bf16 = scale_bf16; p.scale_by = by; p.scale_sk = sk; p.norm = norm;
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-    if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st);
-    check_launch("marlin_tc");
+    if (kind == kTypeM4) { if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st); }
+    else { if (mb == 32) launch<32, kTypeF8>(wm, xm, p, st); else launch<64, kTypeF8>(wm, xm, p, st); }
+    if (!check_launch(who)) return;
+    const int64_t total = (int64_t)m * n;
+    int64_t g = (total / 4 + 255) / 256;
+    if (g > (int64_t)sm_count() * 4) g = (int64_t)sm_count() * 4;
+    if (out_dtype == B200_BF16)
+        launch_pdl(finish_slabs_kernel<__nv_bfloat16>, dim3((int)g), dim3(256), 0, st, (const float*)slabs, p.slabs, p.slab_stride, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, total, n, norm);
+    else
+        launch_pdl(finish_slabs_kernel<__half>, dim3((int)g), dim3(256), 0, st, (const float*)slabs, p.slabs, p.slab_stride, (const __half*)bias, (__half*)out, total, n, norm);
+    count_launch();
+    check_launch(who);
+}
+
+// symmetric int4 x fp16 (marlin_4bit_*): w in the gptq_repack() layout, scales marlin-permuted, activations fp16 in K4 order
+void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
+               float* slabs, cudaStream_t st) {
+    wq16_launch(kTypeM4, x_f16_k4, w, scales, out_dtype == B200_BF16, group_size, 1, 0, nullptr, nullptr, out, out_dtype, m, n, k, slabs, st, "marlin_4bit");
+}
+
+// block-scaled e4m3 weights x fp16 (fp8_matmul); activations fp16 in natural order
+bool fp8_tc_supported(int m, int n, int k, int by, int bx) {
+    if (m < 1 || m > 64 || n < 4 || n % 4 || k < 256 || k % 256 || by < 1 || bx < 64 || bx % 64) return false;
+    return (int64_t)((n + kTileN - 1) / kTileN + 2) * (k / 256) * sm_count() < ((int64_t)1 << 30);
+}
+void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void* bias, void* out, int out_dtype, int m, int n, int k,
+                int by, int bx, float* slabs, float* norm, cudaStream_t st) {
+    const int sk = (k + bx - 1) / bx;
+    launch_pdl(fp8_scale_norm_kernel, dim3(1), dim3(256), 0, st, scale, (int64_t)((n + by - 1) / by) * sk, norm);
+    count_launch();
+    wq16_launch(kTypeF8, x_f16, w, scale, 0, bx, by, sk, norm, bias, out, out_dtype, m, n, k, slabs, st, "fp8_matmul");
 }
 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,

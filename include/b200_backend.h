@@ -169,6 +169,26 @@ void gemm_half_q_half_alt(const void* x, const uint32_t* qweight, const uint32_t
                           const int32_t* g_idx, void* out, int32_t m, int32_t n, int32_t k, int32_t bits, int64_t stream);
 void b200_set_scratch(void* device_ptr, size_t bytes);
 
+/* ---- K10 / K11 / K12: weight-only low-precision float linears -- replace attention_rs::{fp8_linear::fp8_matmul,
+ * nvfp4_linear::nvfp4_matmul, mxfp4_linear::mxfp4_matmul} (call sites /root/reference/src/openai/models/linear.rs:1190-1221,
+ * :1913-1943, :1717-1757; tensor layouts :944-973, :1812-1853, :1686-1700).
+ * out[m,n] = x[m,k] . dequant(W[n,k])^T (+ bias[n]); x, bias, out are f16 or bf16 (`dtype`), fp32 accumulation.
+ *   fp8_matmul : weight e4m3 bytes [n,k]; weight_scale f32 [ceil(n/block_y), ceil(k/block_x)] multiplies its tile
+ *                (default tile [128,128]).  m <= 64, k % 256 == 0, block_x % 64 == 0 run on the tcgen05 pipeline (weights
+ *                scaled and rounded to fp16, activations fp16); other shapes on a SIMT kernel with exact fp32 weights.
+ *   nvfp4_matmul: blocks u8 [n,k/2] (two e2m1 per byte, low nibble = even k), scales e4m3 [n,k/16], global_scale f32
+ *                (the reciprocal / weight_scale_2 value the reference computes, linear.rs:1829-1853); input_scale is ignored
+ *                (weight-only product).  k % 32 == 0.
+ *   mxfp4_matmul: blocks u8 [n,k/2], scales e8m0 [n,k/32]: w = e2m1 * 2^(scale - 127).  k % 32 == 0.
+ * Parity is unpinned upstream (no fixtures; the kernels live in attention-rs): the oracle (oracle/fp_formats.py) follows the
+ * OCP / NVFP4 format definitions and torch.float8_e4m3fn. */
+void fp8_matmul(const void* x, const void* weight, const float* weight_scale, const void* bias, void* out, int32_t m, int32_t n,
+                int32_t k, int32_t block_y, int32_t block_x, int32_t dtype, int64_t stream);
+void nvfp4_matmul(const void* x, const void* blocks, const void* scales, float global_scale, float input_scale, const void* bias,
+                  void* out, int32_t m, int32_t n, int32_t k, int32_t dtype, int64_t stream);
+void mxfp4_matmul(const void* x, const void* blocks, const void* scales, const void* bias, void* out, int32_t m, int32_t n,
+                  int32_t k, int32_t dtype, int64_t stream);
+
 /* ---- K15 / K21: the elementwise ops between the big ones ------------------------------------
  * rms_norm: candle_nn::ops::rms_norm (layers/qrmsnorm.rs:28-31).  out_dtype F32 or F16. */
 void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int32_t n, float eps,

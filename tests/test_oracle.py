@@ -174,3 +174,24 @@ def test_bf16_round_matches_torch():
     x = np.random.default_rng(2).standard_normal(10000).astype(np.float32) * 100
     assert np.array_equal(LL.bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
     assert np.array_equal(LL.bf16_bits_to_f32(LL.f32_to_bf16_bits(x)), LL.bf16_round(x))
+
+
+def test_fp_format_decoders_pinned():
+    """e4m3fn / e8m0 decoders against torch's dtypes (all 256 codes), e2m1 against the OCP MX v1.0 value table; nibble order of
+    the packed fp4 tensors (low nibble = even k, the layout of the reference's `blocks` / `weight_packed` tensors)."""
+    import torch
+    from oracle import fp_formats as F
+    b = np.arange(256, dtype=np.uint8)
+    t = torch.from_numpy(b.copy()).view(torch.float8_e4m3fn).float().numpy()
+    assert np.array_equal(np.nan_to_num(F.e4m3_to_f32(b), nan=777.0), np.nan_to_num(t, nan=777.0))
+    if hasattr(torch, "float8_e8m0fnu"):
+        t8 = torch.from_numpy(b.copy()).view(torch.float8_e8m0fnu).float().numpy().astype(np.float64)
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(np.nan_to_num(F.e8m0_to_f32(b), nan=-1.0), np.nan_to_num(t8, nan=-1.0))
+    assert F.e2m1_to_f32(np.arange(16, dtype=np.uint8)).tolist() == [0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0,
+                                                                      -0.0, -0.5, -1.0, -1.5, -2.0, -3.0, -4.0, -6.0]
+    assert F.unpack_fp4(np.array([[0x21, 0xF7]], np.uint8)).tolist() == [[0.5, 1.0, 6.0, -6.0]]
+    # block scale broadcast: scale[i, j] covers rows [i*by, (i+1)*by) x cols [j*bx, (j+1)*bx)
+    w = np.full((3, 4), 0x38, np.uint8)                   # 1.0 in e4m3
+    s = np.array([[2.0, 3.0], [5.0, 7.0]], np.float32)
+    assert F.dequant_fp8_block(w, s, 2, 2).tolist() == [[2, 2, 3, 3], [2, 2, 3, 3], [5, 5, 7, 7]]
