@@ -238,6 +238,14 @@ def run_b200(args):
     model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, tp_rank=rank, tp_world=world,
                           nccl_comm=comm.handle.value if comm else None)
     stream = model.stream
+    inboxes = None
+    if world > 1:
+        # row-parallel all-reduce + residual add + next RMSNorm as one kernel over NVLink peer memory (falls back to NCCL if
+        # CUDA IPC is not available between the ranks, or with B200_TP_NCCL=1)
+        from candle_vllm_b200.distributed import PeerInboxes
+        inboxes = PeerInboxes(model, rank, world)
+        if not inboxes.active and rank == 0:
+            print(f"[bench] peer inboxes inactive, all-reduce through NCCL: {inboxes.error or 'B200_TP_NCCL set'}", file=sys.stderr)
 
     def barrier():
         if world > 1:
@@ -298,6 +306,9 @@ def run_b200(args):
 
     # ---- (3) roofline of the dominant kernel: paged-attention decode, timed alone per layer ---------
     roof = attention_roofline(pkg, model, cfg, eng, B, cur, tables, world, stream, dev)
+    peer_ar = inboxes is not None and inboxes.active
+    if inboxes is not None:
+        inboxes.close()                            # collective (barrier): before any rank leaves
 
     if rank != 0:
         if world > 1:
@@ -316,7 +327,7 @@ def run_b200(args):
             "dtype": "f16 activations x q4_k/q6_k weights (fp32 accumulate), bf16 attention", "data": "synthetic",
             "config": {"workload": f"Llama-3-8B Q4_K (lm_head Q6_K) decode, batch {B}, ctx {ctx_first}->{ctx_last} of 4096->5120, "
                                    f"block_size {bs}, {args.kv} paged KV, random non-contiguous block tables",
-                       "parallelism": f"tp{world}", "global_batch": B, "layers": cfg.num_layers,
+                       "parallelism": f"tp{world}" + ("" if world == 1 else (" (fused all-reduce + add + norm over NVLink peer memory)" if peer_ar else " (NCCL all-reduce)")), "global_batch": B, "layers": cfg.num_layers,
                        "l2_policy": "inputs larger than L2 (KV 17+ GB and weights 4.4 GB streamed per step; 126 MB L2)"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "prepare_decode (host) + GGUFLLaMa.decode -> b200_llama_decode (C ABI, host buffers)"},

@@ -22,7 +22,8 @@ SYMBOLS = [
     "b200_abi_version", "b200_last_error", "b200_last_error_message", "b200_device_sm_count", "b200_device_cc",
     "copy_blocks_bf16", "copy_blocks_f16", "copy_blocks_f32", "copy_blocks_u8", "swap_blocks", "reshape_and_cache",
     "paged_attention_decode_workspace_bytes", "paged_attention_decode", "paged_attention_prefill",
-    "qmatmul_workspace_bytes", "qmatmul_f32", "qmatmul_f16act", "qmatmul_slab_count", "qmatmul_f16act_slabs", "dequantize_f32", "fp8_matmul", "nvfp4_matmul", "mxfp4_matmul",
+    "qmatmul_workspace_bytes", "qmatmul_f32", "qmatmul_f16act", "qmatmul_slab_count", "qmatmul_f16act_slabs", "b200_llama_peer_inbox_bytes", "b200_llama_set_peer_inboxes", "b200_llama_peer_timeouts", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free",
+    "dequantize_f32", "fp8_matmul", "nvfp4_matmul", "mxfp4_matmul",
     "rms_norm", "fused_rope_f32", "silu_mul", "add_f32", "cast", "embedding_f32", "argmax_f32", "rope_and_cache",
     "b200_llama_create", "b200_llama_destroy", "b200_llama_set_layer", "b200_llama_set_globals",
     "b200_llama_set_kv_cache", "b200_llama_set_comm", "b200_llama_decode", "b200_llama_decode_resident",
@@ -46,6 +47,9 @@ def lib() -> C.CDLL:
         L.paged_attention_decode_workspace_bytes.restype = C.c_size_t
         L.qmatmul_workspace_bytes.restype = C.c_size_t
         L.b200_llama_create.restype = C.c_void_p
+        L.b200_llama_peer_inbox_bytes.restype = C.c_size_t
+        L.b200_ipc_alloc.restype = C.c_void_p
+        L.b200_ipc_open.restype = C.c_void_p
         L.b200_llama_logits.restype = C.c_void_p
         L.b200_llama_next_tokens.restype = C.c_void_p
         L.b200_llama_kernel_launches.restype = C.c_int64

@@ -26,6 +26,10 @@ extern "C" long long b200_total_kernel_launches(void);
 namespace b200 {
 void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st);
 void tp_allgather_bytes(void* comm, const void* src, void* dst, size_t bytes_per_rank, cudaStream_t st);
+size_t tp_peer_inbox_bytes(int world, int rows_max, int n);
+size_t tp_peer_timeout_offset(int world, int rows_max, int n);
+void tp_allreduce_add_norm(float* partial, float* x, const float* norm_w, void* xn_f16_k4, void* const* peers, int rank, int world,
+                           int rows, int n, int rows_max, float eps, cudaStream_t st);
 void argmax_pairs(const float* logits, void* pairs, int rows, int n, int chunks, int index_offset, cudaStream_t st);
 void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st);
 }
@@ -40,6 +44,7 @@ struct b200_llama {
     std::vector<void*> kc, vc;
     int64_t num_blocks = 0;
     void* comm = nullptr;
+    std::vector<void*> peers;                 // every rank's inbox (CUDA IPC mappings; peers[tp_rank] is local): fused all-reduce
 
     // local (tensor-parallel shard) sizes
     int heads_l, kv_l, ffn_l, vocab_l, qkv_row;
@@ -107,9 +112,15 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
     const long long n0 = b200_total_kernel_launches();
     constexpr int kArgmaxChunks = 16;
     embedding_f32(m->tok_embeddings, m->d_tokens, m->x, B, H, s);
+    // tensor parallel with peer inboxes: the all-reduce of the row-parallel GEMMs, the residual add and the NEXT RMSNorm are
+    // one kernel over NVLink peer memory (tp.cu); `partial` is left zeroed by that kernel for the next split-K GEMM
+    const bool fused_ar = c.tp_world > 1 && (int)m->peers.size() == c.tp_world;
+    auto residual_fused = [&](const float* next_norm) {
+        tp_allreduce_add_norm(m->partial, m->x, next_norm, m->xn, m->peers.data(), c.tp_rank, c.tp_world, B, H, c.max_num_seqs, c.rms_eps, st);
+    };
     for (int l = 0; l < c.num_layers; ++l) {
         const b200_llama_layer& w = m->layers[l];
-        rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+        if (!fused_ar || l == 0) rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
         // QKV / gate / up accumulate (split-K) into buffers that their consumers leave zeroed
         {   // fused QKV: three weight matrices, one launch
             const void* ws[3] = {w.wq, w.wk, w.wv};
@@ -126,6 +137,9 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
                                B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16_K4, m->attn_ws, m->attn_ws_bytes, s);
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->attn16, w.wo, m->x, H, B, H, qd, w.to, 1, st);          // x += wo(attn)
+        } else if (fused_ar) {
+            qmatmul_dispatch(m->attn16, w.wo, m->partial, H, B, H, qd, w.to, 1, st);
+            residual_fused(w.ffn_norm);                                                    // x += sum_ranks(partial); xn = ffn_norm(x)
         } else {
             // row-parallel: partial sums -> all-reduce -> residual add (distributed.rs:696-710)
             launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->partial, (int64_t)B * H); count_launch();
@@ -133,7 +147,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);   // tp.cu (NCCL)
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
-        rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+        if (!fused_ar) rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
         {   // fused gate | up
             const void* ws[2] = {w.w1, w.w3};
             const int ts[2] = {w.t1, w.t3}, ns[2] = {m->ffn_l, m->ffn_l};
@@ -143,6 +157,9 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
         silu_mul_zero_src(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, s);      // act = silu(gate)*up; gate/up re-zeroed
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->act16, w.w2, m->x, H, B, H, m->ffn_l, w.t2, 1, st);     // x += w2(act)
+        } else if (fused_ar) {
+            qmatmul_dispatch(m->act16, w.w2, m->partial, H, B, H, m->ffn_l, w.t2, 1, st);
+            residual_fused(l + 1 < c.num_layers ? m->layers[l + 1].attn_norm : m->norm);
         } else {
             launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->partial, (int64_t)B * H); count_launch();
             qmatmul_dispatch(m->act16, w.w2, m->partial, H, B, H, m->ffn_l, w.t2, 1, st);
@@ -150,6 +167,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
     }
+    if (!fused_ar)
     rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
     if (qmatmul_tc_supported(B, m->vocab_l, H, m->output_type) && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) {
         launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
@@ -309,6 +327,35 @@ void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const
     m->num_blocks = num_blocks;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);    // pointers are baked into captured graphs
     m->graphs.clear();
+}
+
+size_t b200_llama_peer_inbox_bytes(const b200_llama* m) {
+    return m ? tp_peer_inbox_bytes(m->cfg.tp_world, m->cfg.max_num_seqs, m->cfg.hidden) : 0;
+}
+
+void b200_llama_set_peer_inboxes(b200_llama* m, void* const* inboxes, int32_t count) {
+    B200_REQUIRE(m, kErrBadArg, "b200_llama_set_peer_inboxes: null model");
+    if (!inboxes || count == 0) { m->peers.clear(); }
+    else {
+        B200_REQUIRE(count == m->cfg.tp_world && count <= 8, kErrBadArg, "b200_llama_set_peer_inboxes: %d inboxes for tp_world %d (max 8)", count, m->cfg.tp_world);
+        B200_REQUIRE(m->cfg.hidden % 4 == 0 && m->cfg.hidden <= 8192, kErrUnsupported, "b200_llama_set_peer_inboxes: hidden %d", m->cfg.hidden);
+        for (int i = 0; i < count; ++i) B200_REQUIRE(inboxes[i], kErrBadArg, "b200_llama_set_peer_inboxes: null inbox %d", i);
+        m->peers.assign(inboxes, inboxes + count);
+    }
+    cudaMemset(m->partial, 0, (size_t)m->cfg.max_num_seqs * m->cfg.hidden * sizeof(float));     // the fused kernel keeps it zeroed from here on
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);    // the forward changes shape
+    m->graphs.clear();
+}
+
+int32_t b200_llama_peer_timeouts(b200_llama* m) {
+    if (!m || m->peers.empty()) return 0;
+    uint32_t v = 0;
+    const char* mine = static_cast<const char*>(m->peers[m->cfg.tp_rank]);
+    if (cudaMemcpy(&v, mine + tp_peer_timeout_offset(m->cfg.tp_world, m->cfg.max_num_seqs, m->cfg.hidden), 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error(kErrCuda, "b200_llama_peer_timeouts: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return (int32_t)v;
 }
 
 void b200_llama_set_comm(b200_llama* m, void* nccl_comm) {

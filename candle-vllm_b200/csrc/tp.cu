@@ -4,6 +4,8 @@
 // process creates the communicator); no link-time dependency.
 #include <dlfcn.h>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -39,7 +41,195 @@ void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st) {
     if (rc != 0) set_error(kErrCuda, "tp_allreduce: ncclAllReduce rc=%d", rc);
 }
 
+// ---- fused all-reduce over NVLink peer memory ------------------------------------------------------------------------
+// Replaces {zero partial, GEMM, ncclAllReduce, add, rms_norm} of the row-parallel linears by {GEMM, this kernel}
+// (reference semantics: AllReduce::cuda_fwd + residual add + RmsNorm, /root/reference/src/openai/distributed.rs:572-653,
+// quantized_llama.rs:470-488).  Two hops over NVLink / NVSwitch, no fences, no separate flags:
+//   * token row r is OWNED by rank r % world: only the owner keeps the fp32 residual stream of that row;
+//   * hop 1 (reduce): every other rank pushes its partial row into the owner's gather slot as {value, epoch} 8-byte words
+//     (NCCL's "LL" idea: an aligned 8-byte store is atomic, so the epoch travelling WITH the datum is the ready flag --
+//     a measured fence + flag protocol cost two extra NVLink round trips per all-reduce);
+//   * the owner polls the words, adds the partials in rank order (one fp32 result per row, bitwise identical for every
+//     consumer), adds the residual, applies the NEXT RMSNorm and
+//   * hop 2 (broadcast): pushes the normalised fp16 row (what the next GEMM consumes, K4 order) to every rank as
+//     {half2, epoch} words.  Non-owners poll their copy.  Per all-reduce a rank sends (w-1)/w x 32 KB/row out and 16 KB/row x
+//     (w-1) for its own rows: 1.35 MB at world 8, B = 32, against 3.6 MB for a one-shot exchange.
+// Buffers are double-buffered by epoch parity: a rank cannot be two all-reduces ahead of a peer because each one needs that
+// peer's words.  One CTA per row; every CTA of a launch is resident (rows <= 148).
+struct PeerSet { char* p[8]; };
+
+__device__ __forceinline__ void st_ll(void* addr, uint32_t a, uint32_t b, uint32_t e) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(e), "r"(b), "r"(e) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const void* addr) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr) : "memory");
+    return v;
+}
+
+// bounded spin: a peer that never shows up (crashed rank) must not wedge the GPU -- after ~4 s the row gives up, poisons its
+// output with NaN and raises the inbox's timeout word (host-visible through b200_llama_peer_timeouts)
+__device__ __forceinline__ bool ll_wait(const void* addr, uint32_t e, uint4& w, uint32_t* timeout_word) {
+    w = ld_ll(addr);
+    if (w.y == e && w.w == e) return true;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        w = ld_ll(addr);
+        if (w.y == e && w.w == e) return true;
+        if ((spins & 0x3ffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) { *timeout_word = 1u; w = make_uint4(0x7fc00000u, e, 0x7fc00000u, e); return false; }
+        }
+    }
+}
+
+struct InboxLayout {
+    size_t gather_bytes, bcast_off, epoch_off, total;
+    int rows_owned;
+    __host__ __device__ InboxLayout(int world, int rows_max, int n) {
+        rows_owned = (rows_max + world - 1) / world;
+        gather_bytes = (size_t)2 * world * rows_owned * n * 8;              // [par][src][owned row][n] x {f32, epoch}
+        bcast_off = (gather_bytes + 255) & ~(size_t)255;
+        const size_t bcast_bytes = (size_t)2 * rows_max * (n / 2) * 8;       // [par][row][n/2] x {half2, epoch}
+        epoch_off = (bcast_off + bcast_bytes + 255) & ~(size_t)255;
+        total = epoch_off + (((size_t)rows_max * 4 + 4 + 255) & ~(size_t)255);        // epochs + one timeout word
+    }
+};
+
+__global__ void __launch_bounds__(256)
+tp_allreduce_add_norm_kernel(float* __restrict__ partial, float* __restrict__ x, const float* __restrict__ norm_w, __half* __restrict__ xn,
+                             PeerSet peers, int rank, int world, int n, int rows_max, float eps) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int kMaxIt = 8;                                 // rows up to 8192 columns stay in registers
+    const int row = blockIdx.x, nv = n >> 2;
+    const InboxLayout lay(world, rows_max, n);
+    char* const mine = peers.p[rank];
+    uint32_t* epoch = reinterpret_cast<uint32_t*>(mine + lay.epoch_off);
+    const uint32_t e = epoch[row] + 1u;
+    __syncthreads();                                          // everyone has read the epoch before thread 0 may bump it at the end
+    const int par = (int)(e & 1u);
+    const int owner = row % world, lrow = row / world;
+    // my partial -> registers (and leave the accumulator zeroed for the next split-K GEMM)
+    float4* pr = reinterpret_cast<float4*>(partial + (int64_t)row * n);
+    float4 v[kMaxIt];
+#pragma unroll
+    for (int it = 0; it < kMaxIt; ++it) {
+        const int i = threadIdx.x + it * 256;
+        if (i < nv) { v[it] = pr[i]; pr[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+    __half* o = xn + (int64_t)row * n;
+    if (rank != owner) {
+        // hop 1: my partial -> the owner's gather slot [par][rank][lrow]
+        char* dst = peers.p[owner] + (((size_t)par * world + rank) * lay.rows_owned + lrow) * n * 8;
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int i = threadIdx.x + it * 256;
+            if (i < nv) {
+                st_ll(dst + (size_t)i * 32, __float_as_uint(v[it].x), __float_as_uint(v[it].y), e);
+                st_ll(dst + (size_t)i * 32 + 16, __float_as_uint(v[it].z), __float_as_uint(v[it].w), e);
+            }
+        }
+        // hop 2: wait for the owner's normalised row in my broadcast slot [par][row]
+        const char* src = mine + lay.bcast_off + ((size_t)par * rows_max + row) * (n / 2) * 8;
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int i = threadIdx.x + it * 256;            // 4 halves = 2 words = one 16-byte LL pair
+            if (i < nv) {
+                uint4 w;
+                ll_wait(src + (size_t)i * 16, e, w, epoch + rows_max);
+                *reinterpret_cast<uint2*>(o + 4 * i) = make_uint2(w.x, w.z);
+            }
+        }
+    } else {
+        // owner: gather the peers' partials (rank order -> one well-defined fp32 sum), residual add, RMSNorm
+        float4* xr = reinterpret_cast<float4*>(x + (int64_t)row * n);
+        float ss = 0.f;
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int i = threadIdx.x + it * 256;
+            if (i < nv) {
+                float4 a = xr[i];
+                for (int p = 0; p < world; ++p) {
+                    if (p == rank) { a.x += v[it].x; a.y += v[it].y; a.z += v[it].z; a.w += v[it].w; continue; }
+                    const char* src = mine + (((size_t)par * world + p) * lay.rows_owned + lrow) * n * 8 + (size_t)i * 32;
+                    uint4 w0, w1;
+                    ll_wait(src, e, w0, epoch + rows_max);
+                    ll_wait(src + 16, e, w1, epoch + rows_max);
+                    a.x += __uint_as_float(w0.x); a.y += __uint_as_float(w0.z); a.z += __uint_as_float(w1.x); a.w += __uint_as_float(w1.z);
+                }
+                xr[i] = a;
+                v[it] = a;
+                ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+            }
+        }
+        __shared__ float red[8];
+        ss = warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        const float sc = rsqrtf(tot / (float)n + eps);
+        const float4* wr = reinterpret_cast<const float4*>(norm_w);
+#pragma unroll
+        for (int it = 0; it < kMaxIt; ++it) {
+            const int i = threadIdx.x + it * 256;
+            if (i < nv) {
+                const float4 g = __ldg(wr + i);
+                // K4 order: the middle two of every four swapped (include/b200_backend.h)
+                const __half2 p0 = __floats2half2_rn(v[it].x * sc * g.x, v[it].z * sc * g.z), p1 = __floats2half2_rn(v[it].y * sc * g.y, v[it].w * sc * g.w);
+                const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&p0), u1 = *reinterpret_cast<const uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(o + 4 * i) = make_uint2(u0, u1);
+                // hop 2: broadcast to every other rank's slot [par][row]
+                for (int p = 0; p < world; ++p)
+                    if (p != rank) st_ll(peers.p[p] + lay.bcast_off + ((size_t)par * rows_max + row) * (n / 2) * 8 + (size_t)i * 16, u0, u1, e);
+            }
+        }
+    }
+    if (threadIdx.x == 0) epoch[row] = e;
+}
+
+size_t tp_peer_inbox_bytes(int world, int rows_max, int n) { return InboxLayout(world, rows_max, n).total; }
+size_t tp_peer_timeout_offset(int world, int rows_max, int n) { return InboxLayout(world, rows_max, n).epoch_off + (size_t)rows_max * 4; }
+
+void tp_allreduce_add_norm(float* partial, float* x, const float* norm_w, void* xn_f16_k4, void* const* peers, int rank, int world,
+                           int rows, int n, int rows_max, float eps, cudaStream_t st) {
+    if (world < 2 || world > 8 || n % 4 || n > 8192 || rows > 128) { set_error(kErrUnsupported, "tp_allreduce_add_norm: world %d, n %d, rows %d", world, n, rows); return; }
+    PeerSet ps{};
+    for (int i = 0; i < world; ++i) ps.p[i] = static_cast<char*>(peers[i]);
+    launch_pdl(tp_allreduce_add_norm_kernel, dim3(rows), dim3(256), 0, st, partial, x, norm_w, static_cast<__half*>(xn_f16_k4), ps, rank, world, n,
+               rows_max, eps);
+    count_launch();
+    check_launch("tp_allreduce_add_norm");
+}
+
 }  // namespace b200
+
+// ---- CUDA IPC plumbing for the peer inboxes (one process per GPU) --------------------------------------------------------------
+extern "C" void* b200_ipc_alloc(size_t bytes, void* handle_out) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { b200::set_error(b200::kErrCuda, "b200_ipc_alloc: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { b200::set_error(b200::kErrCuda, "b200_ipc_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); cudaFree(p); cudaGetLastError(); return nullptr; }
+    memcpy(handle_out, &h, sizeof(h));
+    cudaDeviceSynchronize();
+    return p;
+}
+extern "C" void* b200_ipc_open(const void* handle) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { b200::set_error(b200::kErrCuda, "b200_ipc_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void b200_ipc_close(void* p) { if (p) cudaIpcCloseMemHandle(p); }
+extern "C" void b200_ipc_free(void* p) { if (p) cudaFree(p); }
 
 extern "C" void b200_allreduce_f32(void* nccl_comm, float* buf, int64_t n, int64_t stream) {
     b200::tp_allreduce_f32(nccl_comm, buf, n, b200::as_stream(stream));

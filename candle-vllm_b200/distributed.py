@@ -80,3 +80,77 @@ class Comm:
         if self.handle:
             _libnccl().ncclCommDestroy(self.handle)
             self.handle = C.c_void_p(0)
+
+
+class PeerInboxes:
+    """NVLink peer-memory inboxes for the engine's fused all-reduce (``b200_llama_set_peer_inboxes``): allocate ours, swap the
+    CUDA IPC handles over ``torch.distributed``, map the peers'.  ``B200_TP_NCCL=1`` keeps the engine on NCCL; so does any
+    rank failing to allocate / map (``.active`` is False on ALL ranks then, ``.error`` says why)."""
+
+    def __init__(self, model, rank: int, world: int, group=None):
+        self.model, self.rank, self.world = model, rank, world
+        self.mine, self.mapped, self.error = None, [], ""
+        if world == 1 or os.environ.get("B200_TP_NCCL", "0") not in ("", "0"):
+            return
+        L = lib()
+        on_gpu = dist.get_backend(group) == "nccl"
+        nbytes = int(L.b200_llama_peer_inbox_bytes(model._h))
+        handle = (C.c_ubyte * 64)()
+        ok, self.error = True, ""
+        # every rank walks through the same collectives whatever happens locally; success is agreed on at the end
+        mine_ptr = L.b200_ipc_alloc(C.c_size_t(nbytes), handle)
+        if L.b200_last_error() or not mine_ptr:
+            ok, self.error, mine_ptr = False, "b200_ipc_alloc: " + L.b200_last_error_message().decode(), None
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8)
+        mine = mine.cuda() if on_gpu else mine
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        ptrs = []
+        for r in range(world):
+            if r == rank or not ok:
+                ptrs.append(mine_ptr)
+                continue
+            h = (C.c_ubyte * 64)(*gathered[r].cpu().numpy().tolist())
+            p = L.b200_ipc_open(h)
+            if L.b200_last_error() or not p:
+                ok, self.error = False, "b200_ipc_open: " + L.b200_last_error_message().decode()
+                ptrs.append(None)
+                continue
+            self.mapped.append(p)
+            ptrs.append(p)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        flag = flag.cuda() if on_gpu else flag
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # also the barrier: every inbox is mapped and zeroed
+        if int(flag.item()) == 0:
+            for p in self.mapped:
+                L.b200_ipc_close(C.c_void_p(p))
+            if mine_ptr:
+                L.b200_ipc_free(C.c_void_p(mine_ptr))
+            self.mapped = []
+            self.error = self.error or "a peer rank could not map the inboxes"
+            return                                                     # inactive: the engine stays on NCCL
+        self.mine = mine_ptr
+        arr = (C.c_void_p * world)(*ptrs)
+        L.b200_llama_set_peer_inboxes(model._h, arr, C.c_int32(world))
+        check("b200_llama_set_peer_inboxes")
+
+    @property
+    def active(self) -> bool:
+        return self.mine is not None
+
+    def timed_out(self) -> bool:
+        """True when some row gave up waiting for a peer (a rank died); results are NaN from then on."""
+        return self.active and int(lib().b200_llama_peer_timeouts(self.model._h)) != 0
+
+    def close(self, group=None) -> None:
+        if self.mine is None:
+            return
+        L = lib()
+        torch.cuda.synchronize()
+        L.b200_llama_set_peer_inboxes(self.model._h, None, C.c_int32(0))
+        if dist.is_initialized():
+            dist.barrier(group=group)                   # nobody is still pushing into an inbox that is about to go away
+        for p in self.mapped:
+            L.b200_ipc_close(C.c_void_p(p))
+        L.b200_ipc_free(C.c_void_p(self.mine))
+        self.mine, self.mapped = None, []

@@ -246,6 +246,20 @@ void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const
                              int64_t num_blocks);
 /* tensor-parallel all-reduce hook: an NCCL communicator (ncclComm_t) created by the host */
 void b200_llama_set_comm(b200_llama* m, void* nccl_comm);
+/* Tensor parallel over NVLink peer memory: every rank allocates an inbox of b200_llama_peer_inbox_bytes() with
+ * b200_ipc_alloc (cudaMalloc + zero + CUDA IPC handle), the handles travel over the host control plane, every rank maps its
+ * peers' inboxes with b200_ipc_open and hands all `tp_world` pointers (its own at index tp_rank) to the engine.  The
+ * row-parallel linears then run {GEMM, one fused kernel}: push the partial row to every peer, epoch flags, local sum, residual
+ * add and the next RMSNorm (replaces AllReduce::cuda_fwd + add + RmsNorm, distributed.rs:572-653).  Without inboxes the engine
+ * uses NCCL on the communicator of b200_llama_set_comm.  count = 0 switches back. */
+size_t b200_llama_peer_inbox_bytes(const b200_llama* m);
+void b200_llama_set_peer_inboxes(b200_llama* m, void* const* inboxes, int32_t count);
+/* 1 when a row of the fused all-reduce gave up waiting for a peer (~4 s: a rank died); its outputs are NaN from then on */
+int32_t b200_llama_peer_timeouts(b200_llama* m);
+void* b200_ipc_alloc(size_t bytes, void* handle_out_64_bytes);
+void* b200_ipc_open(const void* handle_64_bytes);
+void b200_ipc_close(void* mapped);
+void b200_ipc_free(void* allocated);
 /* One decode step from HOST metadata (what prepare_decode builds, inputs.rs:376-454):
  * tokens u32[B], positions i64[B], slot_mapping i64[B], context_lens u32[B],
  * block_tables u32[B, table_width].  Copies them into the static device buffers (async, pinned

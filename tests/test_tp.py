@@ -79,7 +79,7 @@ def _nccl_worker(rank, world, port, out):
         tables = synthetic.random_block_tables(4, 4, nb, seed=2)
         lens, toks = [10, 64, 65, 200], [5, 9, 700, 33]
 
-        def run(tp_rank, tp_world, comm_handle):
+        def run(tp_rank, tp_world, comm_handle, peer=False):
             w = synthetic.make_weights(cfg, dev, seed=0, tp_rank=tp_rank, tp_world=tp_world)
             eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim, pkg.CacheConfig(cfg.block_size, nb), device=dev,
                                   num_shards=tp_world)
@@ -87,16 +87,25 @@ def _nccl_worker(rank, world, port, out):
             for k, v in eng.gpu_cache:                          # start from empty context instead so results are comparable
                 k.zero_(); v.zero_()
             model = pkg.GGUFLLaMa(cfg, w, eng.gpu_cache, tp_rank=tp_rank, tp_world=tp_world, nccl_comm=comm_handle)
+            inbox = None
+            if peer:                                            # fused all-reduce over NVLink peer memory instead of NCCL
+                from candle_vllm_b200.distributed import PeerInboxes
+                inbox = PeerInboxes(model, tp_rank, tp_world)
+                assert inbox.active
             outs, L, T = [], [1, 1, 1, 1], list(toks)
-            for _ in range(6):                                  # decode from an empty cache: context grows 1..6
+            for _ in range(12 if peer else 6):                  # decode from an empty cache: context grows 1..
                 nxt, _ = model.decode(pkg.prepare_decode(L, T, tables, cfg.block_size))
                 outs.append(nxt.copy()); T = [int(t) for t in nxt]; L = [x + 1 for x in L]
+            if inbox is not None:
+                inbox.close()
             return np.stack(outs)
 
         tp = run(rank, world, comm.handle.value)
+        tp_peer = run(rank, world, comm.handle.value, peer=True)
         if rank == 0:
             ref = run(0, 1, None)
-            out.put(bool(np.array_equal(tp, ref)))
+            # NCCL path; peer-memory path (its first 6 steps are the same decode, then 6 more graph replays: epochs, parity)
+            out.put(bool(np.array_equal(tp, ref)) and bool(np.array_equal(tp_peer[:6], ref)))
         dist.barrier()
         comm.destroy()
     finally:
