@@ -73,7 +73,7 @@ def _nccl_worker(rank, world, port, out):
     try:
         from candle_vllm_b200.distributed import Comm
         comm = Comm(rank, world)
-        cfg = pkg.LlamaConfig(hidden=512, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=128, ffn=1024, vocab=768,
+        cfg = pkg.LlamaConfig(hidden=512, num_layers=2, num_heads=8, num_kv_heads=4, head_dim=128, ffn=1024, vocab=768,
                               max_pos=512, block_size=64, max_num_seqs=8, max_blocks_per_seq=8)
         nb = 24
         tables = synthetic.random_block_tables(4, 4, nb, seed=2)
@@ -113,13 +113,16 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-def test_tp2_decode_matches_tp1_on_two_gpus():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_decode_matches_tp1(world):
+    """NCCL all-reduce path and the fused peer-memory all-reduce (CUDA IPC inboxes) against the unsharded model: same greedy
+    tokens.  world = 4 also exercises rows owned by ranks that hold no sequence (4 sequences, owners r % 4) and epoch parity."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs: p.start()
     for p in procs: p.join(300)
     assert all(p.exitcode == 0 for p in procs)
