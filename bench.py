@@ -104,6 +104,22 @@ def cpu_sample_setup(batch: int, ctx: int):
 
     keep = (ws, norms, kc, vc, bt, ctx_lens, pos, slots, cos, sin, x, scratch, layer, cfg)   # raw pointers inside
 
+    # all the host threads that HELP: OpenMP's default is the logical CPU count, which can exceed what the container may use
+    # (measured on the GPU box: 128 threads were 10x slower than 64).  Calibrate on the Q6_K slice and keep the fastest.
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cands = sorted({max(1, avail), max(1, avail // 2), max(1, avail // 4)}, reverse=True)
+    timing = {}
+    for n_thr in cands:
+        cpu_ref.set_num_threads(n_thr)
+        cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)                   # warm the team
+        t0 = time.perf_counter()
+        cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)
+        timing[n_thr] = time.perf_counter() - t0
+    cpu_ref.set_num_threads(min(timing, key=timing.get))
+
     def step():
         """one bounded sample -> seconds for a FULL decode step (scaled)"""
         assert keep

@@ -28,6 +28,8 @@
 // layers/attention.rs:707-718, :983-994; metadata pipelines/inputs.rs:552-568).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "attention.cuh"
@@ -428,6 +430,8 @@ bool make_kv_map(CUtensorMap* map, const void* cache, int64_t num_blocks, int kv
 }
 
 int pick_chunk_pages(int num_seqs, int kvh, int max_blocks) {
+    static const int forced = [] { const char* e = getenv("B200_ATTN_CHUNK_PAGES"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (forced >= 1 && forced <= kMaxChunkPages) return forced;
     int chunk = kMaxChunkPages;
     const int64_t want = 4ll * sm_count();
     while (chunk > 1 && (int64_t)num_seqs * kvh * ((max_blocks + chunk - 1) / chunk) < want) chunk >>= 1;

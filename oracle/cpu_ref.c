@@ -64,6 +64,16 @@ int ref_num_threads(void) {
 #endif
 }
 
+/* bench.py picks the thread count that is actually fastest on the box (logical CPUs can exceed the cores the container may use) */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+
 /* ---- Q8_K activation quantisation (candle BlockQ8K::from_float [UPSTREAM]) ---------------- */
 void ref_quantize_row_q8_K(const float* x, void* vy, int k) {
     block_q8_K* y = (block_q8_K*)vy;

@@ -51,6 +51,10 @@ def num_threads() -> int:
     return int(lib().ref_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    lib().ref_set_num_threads(C.c_int(int(n)))
+
+
 def qmatmul_q8k(x: np.ndarray, w: np.ndarray, ggml_type: int, n: int, k: int) -> np.ndarray:
     x = np.ascontiguousarray(x, np.float32).reshape(-1, k)
     w = np.ascontiguousarray(w, np.uint8)
