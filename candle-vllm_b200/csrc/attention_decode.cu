@@ -432,9 +432,15 @@ bool make_kv_map(CUtensorMap* map, const void* cache, int64_t num_blocks, int kv
 int pick_chunk_pages(int num_seqs, int kvh, int max_blocks) {
     static const int forced = [] { const char* e = getenv("B200_ATTN_CHUNK_PAGES"); return e ? atoi(e) : 0; }();   // tuning aid
     if (forced >= 1 && forced <= kMaxChunkPages) return forced;
+    // Measured (tools/attn_check.py, B = 32, ctx 4400): with 8 kv heads 8-page chunks win (5.82 TB/s vs 5.76 / 5.65 for 4 / 2
+    // pages); with 4 or 1 kv heads per rank (tensor-parallel shards) 4-page chunks win by 7-8 % -- too few items leave the
+    // dynamic queue nothing to balance.  So: 8 pages while that still gives every warp ~2 items, otherwise 4, and smaller
+    // only when the whole problem is tiny.
+    auto items = [&](int c) { return (int64_t)num_seqs * kvh * ((max_blocks + c - 1) / c); };
     int chunk = kMaxChunkPages;
-    const int64_t want = 4ll * sm_count();
-    while (chunk > 1 && (int64_t)num_seqs * kvh * ((max_blocks + chunk - 1) / chunk) < want) chunk >>= 1;
+    if (items(chunk) < 2ll * sm_count() * kWarps) chunk >>= 1;
+    const int64_t want = 3ll * sm_count();
+    while (chunk > 1 && items(chunk) < want) chunk >>= 1;
     return chunk;
 }
 
