@@ -6,7 +6,7 @@
 // row-major int4 layout (same number of words; only marlin_4bit_* reads it, so the layout is private to the
 // library exactly as Marlin's tile layout is private to attention-rs).  Pre-repacked "marlin" checkpoints
 // (checkpoint_format == "marlin", linear.rs:219-220) carry Marlin's own tile order and are NOT accepted.
-// The GEMM runs on the tcgen05 dequant pipeline of qmatmul_tc.cu (whole-tile decomposition, 16-bit output).
+// The GEMM runs on the tcgen05 dequant pipeline of qmatmul_tc.cu (stream-K into fp32 slabs + a finishing pass to 16 bit).
 // Supported: 4-bit symmetric, group size 64 / 128 / -1, no act-order, f16 / bf16, m <= 64, k % 256 == 0 -- the set the
 // reference itself repacks to Marlin (linear.rs:319-325).  Anything else records kErrUnsupported.
 #include "qmatmul.cuh"

@@ -1,30 +1,30 @@
-// qmatmul_tc.cu -- tcgen05 dequant-GEMM for GGML Q4_K / Q6_K weights at decode batch sizes (m <= 64).
+// qmatmul_tc.cu -- tcgen05 dequant-GEMM for weight-only quantised linears at decode batch sizes (m <= 64):
+// GGML Q4_K / Q6_K (QMatMul), symmetric int4 (marlin_4bit_*) and block-scaled FP8 (fp8_matmul).
 //
-//   y[m, n] (+)= sum_k x[m, k] * dequant(W)[n, k]        W = verbatim GGUF Q4_K blocks, row-major over n
+//   y[m, n] (+)= sum_k x[m, k] * dequant(W)[n, k]        W row-major over n, verbatim checkpoint bytes (GGUF blocks, ...)
 //
-// The op is an HBM-bound weight stream (0.5625 B/weight, 114 flop/B at m = 32); the tensor core is
-// there so that the CUDA cores only have to DEQUANTISE, never multiply:
-//   * "swap-AB": the weight tile is the UMMA A operand (M = 128 weight rows), the activations are the
-//     B operand (N = 32 or 64 batch rows), D[128 x N] fp32 lives in TMEM.
-//   * warp 8 (one lane) streams raw Q4_K super-blocks with TMA: a 2-D byte tensor map over W with a
-//     {144 B, 128 rows} box (one super-block column of the tile = 18 KB) plus the matching 256-wide
-//     slice of the fp16 activations (4 swizzled {64, N} boxes) into a 6-stage mbarrier ring.
-//   * warps 0-7 dequantise: thread = weight row = TMEM lane.  Each thread reads its own 144-byte
-//     block from shared memory (conflict-free LDS.128), decodes the 6-bit scales/mins, turns nibbles
-//     into fp16 with a subnormal bit trick (nibble placed in mantissa bits 6-9 = q * 2^-18, one HFMA2
-//     with (d*sc*2^18, -dmin*m) gives d*sc*q - dmin*m with a single rounding) and writes the fp16 row
-//     straight into TMEM (tcgen05.st) as the A operand -- the dequantised weights never touch shared
-//     memory.  Nibble pairs come out as (k0,k2),(k1,k3) per 4 weights; instead of permuting them the
-//     activations are stored in the matching "K4" order (see B200_F16_K4 in the header).
-//   * warp 9 (one lane) issues tcgen05.mma kind::f16 (A from TMEM, B from the swizzled smem tile),
-//     16 k-steps per super-block, commits to the stage / A-buffer barriers.
-//   * persistent stream-K: the (tile, super-block) space is cut into one contiguous range per CTA, so
-//     every SM streams the same number of bytes; tile segments are reduced with fp32 red.global.add
-//     (the residual add of wo / w2 falls out for free), whole tiles are stored.
+// The op is an HBM-bound weight stream (0.5625 B/weight for Q4_K, 114 flop/B at m = 32); the tensor core is there so that
+// the CUDA cores only have to DEQUANTISE, never multiply.  19 warps per CTA, one CTA per SM, persistent:
+//   * "swap-AB": the weight tile is the UMMA A operand (M = 128 weight rows), the activations are the B operand
+//     (N = 32 or 64 batch rows), D[128 x N] fp32 lives in TMEM (two accumulators, folded in the epilogue).
+//   * W producer warp: raw weight bytes of one unit (128 rows x 256 weights: 18 KB for Q4_K) by TMA into a deep ring that
+//     the dequant warps hand back as soon as the bytes are in registers.  X producer warp: the matching 256-wide slice of
+//     the fp16 activations (4 swizzled {64, N} boxes, L2 resident) into a shallow ring released by the MMA commit.
+//   * 16 dequant warps: thread = weight row = TMEM lane; warp w serves lane quadrant w & 3 and quarter w >> 2 (64 weights)
+//     of the unit.  Nibbles become fp16 with a subnormal bit trick (nibble in mantissa bits 6-9 = q * 2^-18, one HFMA2 with
+//     (d*sc*2^18, -dmin*m) gives d*sc*q - dmin*m with a single rounding) and go straight into TMEM (tcgen05.st) as the
+//     A operand (3 buffers) -- dequantised weights never touch shared memory.  Nibble pairs come out as (k0,k2),(k1,k3)
+//     per 4 weights; instead of permuting them the activations are stored in the matching "K4" order (B200_F16_K4).
+//   * MMA warp: warp-uniform loop, one elected lane issues tcgen05.mma kind::f16 (A from TMEM, B from the swizzled smem
+//     tile), 16 k-steps per unit, commits to the X-stage / A-buffer barriers.
+//   * stream-K: the (tile, unit) space is cut into one contiguous range per CTA (whole tiles per CTA when there are >= 4
+//     tiles per SM); split tiles are reduced with fp32 red.global.add (the residual add of wo / w2 falls out for free) or
+//     written to per-CTA slabs (deterministic mode; the 16-bit-output GEMMs add a finishing pass).
+// Measured behaviour, fixes and dead ends: DESIGN.md 4.2, profiles/r01_qmatmul_tc_ncu.md.
 //
-// Reference semantics: QMatMul::forward (/root/reference/src/openai/models/linear.rs:765-806); block
-// format SURVEY.md Appendix A.  The reference's CUDA path quantises activations to Q8_1 and uses
-// dp4a; here activations are fp16 and accumulation fp32 (strictly closer to the fp32 target).
+// Reference semantics: QMatMul::forward (/root/reference/src/openai/models/linear.rs:765-806); block formats SURVEY.md
+// Appendix A.  The reference's CUDA path quantises activations to Q8_1 and uses dp4a; here activations are fp16 and
+// accumulation fp32 (strictly closer to the fp32 target).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -186,15 +186,8 @@ __device__ __forceinline__ int seg_of_tile(const GemmParams& p, int tile) { retu
 // first tile of segment sg (constant indices only: dynamic indexing would spill the parameter struct to local memory)
 __device__ __forceinline__ int seg_first_tile(const GemmParams& p, int sg) { return sg == 0 ? 0 : (sg == 1 ? p.tile_end[0] : p.tile_end[1]); }
 
-// 6-bit scale / min of sub-block J from the 12 packed bytes held in three 32-bit words (ggml get_scale_min_k4)
-template <int J>
-__device__ __forceinline__ void scale_min(uint32_t s0, uint32_t s1, uint32_t s2, int& sc, int& mn) {
-    auto byte = [&](int i) -> uint32_t { return ((i < 4 ? s0 : (i < 8 ? s1 : s2)) >> (8 * (i & 3))) & 0xffu; };
-    if constexpr (J < 4) { sc = byte(J) & 63; mn = byte(J + 4) & 63; }
-    else { sc = (byte(J + 4) & 0xF) | ((byte(J - 4) >> 6) << 4); mn = (byte(J + 4) >> 4) | ((byte(J) >> 6) << 4); }
-}
-
-// the two 6-bit scales and mins of sub-blocks 2kC and 2kC+1, packed as (lo | hi << 16) integers
+// the two 6-bit scales and mins of sub-blocks 2kC and 2kC+1 from the 12 packed bytes held in three 32-bit words
+// (ggml get_scale_min_k4), packed as (lo | hi << 16) integers
 template <int kC>
 __device__ __forceinline__ void scale_min_pair(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t& sc2, uint32_t& mn2) {
     constexpr uint32_t sel = (kC & 1) ? 0x4342u : 0x4140u;       // bytes (2,3) or (0,1) of a word -> low bytes of the two halves
