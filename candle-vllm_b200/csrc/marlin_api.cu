@@ -7,8 +7,10 @@
 // library exactly as Marlin's tile layout is private to attention-rs).  Pre-repacked "marlin" checkpoints
 // (checkpoint_format == "marlin", linear.rs:219-220) carry Marlin's own tile order and are NOT accepted.
 // The GEMM runs on the tcgen05 dequant pipeline of qmatmul_tc.cu (stream-K into fp32 slabs + a finishing pass to 16 bit).
-// Supported: 4-bit symmetric, group size 64 / 128 / -1, no act-order, f16 / bf16, m <= 64, k % 256 == 0 -- the set the
-// reference itself repacks to Marlin (linear.rs:319-325).  Anything else records kErrUnsupported.
+// Marlin path: 4-bit, group size 64 / 128 / -1, no act-order, f16 / bf16, m <= 64, k % 256 == 0 -- the set the reference itself
+// repacks to Marlin (linear.rs:319-325) -- symmetric GPTQ (marlin_4bit_*) and AWQ with zero points (awq_repack +
+// marlin_awq_4bit_*, zero points in the layout of examples/convert_awq_marlin.py).  Everything else (act-order, asymmetric GPTQ,
+// 8 bit) takes the shape-generic gemm_half_q_half_alt kernel, as in the reference (gptq.rs:182-197).
 #include "qmatmul.cuh"
 
 namespace b200 {
@@ -27,6 +29,68 @@ __global__ void gptq_repack_kernel(const uint32_t* __restrict__ in, uint32_t* __
         for (int j = 0; j < 4; ++j) o |= (((lo >> (4 * j)) & 0xFu) | (((hi >> (4 * j)) & 0xFu) << 4)) << (8 * j);
         out[(int64_t)col * k_packed + wk] = o;
     }
+}
+
+// AWQ checkpoint layout: u32 [K, N/8], nibble i of word (k, j) = q[k][8 j + order[i]], order = [0,2,4,6,1,3,5,7] (AutoAWQ).
+// Same private output layout as gptq_repack: [n][k/8 words], byte b of 64-k chunk c: low nibble q[64c + b][n], high q[64c + 32 + b][n].
+__global__ void awq_repack_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int k, int n_packed) {
+    const int n = n_packed * 8, kw = k / 8;
+    const int64_t total = (int64_t)kw * n;                  // output words: [n][k / 8]
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % n);                       // consecutive threads -> consecutive n
+        const int wk = (int)(i / n);
+        const int c = wk >> 3, w = wk & 7;
+        const int sh = 4 * ((0x73625140u >> (4 * (col & 7))) & 7);     // nibble that holds column (col & 7): inverse of the order
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 4 * w + j;
+            const uint32_t lo = (in[(int64_t)(64 * c + b) * n_packed + (col >> 3)] >> sh) & 0xFu;
+            const uint32_t hi = (in[(int64_t)(64 * c + 32 + b) * n_packed + (col >> 3)] >> sh) & 0xFu;
+            o |= (lo | (hi << 4)) << (8 * j);
+        }
+        out[(int64_t)col * kw + wk] = o;
+    }
+}
+
+// Conventional GPTQ (act-order and / or asymmetric, 4 or 8 bit): the shape-generic path behind gemm_half_q_half_alt
+// (call site /root/reference/src/backend/gptq.rs:182-197).  qweight [K / pack, N] packed along K, qzeros [G, N / pack] packed
+// along N and stored minus one (GPTQ v1), scales f16 [G, N], group of row k = g_idx[k].  One thread per output column
+// (coalesced weight words), 8 activation rows per pass, fp32 accumulation, f16 output.
+template <int kBits>
+__global__ void __launch_bounds__(128)
+gptq_alt_kernel(const __half* __restrict__ x, const uint32_t* __restrict__ qw, const uint32_t* __restrict__ qz, const __half* __restrict__ sc,
+                const int32_t* __restrict__ g_idx, __half* __restrict__ out, int m, int n, int k) {
+    constexpr int kPack = 32 / kBits;
+    constexpr uint32_t kMask = (1u << kBits) - 1u;
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    const int m0 = blockIdx.y * 8;
+    if (col >= n) return;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    int g_prev = -1;
+    float s = 0.f, z = 0.f;
+    for (int kp = 0; kp < k / kPack; ++kp) {
+        const uint32_t word = qw[(int64_t)kp * n + col];
+#pragma unroll
+        for (int j = 0; j < kPack; ++j) {
+            const int kk = kp * kPack + j;
+            const int g = g_idx[kk];
+            if (g != g_prev) {                               // act-order: the group can change at any row
+                g_prev = g;
+                s = __half2float(sc[(int64_t)g * n + col]);
+                z = (float)(((qz[(int64_t)g * (n / kPack) + col / kPack] >> (kBits * (col % kPack))) & kMask) + 1u);
+            }
+            const float wv = ((float)((word >> (kBits * j)) & kMask) - z) * s;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (m0 + i < m) acc[i] += __half2float(x[(int64_t)(m0 + i) * k + kk]) * wv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (m0 + i < m) out[(int64_t)(m0 + i) * n + col] = __float2half_rn(acc[i]);
 }
 
 // activation scratch (fp16, K4 order): the reference ABI has no slot for it (its `workspace` is N words of locks),
@@ -53,12 +117,13 @@ void* get_scratch(size_t bytes, cudaStream_t st) {
 }
 
 static void marlin_4bit(const void* x, const void* qweight, const void* scales, const void* qzeros, const void* g_idx, void* out,
-                        int m, int k, int n, int group_size, int dtype, int64_t stream) {
+                        int m, int k, int n, int group_size, int dtype, bool awq, int64_t stream) {
     if (m == 0 || n == 0) return;
     B200_REQUIRE(x && qweight && scales && out, kErrBadArg, "marlin_4bit: null pointer");
+    B200_REQUIRE(!awq || qzeros, kErrBadArg, "marlin_awq_4bit: qzeros (marlin zero-point layout, examples/convert_awq_marlin.py) is required");
     B200_REQUIRE(m > 0 && n > 0 && k > 0, kErrBadArg, "marlin_4bit: bad sizes m=%d k=%d n=%d", m, k, n);
     B200_REQUIRE(g_idx == nullptr, kErrUnsupported, "marlin_4bit: act-order (g_idx) is not supported (linear.rs:319-325 never repacks it)");
-    (void)qzeros;                                      // symmetric: zero point 8 (the reference passes qzeros but Marlin ignores them)
+    if (!awq) qzeros = nullptr;                        // symmetric: zero point 8 (the reference passes qzeros but Marlin ignores them)
     B200_REQUIRE(group_size == -1 || group_size == 64 || group_size == 128, kErrUnsupported, "marlin_4bit: group size %d (64, 128, -1)", group_size);
     B200_REQUIRE(k % 256 == 0 && n % 64 == 0, kErrUnsupported, "marlin_4bit: k %% 256 and n %% 64 must be 0 (k=%d n=%d)", k, n);
     B200_REQUIRE(m <= 64, kErrUnsupported, "marlin_4bit: m = %d > 64 (decode batches only in this round)", m);
@@ -68,7 +133,7 @@ static void marlin_4bit(const void* x, const void* qweight, const void* scales, 
     char* xs = static_cast<char*>(get_scratch(x_bytes + (size_t)wq16_slabs(n, k) * m * n * 4, st));
     if (!xs) return;
     cast(x, xs, (int64_t)m * k, dtype, B200_F16_K4, stream);
-    marlin_tc(xs, qweight, scales, out, dtype, m, n, k, group_size, reinterpret_cast<float*>(xs + x_bytes), st);
+    marlin_tc(xs, qweight, scales, qzeros, out, dtype, m, n, k, group_size, reinterpret_cast<float*>(xs + x_bytes), st);
 }
 
 }  // namespace b200
@@ -96,27 +161,48 @@ void gptq_repack(const void* in, void* out, int32_t k_packed, int32_t n, int64_t
 void marlin_4bit_f16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx, void* out,
                      int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream) {
     (void)workspace;
-    marlin_4bit(x, qweight, scales, qzeros, g_idx, out, m, k, n, group_size, B200_F16, stream);
+    marlin_4bit(x, qweight, scales, qzeros, g_idx, out, m, k, n, group_size, B200_F16, false, stream);
 }
 void marlin_4bit_bf16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx, void* out,
                       int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream) {
     (void)workspace;
-    marlin_4bit(x, qweight, scales, qzeros, g_idx, out, m, k, n, group_size, B200_BF16, stream);
+    marlin_4bit(x, qweight, scales, qzeros, g_idx, out, m, k, n, group_size, B200_BF16, false, stream);
 }
-void marlin_awq_4bit_f16(const void*, const int32_t*, const void*, const void*, const void*, void*, int32_t, int32_t, int32_t,
-                         const void*, int32_t, int64_t) {
-    set_error(kErrUnsupported, "marlin_awq_4bit_f16: AWQ (zero-point) int4 is not implemented in this round");
+void marlin_awq_4bit_f16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx, void* out,
+                         int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream) {
+    (void)workspace;
+    marlin_4bit(x, qweight, scales, qzeros, g_idx, out, m, k, n, group_size, B200_F16, true, stream);
 }
-void marlin_awq_4bit_bf16(const void*, const int32_t*, const void*, const void*, const void*, void*, int32_t, int32_t, int32_t,
-                          const void*, int32_t, int64_t) {
-    set_error(kErrUnsupported, "marlin_awq_4bit_bf16: AWQ (zero-point) int4 is not implemented in this round");
+void marlin_awq_4bit_bf16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx, void* out,
+                          int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream) {
+    (void)workspace;
+    marlin_4bit(x, qweight, scales, qzeros, g_idx, out, m, k, n, group_size, B200_BF16, true, stream);
 }
-void awq_repack(const void*, void*, int32_t, int32_t, int32_t, int64_t) {
-    set_error(kErrUnsupported, "awq_repack: AWQ int4 is not implemented in this round");
+void awq_repack(const void* in, void* out, int32_t k, int32_t n_packed, int32_t bits, int64_t stream) {
+    B200_REQUIRE(in && out && k > 0 && n_packed > 0, kErrBadArg, "awq_repack: bad arguments");
+    B200_REQUIRE(bits == 4, kErrUnsupported, "awq_repack: %d-bit AWQ (4 only)", bits);
+    B200_REQUIRE(k % 64 == 0, kErrUnsupported, "awq_repack: K must be a multiple of 64 (k=%d)", k);
+    const int64_t total = (int64_t)(k / 8) * n_packed * 8;
+    int64_t g = (total + 255) / 256;
+    if (g > (int64_t)sm_count() * 16) g = (int64_t)sm_count() * 16;
+    awq_repack_kernel<<<(int)g, 256, 0, as_stream(stream)>>>((const uint32_t*)in, (uint32_t*)out, k, n_packed);
+    count_launch();
+    check_launch("awq_repack");
 }
-void gemm_half_q_half_alt(const void*, const uint32_t*, const uint32_t*, const void*, const int32_t*, void*, int32_t, int32_t, int32_t,
-                          int32_t, int64_t) {
-    set_error(kErrUnsupported, "gemm_half_q_half_alt: act-order / asymmetric GPTQ is not implemented in this round");
+void gemm_half_q_half_alt(const void* x, const uint32_t* qweight, const uint32_t* qzeros, const void* scales, const int32_t* g_idx, void* out,
+                          int32_t m, int32_t n, int32_t k, int32_t bits, int64_t stream) {
+    if (m == 0 || n == 0) return;
+    B200_REQUIRE(x && qweight && qzeros && scales && out && m > 0 && n > 0 && k > 0, kErrBadArg, "gemm_half_q_half_alt: bad arguments");
+    B200_REQUIRE(g_idx, kErrBadArg, "gemm_half_q_half_alt: g_idx is required (the group of every weight row)");
+    B200_REQUIRE(bits == 4 || bits == 8, kErrUnsupported, "gemm_half_q_half_alt: %d-bit weights (4 or 8)", bits);
+    B200_REQUIRE(k % (32 / bits) == 0 && n % (32 / bits) == 0, kErrBadArg, "gemm_half_q_half_alt: k and n must be multiples of %d", 32 / bits);
+    const dim3 grid(ceil_div(n, 128), ceil_div(m, 8));
+    if (bits == 4)
+        gptq_alt_kernel<4><<<grid, 128, 0, as_stream(stream)>>>((const __half*)x, qweight, qzeros, (const __half*)scales, g_idx, (__half*)out, m, n, k);
+    else
+        gptq_alt_kernel<8><<<grid, 128, 0, as_stream(stream)>>>((const __half*)x, qweight, qzeros, (const __half*)scales, g_idx, (__half*)out, m, n, k);
+    count_launch();
+    check_launch("gemm_half_q_half_alt");
 }
 
 }  // extern "C"

@@ -39,9 +39,9 @@ int qmatmul_slabs_needed(int nseg, const int* n, const int* types, int m, int k)
 // 16-bit-output weight-only GEMMs on the tcgen05 pipeline: fp32 partial-sum slabs ([wq16_slabs][m][n] f32, caller scratch)
 // + a finishing pass.  m <= 64, k % 256 == 0.
 int wq16_slabs(int n, int k);
-// symmetric int4 (GPTQ, repacked by gptq_repack) x fp16 activations in K4 order
-void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
-               float* slabs, cudaStream_t st);
+// int4 (GPTQ symmetric / AWQ with zero points; repacked by gptq_repack / awq_repack) x fp16 activations in K4 order
+void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const void* qzeros /* null: symmetric */, void* out, int out_dtype,
+               int m, int n, int k, int group_size, float* slabs, cudaStream_t st);
 // e4m3 [n,k] with f32 scale per [by, bx] tile x fp16 activations in natural order
 bool fp8_tc_supported(int m, int n, int k, int by, int bx);
 void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void* bias, void* out, int out_dtype, int m, int n, int k,

@@ -179,6 +179,7 @@ struct GemmParams {
     int group_size, k;             // marlin group size / fp8 bx
     int scale_bf16, scale_by, scale_sk;
     const float* norm;             // fp8: {2^p, 2^-p} range shift of the tile scales (device)
+    const uint32_t* zp;            // AWQ: packed zero points [K/g, N/8] in the marlin layout (null: symmetric, zero point 8)
     long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
     int debug;                     // profiling aid (B200_GEMM_DEBUG): 1 = skip MMA issue, 2 = skip dequant, 4 = skip epilogue stores
 };
@@ -276,7 +277,7 @@ struct Q4KQuarter {
 // nibbles are k = 0..31 and high nibbles k = 32..63 of the chunk -- the same nibble geometry as a Q4_K chunk, so the
 // subnormal-placement + HFMA2 trick applies unchanged: w = s*q - 8*s with one per-group scale s
 // (/root/reference/src/backend/gptq.rs:115-178 call site; scales arrive marlin-permuted, linear.rs:341-379).
-struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg, by, sk; const float* norm; };   // by / sk: fp8 scale-tile rows, scale columns; norm: fp8 range shift
+struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg, by, sk; const float* norm; const uint32_t* zp; };   // by / sk: fp8 scale-tile rows, scale columns; norm: fp8 range shift; zp: AWQ zero points (marlin layout) or null
 __device__ __forceinline__ int marlin_scale_pos(int n, bool grouped) {
     // inverse of marlin_permute_scales: position of original column n inside its permuted block
     if (grouped) { const int b = n & 63; return (n & ~63) | (8 * (b & 7) + (b >> 3)); }
@@ -297,11 +298,22 @@ struct M4Quarter {
         const int64_t idx = (int64_t)g * c.n_total + marlin_scale_pos(c.n_idx, grouped);
         return c.bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(c.scales)[idx]) : __half2float(static_cast<const __half*>(c.scales)[idx]);
     }
+    // zero point of column n_idx in group g: symmetric GPTQ = 8; AWQ = nibble of the packed [G, N/8] tensor in the layout the
+    // reference's converter writes (examples/convert_awq_marlin.py:75-113: scale_perm inside 64-column blocks, then the
+    // [0,2,4,6,1,3,5,7] interleave inside 8): column b of a block sits in word (b & 7), nibble inv_interleave[b >> 3]
+    static __device__ __forceinline__ float zero_at(const M4Ctx& c, int k) {
+        if (!c.zp) return 8.f;
+        const int g = c.group_size > 0 ? k / c.group_size : 0;
+        const int b = c.n_idx & 63;
+        const uint32_t word = c.zp[(int64_t)g * (c.n_total >> 3) + ((c.n_idx >> 6) << 3) + (b & 7)];
+        const int nib = (0x73625140u >> (4 * (b >> 3))) & 7;          // inverse of [0,2,4,6,1,3,5,7]: 0,4,1,5,2,6,3,7
+        return (float)((word >> (4 * nib)) & 0xFu);
+    }
     static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
         const float s0 = scale_at(c, c.k0 + kC * 64), s1 = scale_at(c, c.k0 + kC * 64 + 32);
         const bool fast = __all_sync(0xffffffffu, fmaxf(fabsf(s0), fabsf(s1)) * 262144.f <= 65504.f);
         const __half2 s_lo = __float2half2_rn(fast ? s0 * 262144.f : s0), s_hi = __float2half2_rn(fast ? s1 * 262144.f : s1);
-        const __half2 n_lo = __float2half2_rn(-8.f * s0), n_hi = __float2half2_rn(-8.f * s1);
+        const __half2 n_lo = __float2half2_rn(-zero_at(c, c.k0 + kC * 64) * s0), n_hi = __float2half2_rn(-zero_at(c, c.k0 + kC * 64 + 32) * s1);
         uint32_t v[32];
         if (fast) {
 #pragma unroll
@@ -661,7 +673,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const uint32_t afp = aph ^ 1;
                 const bool skip = (p.debug & 2) != 0;
                 const M4Ctx mc{p.scales, p.n[0], p.group_size, (int)(u - tile_begin) * kSB, tile * kTileN + row < p.n[0] ? tile * kTileN + row : 0,
-                               p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm};
+                               p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm, p.zp};
                 switch (qt) {
                     case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                     case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
@@ -919,7 +931,7 @@ int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* c
 int wq16_slabs(int n, int k) { return qmatmul_tc_slab_count((n + kTileN - 1) / kTileN, k / 256); }
 
 static void wq16_launch(int kind, const void* x_f16, const void* w, const void* scales, int scale_bf16, int group_or_bx, int by, int sk,
-                        const float* norm, const void* bias, void* out, int out_dtype, int m, int n, int k, float* slabs, cudaStream_t st,
+                        const float* norm, const uint32_t* zp, const void* bias, void* out, int out_dtype, int m, int n, int k, float* slabs, cudaStream_t st,
                         const char* who) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) { set_error(kErrCuda, "%s: cuTensorMapEncodeTiled unavailable", who); return; }
@@ -945,7 +957,7 @@ static void wq16_launch(int kind, const void* x_f16, const void* w, const void* 
     p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
     p.slabs = qmatmul_tc_slab_count(tiles, nsb);
     p.slab_stride = (int64_t)m * n;
-    p.scales = scales; p.group_size = group_or_bx; p.k = k; p.scale_bf16 = scale_bf16; p.scale_by = by; p.scale_sk = sk; p.norm = norm;
+    p.scales = scales; p.group_size = group_or_bx; p.k = k; p.scale_bf16 = scale_bf16; p.scale_by = by; p.scale_sk = sk; p.norm = norm; p.zp = zp;
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     if (kind == kTypeM4) { if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st); }
     else { if (mb == 32) launch<32, kTypeF8>(wm, xm, p, st); else launch<64, kTypeF8>(wm, xm, p, st); }
@@ -961,10 +973,12 @@ static void wq16_launch(int kind, const void* x_f16, const void* w, const void* 
     check_launch(who);
 }
 
-// symmetric int4 x fp16 (marlin_4bit_*): w in the gptq_repack() layout, scales marlin-permuted, activations fp16 in K4 order
-void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, void* out, int out_dtype, int m, int n, int k, int group_size,
-               float* slabs, cudaStream_t st) {
-    wq16_launch(kTypeM4, x_f16_k4, w, scales, out_dtype == B200_BF16, group_size, 1, 0, nullptr, nullptr, out, out_dtype, m, n, k, slabs, st, "marlin_4bit");
+// int4 x fp16 (marlin_4bit_* / marlin_awq_4bit_*): w in the gptq_repack() / awq_repack() layout, scales marlin-permuted,
+// qzeros = null (symmetric, zero point 8) or the converter's packed AWQ zero points; activations fp16 in K4 order
+void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const void* qzeros, void* out, int out_dtype, int m, int n, int k,
+               int group_size, float* slabs, cudaStream_t st) {
+    wq16_launch(kTypeM4, x_f16_k4, w, scales, out_dtype == B200_BF16, group_size, 1, 0, nullptr, static_cast<const uint32_t*>(qzeros), nullptr, out,
+                out_dtype, m, n, k, slabs, st, qzeros ? "marlin_awq_4bit" : "marlin_4bit");
 }
 
 // block-scaled e4m3 weights x fp16 (fp8_matmul); activations fp16 in natural order
@@ -977,7 +991,7 @@ void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void
     const int sk = (k + bx - 1) / bx;
     launch_pdl(fp8_scale_norm_kernel, dim3(1), dim3(256), 0, st, scale, (int64_t)((n + by - 1) / by) * sk, norm);
     count_launch();
-    wq16_launch(kTypeF8, x_f16, w, scale, 0, bx, by, sk, norm, bias, out, out_dtype, m, n, k, slabs, st, "fp8_matmul");
+    wq16_launch(kTypeF8, x_f16, w, scale, 0, bx, by, sk, norm, nullptr, bias, out, out_dtype, m, n, k, slabs, st, "fp8_matmul");
 }
 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,

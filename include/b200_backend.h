@@ -154,7 +154,13 @@ void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggm
  *   g_idx must be NULL; group_size 64 / 128 / -1; m <= 64; k % 256 == 0; n % 64 == 0.  `workspace` (n zeroed u32 of
  *   locks in Marlin) is unused.  The fp16 copy of x lives in a library-owned scratch buffer, grown outside stream
  *   capture or handed over once with b200_set_scratch().
- * AWQ / act-order entry points exist but record an "unsupported" error in this round. */
+ * awq_repack: AWQ qweight u32 [k, n_packed = N/8] (nibble i of a word = column 8j + [0,2,4,6,1,3,5,7][i]) -> the same private layout.
+ * marlin_awq_4bit_{f16,bf16}: as marlin_4bit_* with zero points: out = x . ((q - z) * scale)^T; qzeros u32 [k/group, n/8] in the
+ *   layout the reference's offline converter writes (examples/convert_awq_marlin.py:75-113: scale_perm inside 64-column blocks,
+ *   [0,2,4,6,1,3,5,7] interleave inside 8, packed along columns).
+ * gemm_half_q_half_alt: conventional GPTQ (act-order and / or asymmetric, 4 or 8 bit; no repack): x f16 [m,k], qweight u32
+ *   [k/pack, n] packed along k, qzeros u32 [G, n/pack] packed along n and stored minus one, scales f16 [G, n], g_idx i32 [k]
+ *   (required), out f16 [m,n]; shape-generic SIMT kernel. */
 void gptq_repack(const void* in, void* out, int32_t k_packed, int32_t n, int64_t stream);
 void awq_repack(const void* in, void* out, int32_t k, int32_t n_packed, int32_t bits, int64_t stream);
 void marlin_4bit_f16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx,

@@ -64,3 +64,73 @@ def dequant_gptq(qweight: np.ndarray, scales: np.ndarray, group_size: int) -> np
 
 def gptq_matmul(x: np.ndarray, qweight: np.ndarray, scales: np.ndarray, group_size: int) -> np.ndarray:
     return (np.asarray(x, np.float64) @ dequant_gptq(qweight, scales, group_size).T).astype(np.float32)
+
+
+# ---- AWQ (zero-point int4) and conventional GPTQ (act-order / asymmetric) ------------------------------------------------
+AWQ_ORDER = [0, 2, 4, 6, 1, 3, 5, 7]        # nibble i of an AWQ word holds column 8 j + AWQ_ORDER[i] (AutoAWQ pack order)
+
+
+def pack_cols(q: np.ndarray) -> np.ndarray:
+    """u8 [R, N] -> u32 [R, N/8], nibble i of word j = column 8 j + i (examples/convert_awq_marlin.py:19-42)."""
+    R, N = q.shape
+    q = q.astype(np.uint32).reshape(R, N // 8, 8)
+    out = np.zeros((R, N // 8), np.uint32)
+    for i in range(8):
+        out |= q[:, :, i] << np.uint32(4 * i)
+    return out
+
+
+def unpack_cols(packed: np.ndarray) -> np.ndarray:
+    """examples/convert_awq_marlin.py:44-73"""
+    R, Np = packed.shape
+    q = np.empty((R, Np, 8), np.uint8)
+    for i in range(8):
+        q[:, :, i] = (packed >> np.uint32(4 * i)) & 0xF
+    return q.reshape(R, Np * 8)
+
+
+def pack_awq(q: np.ndarray) -> np.ndarray:
+    """u8 [R, N] natural columns -> AWQ words [R, N/8]"""
+    R, N = q.shape
+    return pack_cols(q.reshape(R, N // 8, 8)[:, :, AWQ_ORDER].reshape(R, N))
+
+
+def unpack_awq(packed: np.ndarray) -> np.ndarray:
+    q = unpack_cols(packed)
+    R, N = q.shape
+    return q.reshape(R, N // 8, 8)[:, :, np.argsort(AWQ_ORDER)].reshape(R, N)
+
+
+def marlin_zero_points(zp: np.ndarray) -> np.ndarray:
+    """natural zero points u8 [G, N] -> the packed layout marlin_awq_4bit_* takes (examples/convert_awq_marlin.py:75-96):
+    scale_perm within 64-column blocks, [0,2,4,6,1,3,5,7] interleave within 8, packed along columns."""
+    G, N = zp.shape
+    scale_perm, _ = get_scale_perms()
+    z = zp.reshape(-1, 64)[:, scale_perm]
+    z = z.reshape(-1, 8)[:, AWQ_ORDER].reshape(G, N)
+    return pack_cols(z)
+
+
+def awq_to_marlin_zero_points(qzeros_awq: np.ndarray) -> np.ndarray:
+    """examples/convert_awq_marlin.py:99-113: what the reference's offline converter writes into ``qzeros``"""
+    return marlin_zero_points(unpack_awq(qzeros_awq))
+
+
+def dequant_awq(qweight_awq: np.ndarray, qzeros_awq: np.ndarray, scales: np.ndarray, group_size: int) -> np.ndarray:
+    """-> W f64 [N, K] = (q[k, n] - z[k // g, n]) * s[k // g, n]; qweight [K, N/8], qzeros [K/g, N/8] AWQ words"""
+    q = unpack_awq(qweight_awq).astype(np.float64)
+    K, N = q.shape
+    g = K if group_size == -1 else group_size
+    z = np.repeat(unpack_awq(qzeros_awq).astype(np.float64), g, axis=0)[:K]
+    s = np.repeat(np.asarray(scales, np.float64), g, axis=0)[:K]
+    return ((q - z) * s).T
+
+
+def dequant_gptq_alt(qweight: np.ndarray, qzeros: np.ndarray, scales: np.ndarray, g_idx: np.ndarray) -> np.ndarray:
+    """conventional GPTQ (act-order / asymmetric; gemm_half_q_half_alt, gptq.rs:182-197): qweight [K/8, N] packed along K,
+    qzeros [G, N/8] packed along N in natural order and stored MINUS ONE (GPTQ v1), group of row k = g_idx[k].
+    -> W f64 [N, K] = (q[k, n] - (z[g_idx[k], n] + 1)) * s[g_idx[k], n]"""
+    q = unpack_gptq(qweight).astype(np.float64)
+    z = unpack_cols(qzeros).astype(np.float64)[np.asarray(g_idx, np.int64)] + 1.0
+    s = np.asarray(scales, np.float64)[np.asarray(g_idx, np.int64)]
+    return ((q - z) * s).T

@@ -74,3 +74,29 @@ def marlin_perms():
 
 if __name__ == "__main__" and os.path.exists("/root/reference/examples/convert_awq_marlin.py"):
     marlin_perms()
+
+
+def awq_zero_points():
+    """tests/golden/awq_zero_points.json: AWQ-packed zero points and what the reference's offline converter turns them into
+    (`awq_to_marlin_zero_points`, /root/reference/examples/convert_awq_marlin.py:99-113, EXECUTED here with safetensors
+    stubbed out) -- the layout `marlin_awq_4bit_*` takes as `qzeros`."""
+    import importlib.util
+    import sys
+    import types
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from oracle import gptq as OG
+    for m in ("safetensors", "safetensors.torch"):
+        mod = types.ModuleType(m); mod.load_file = mod.save_file = None; sys.modules.setdefault(m, mod)
+    spec = importlib.util.spec_from_file_location("conv", "/root/reference/examples/convert_awq_marlin.py")
+    conv = importlib.util.module_from_spec(spec); spec.loader.exec_module(conv)
+    zp = np.random.default_rng(0).integers(0, 16, (3, 128), dtype=np.uint8)
+    packed = OG.pack_awq(zp)
+    ref = conv.awq_to_marlin_zero_points(torch.from_numpy(packed.view(np.int32)), 3, 128, 4).numpy().view(np.uint32)
+    with open(os.path.join(HERE, "awq_zero_points.json"), "w") as f:
+        json.dump({"zp": zp.tolist(), "awq_packed": packed.tolist(), "marlin_zp": ref.tolist()}, f)
+
+
+if __name__ == "__main__" and os.path.exists("/root/reference/examples/convert_awq_marlin.py"):
+    awq_zero_points()
