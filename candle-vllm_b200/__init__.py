@@ -18,5 +18,6 @@ from .inputs import prepare_decode, prepare_prompt, used_blocks_for_len, PAD_SLO
 from .llama import LlamaConfig, GGUFLLaMa  # noqa: F401
 from .block_manager import BlockManager, PrefixCache, PrefixCacheConfig, Seq, SeqGroup, AllocStatus  # noqa: F401
 from .gptq import gptq_matmul, marlin_weight_repack, marlin_permute_scales  # noqa: F401
+from .linear import QLinear  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

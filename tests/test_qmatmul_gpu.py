@@ -115,3 +115,38 @@ def test_small_ops_match_oracle():
     lg[3, 77] = lg[3, 99999] = 50.0                        # tie -> first index
     am = pkg.argmax(torch.from_numpy(lg).to(DEV)).cpu().numpy()
     assert np.array_equal(am, lg.argmax(axis=1))
+
+
+def test_qlinear_dispatch_like_reference():
+    """QLinear (linear.rs:845-916): GGUF tensor -> QMatMul on f32-cast x (f32 out, [b,1,d] squeezed and restored, bias added);
+    transposed GGUF tensor -> dequantise + dense matmul; GPTQ tuple -> gptq_matmul."""
+    from oracle import gptq as OG
+    rng = np.random.default_rng(9)
+    n, k = 256, 512
+    w = G.random_weight(rng, pkg.GgmlType.Q4_K, n, k)
+    qt = pkg.QTensor.from_numpy(w, pkg.GgmlType.Q4_K, (n, k))
+    bias = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(DEV)
+    lin = pkg.QLinear.from_qtensor(qt, bias)
+    x = torch.from_numpy(rng.standard_normal((6, 1, k)).astype(np.float32)).to(DEV).to(torch.bfloat16)
+    y = lin.forward(x)
+    assert y.shape == (6, 1, n) and y.dtype == torch.float32
+    ref = G.qmatmul_dequant(x.float().cpu().numpy().reshape(6, k), w, pkg.GgmlType.Q4_K, n, k) + bias.cpu().numpy()
+    assert rel_fro(y.cpu().numpy().reshape(6, n), ref) < 1e-3
+    y2 = lin.forward(x.reshape(2, 3, k))                                  # seq_len > 1: shape kept
+    assert y2.shape == (2, 3, n) and torch.allclose(y2.reshape(6, n), y.reshape(6, n), rtol=1e-5, atol=1e-5)
+    # transposed weight: the tensor holds W^T [in = 256, out = 512]
+    lin_t = pkg.QLinear.from_qtensor(qt, None, transposed_weight=True)
+    xt = torch.from_numpy(rng.standard_normal((4, n)).astype(np.float32)).to(DEV).half()
+    yt = lin_t.forward(xt)
+    wd = G.dequantize_weight(w, pkg.GgmlType.Q4_K, n, k)
+    assert yt.shape == (4, k) and rel_fro(yt.float().cpu().numpy(), xt.float().cpu().numpy() @ wd) < 2e-3
+    # GPTQ tuple
+    q = rng.integers(0, 16, (k, n), dtype=np.uint8)
+    sc = torch.from_numpy(rng.uniform(0.005, 0.02, (k // 128, n)).astype(np.float32)).to(DEV).half()
+    w_m = pkg.marlin_weight_repack(torch.from_numpy(OG.pack_gptq(q).view(np.int32)).to(DEV), 4, False)
+    gl = pkg.QLinear.from_gptq(w_m, pkg.marlin_permute_scales(sc, k, n, 128), None, None, torch.zeros(n, dtype=torch.int32, device=DEV), 128, 4,
+                               bias=bias.half())
+    xg = torch.from_numpy(rng.standard_normal((2, 3, k)).astype(np.float32)).to(DEV).half()
+    yg = gl.forward(xg)
+    refg = OG.gptq_matmul(xg.float().cpu().numpy().reshape(6, k), OG.pack_gptq(q), sc.float().cpu().numpy(), 128) + bias.half().float().cpu().numpy()
+    assert yg.shape == (2, 3, n) and rel_fro(yg.float().cpu().numpy().reshape(6, n), refg) < 2e-3
