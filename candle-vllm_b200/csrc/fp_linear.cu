@@ -149,17 +149,21 @@ void fp8_matmul(const void* x, const void* weight, const float* weight_scale, co
     if (!common_check("fp8_matmul", x, weight, weight_scale, out, m, n, k, dtype, 16)) return;
     B200_REQUIRE(block_y > 0 && block_x > 0, kErrBadArg, "fp8_matmul: block sizes [%d, %d]", block_y, block_x);
     static const bool force_generic = [] { const char* e = getenv("B200_FP8_GENERIC"); return e && atoi(e) != 0; }();
-    if (!force_generic && fp8_tc_supported(m, n, k, block_y, block_x) && (((uintptr_t)out | (uintptr_t)weight_scale) & 7) == 0) {
-        // decode batches: tcgen05 pipeline (qmatmul_tc.cu).  Scratch = fp16 copy of x + fp32 partial-sum slabs.
+    if (!force_generic && fp8_tc_supported(m > 64 ? 64 : m, n, k, block_y, block_x) && (((uintptr_t)out | (uintptr_t)weight_scale) & 7) == 0) {
+        // tcgen05 pipeline (qmatmul_tc.cu), 64 rows per pass.  Scratch = fp16 copy of x (bf16 input) + fp32 partial-sum slabs + norm.
         cudaStream_t st = as_stream(stream);
-        const size_t x_bytes = ((size_t)m * k * 2 + 255) & ~(size_t)255;
-        const size_t slab_bytes = (size_t)wq16_slabs(n, k) * m * n * 4;
+        const int mc = m < 64 ? m : 64;
+        const size_t x_bytes = ((size_t)mc * k * 2 + 255) & ~(size_t)255;
+        const size_t slab_bytes = (size_t)wq16_slabs(n, k) * mc * n * 4;
         char* xs = static_cast<char*>(get_scratch(x_bytes + slab_bytes + 256, st));
         if (!xs) return;
-        const void* x16 = x;                                   // f16 activations feed the tensor map directly
-        if (dtype != B200_F16) { cast(x, xs, (int64_t)m * k, dtype, B200_F16, stream); x16 = xs; }
-        fp8_tc_run(x16, weight, weight_scale, bias, out, dtype, m, n, k, block_y, block_x, reinterpret_cast<float*>(xs + x_bytes),
-                   reinterpret_cast<float*>(xs + x_bytes + slab_bytes), st);
+        for (int m0 = 0; m0 < m; m0 += 64) {
+            const int mm = m - m0 < 64 ? m - m0 : 64;
+            const void* x16 = static_cast<const char*>(x) + (size_t)m0 * k * 2;                     // f16 activations feed the tensor map directly
+            if (dtype != B200_F16) { cast(x16, xs, (int64_t)mm * k, dtype, B200_F16, stream); x16 = xs; }
+            fp8_tc_run(x16, weight, weight_scale, bias, static_cast<char*>(out) + (size_t)m0 * n * 2, dtype, mm, n, k, block_y, block_x,
+                       reinterpret_cast<float*>(xs + x_bytes), reinterpret_cast<float*>(xs + x_bytes + slab_bytes), st);
+        }
         return;
     }
     const Fp8Dec dec{static_cast<const uint8_t*>(weight), weight_scale, k, block_y, block_x, (k + block_x - 1) / block_x};

@@ -126,14 +126,20 @@ static void marlin_4bit(const void* x, const void* qweight, const void* scales, 
     if (!awq) qzeros = nullptr;                        // symmetric: zero point 8 (the reference passes qzeros but Marlin ignores them)
     B200_REQUIRE(group_size == -1 || group_size == 64 || group_size == 128, kErrUnsupported, "marlin_4bit: group size %d (64, 128, -1)", group_size);
     B200_REQUIRE(k % 256 == 0 && n % 64 == 0, kErrUnsupported, "marlin_4bit: k %% 256 and n %% 64 must be 0 (k=%d n=%d)", k, n);
-    B200_REQUIRE(m <= 64, kErrUnsupported, "marlin_4bit: m = %d > 64 (decode batches only in this round)", m);
     cudaStream_t st = as_stream(stream);
-    // scratch: fp16 K4 copy of x, then the fp32 partial-sum slabs of the stream-K GEMM
-    const size_t x_bytes = ((size_t)m * k * 2 + 255) & ~(size_t)255;
-    char* xs = static_cast<char*>(get_scratch(x_bytes + (size_t)wq16_slabs(n, k) * m * n * 4, st));
+    // scratch: fp16 K4 copy of (up to 64 rows of) x, then the fp32 partial-sum slabs of the stream-K GEMM.  More than 64 rows
+    // (prefill chunks) run 64 at a time, stream-ordered on the same scratch.
+    const int mc = m < 64 ? m : 64;
+    const size_t x_bytes = ((size_t)mc * k * 2 + 255) & ~(size_t)255;
+    char* xs = static_cast<char*>(get_scratch(x_bytes + (size_t)wq16_slabs(n, k) * mc * n * 4, st));
     if (!xs) return;
-    cast(x, xs, (int64_t)m * k, dtype, B200_F16_K4, stream);
-    marlin_tc(xs, qweight, scales, qzeros, out, dtype, m, n, k, group_size, reinterpret_cast<float*>(xs + x_bytes), st);
+    const size_t esz = 2;                                            // f16 / bf16
+    for (int m0 = 0; m0 < m; m0 += 64) {
+        const int mm = m - m0 < 64 ? m - m0 : 64;
+        cast(static_cast<const char*>(x) + (size_t)m0 * k * esz, xs, (int64_t)mm * k, dtype, B200_F16_K4, stream);
+        marlin_tc(xs, qweight, scales, qzeros, static_cast<char*>(out) + (size_t)m0 * n * esz, dtype, mm, n, k, group_size,
+                  reinterpret_cast<float*>(xs + x_bytes), st);
+    }
 }
 
 }  // namespace b200

@@ -10,6 +10,8 @@ void qmatmul_generic(const void* x, bool x_is_f16, const void* w, float* y, int6
 
 // tcgen05 path (qmatmul_tc.cu): fp16 activations [m,k], m <= 32 * n_mtiles; returns false when the shape is not covered
 bool qmatmul_tc_supported(int m, int n, int k, int ggml_type);
+// same, with m > 64 served 64 rows per pass (qmatmul_dispatch)
+bool qmatmul_tc_usable(int m, int n, int k, int ggml_type);
 // true when some output tile is split across CTAs: y must hold the addend (zeros for a plain product)
 bool qmatmul_tc_needs_zeroed_output(int n, int k);
 

@@ -151,7 +151,7 @@ void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggm
  *   private int4 layout (the reference reshapes the result to [K/16, 2n], gptq.rs:283-297; only marlin_4bit_* reads it).
  * marlin_4bit_{f16,bf16}: out[m,n] = x[m,k] . ((q - 8) * scale)^T; scales [k/group, n] in the order produced by the
  *   reference's marlin_permute_scales (/root/reference/src/openai/models/linear.rs:354-379); qzeros ignored (symmetric),
- *   g_idx must be NULL; group_size 64 / 128 / -1; m <= 64; k % 256 == 0; n % 64 == 0.  `workspace` (n zeroed u32 of
+ *   g_idx must be NULL; group_size 64 / 128 / -1; k % 256 == 0; n % 64 == 0; any m (64 rows per tensor-core pass).  `workspace` (n zeroed u32 of
  *   locks in Marlin) is unused.  The fp16 copy of x lives in a library-owned scratch buffer, grown outside stream
  *   capture or handed over once with b200_set_scratch().
  * awq_repack: AWQ qweight u32 [k, n_packed = N/8] (nibble i of a word = column 8j + [0,2,4,6,1,3,5,7][i]) -> the same private layout.
@@ -180,7 +180,7 @@ void b200_set_scratch(void* device_ptr, size_t bytes);
  * :1913-1943, :1717-1757; tensor layouts :944-973, :1812-1853, :1686-1700).
  * out[m,n] = x[m,k] . dequant(W[n,k])^T (+ bias[n]); x, bias, out are f16 or bf16 (`dtype`), fp32 accumulation.
  *   fp8_matmul : weight e4m3 bytes [n,k]; weight_scale f32 [ceil(n/block_y), ceil(k/block_x)] multiplies its tile
- *                (default tile [128,128]).  m <= 64, k % 256 == 0, block_x % 64 == 0 run on the tcgen05 pipeline (weights
+ *                (default tile [128,128]).  k % 256 == 0, block_x % 64 == 0 run on the tcgen05 pipeline, 64 rows per pass (weights
  *                scaled and rounded to fp16, activations fp16); other shapes on a SIMT kernel with exact fp32 weights.
  *   nvfp4_matmul: blocks u8 [n,k/2] (two e2m1 per byte, low nibble = even k), scales e4m3 [n,k/16], global_scale f32
  *                (the reciprocal / weight_scale_2 value the reference computes, linear.rs:1829-1853); input_scale is ignored

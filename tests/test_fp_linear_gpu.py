@@ -2,7 +2,7 @@
 oracle (oracle/fp_formats.py; parity unpinned upstream, element formats pinned to torch / OCP tables in test_oracle.py).
 Tolerances: the SIMT kernels decode weights exactly and accumulate in fp32 -> the result differs from the fp64 target only
 by fp32 summation noise and ONE final rounding to the activation dtype (rel-Frobenius <= 2.5e-3 bf16, 4e-4 f16).  The tcgen05
-block-FP8 path rounds scaled weights and activations to fp16 first: rel-Frobenius <= 1e-3 on f16 I/O."""
+block-FP8 path (any m, 64 rows per pass) rounds scaled weights and activations to fp16 first: rel-Frobenius <= 1e-3 on f16 I/O."""
 import os
 
 import numpy as np
@@ -35,7 +35,7 @@ def test_fp8_block_matmul(dtype, m, n, k, by, bx):
     y = lin.forward(x).float().cpu().numpy()
     ref = F.linear(xf, F.dequant_fp8_block(w, s, by, bx), None if bias is None else bias.float().cpu().numpy())
     assert y.shape == (m, n) and np.isfinite(y).all()
-    tol = max(TOL[dtype], 1e-3) if (m <= 64 and k % 256 == 0 and bx % 64 == 0) else TOL[dtype]       # tcgen05 path: fp16 operands
+    tol = max(TOL[dtype], 1e-3) if (k % 256 == 0 and bx % 64 == 0 and n % 4 == 0) else TOL[dtype]    # tcgen05 path (64 rows per pass): fp16 operands
     assert rel_fro(y, ref) < tol, rel_fro(y, ref)
 
 

@@ -38,7 +38,8 @@ def test_pack_unpack_and_permute_roundtrip():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("m,k,n,g", [(32, 512, 256, 128), (7, 1024, 384, 64), (64, 256, 128, -1), (32, 4096, 1024, 128), (1, 2048, 512, 128)])
+@pytest.mark.parametrize("m,k,n,g", [(32, 512, 256, 128), (7, 1024, 384, 64), (64, 256, 128, -1), (32, 4096, 1024, 128), (1, 2048, 512, 128),
+                                     (150, 512, 256, 128)])         # > 64 rows: 64 per tensor-core pass
 def test_marlin_matmul_matches_oracle(dtype, m, k, n, g):
     rng = np.random.default_rng(m * 7 + n)
     q = rng.integers(0, 16, (k, n), dtype=np.uint8)
