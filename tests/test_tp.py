@@ -47,6 +47,14 @@ def _gloo_worker(rank, world, port, out):
         g = torch.stack(gathered)                       # [world, B, 2]
         pick = g[g[:, :, 0].argmax(dim=0), torch.arange(B), 1].long()
         ok = bool(torch.equal(pick, logits.argmax(dim=1)))
+        # peer-memory inboxes degrade collectively: without a GPU the CUDA-IPC allocation fails on every rank, all ranks still walk
+        # through the same collectives (no hang) and agree on "inactive" -- the engine would then stay on NCCL
+        import types
+        from candle_vllm_b200.distributed import PeerInboxes
+        if not torch.cuda.is_available():
+            box = PeerInboxes(types.SimpleNamespace(_h=None), rank, world)
+            ok = ok and (not box.active) and bool(box.error) and (not box.timed_out())
+            box.close()
         if rank == 0:
             out.put((err, ok))
     finally:
