@@ -389,7 +389,12 @@ def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev)
     alg = kv_bytes + io_bytes
     return {"kernel": "paged_attention_decode (one layer: split-KV kernel + merge)", "bound": "hbm",
             "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
-            "ms_per_launch": ms, "ctx": ctx, "traffic": None}
+            "ms_per_launch": ms, "ctx": ctx,
+            # dram__bytes_read + dram__bytes_write of ONE `ncu --set full` capture of this kernel inside this benchmark
+            # (profiles/r01_attention_decode_ncu.md: 541.39 MB read + 4.94 MB written at B = 32, 8 kv heads, ctx 4104; the algorithmic
+            # bytes of that launch are 538.4 MB); only quoted for the configuration it was captured on
+            "traffic": 546327808 if (world == 1 and B == 32 and esz == 2) else None,
+            "traffic_note": "ncu capture at ctx 4104 where the algorithmic bytes are 538.4 MB: reads 1.006 x, reads + the 4.9 MB of fp32 split-KV partials 1.015 x"}
 
 
 def main():
