@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--kv", default="bf16", choices=["bf16", "fp8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--parity-steps", type=int, default=3, help="decode steps compared against a TP=1 engine before timing (0 = off)")
     return ap.parse_args()
 
 
@@ -104,49 +105,42 @@ def cpu_sample_setup(batch: int, ctx: int):
 
     keep = (ws, norms, kc, vc, bt, ctx_lens, pos, slots, cos, sin, x, scratch, layer, cfg)   # raw pointers inside
 
-    # all the host threads that HELP: OpenMP's default is the logical CPU count, which can exceed what the container may use
-    # (measured on the GPU box: 128 threads were 10x slower than 64).  Calibrate on the Q6_K slice and keep the fastest.
+    # ONE thread count, chosen by rule and printed (r01 re-calibrated per run and moved 4x between boxes): the physical cores this
+    # process may use = half the schedulable logical CPUs (SMT pairs; on the GPU box 128 logical threads ran 10x slower than 64)
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    cands = sorted({max(1, avail), max(1, avail // 2), max(1, avail // 4)}, reverse=True)
-    timing = {}
-    for n_thr in cands:
-        cpu_ref.set_num_threads(n_thr)
-        cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)                   # warm the team
-        t0 = time.perf_counter()
-        cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)
-        timing[n_thr] = time.perf_counter() - t0
-    cpu_ref.set_num_threads(min(timing, key=timing.get))
+    n_thr = max(1, avail // 2) if avail >= 16 else max(1, avail)
+    cpu_ref.set_num_threads(n_thr)
+    one_layer()                                                    # warm the team and the page tables (not counted)
 
     def step():
-        """one bounded sample -> seconds for a FULL decode step (scaled)"""
+        """one bounded sample -> seconds for a FULL decode step (scaled): two full decoder layers + a lm_head row slice"""
         assert keep
-        t_layer = one_layer()
+        t_layer = 0.5 * (one_layer() + one_layer())
         t0 = time.perf_counter()
         cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)
         t_head = time.perf_counter() - t0
         return 32 * t_layer + t_head * (V / rows), t_layer, t_head
 
     info = dict(cores=cpu_ref.num_threads(), kind="port",
-                sample=f"per step: 1 of 32 decoder layers (batch {batch}, ctx {ctx}, Q4_K x Q8_K int dot + f32 paged "
-                       f"attention) + {rows}/{V} Q6_K lm_head rows, scaled to the full model")
+                sample=f"per step: 2 of 32 decoder layers (batch {batch}, ctx {ctx}, Q4_K x Q8_K int dot + f32 paged "
+                       f"attention) + {rows}/{V} Q6_K lm_head rows, scaled to the full model; {n_thr} threads = "
+                       f"{'half the ' + str(avail) + ' schedulable logical CPUs' if avail >= 16 else 'all schedulable CPUs'}; mean over samples")
     return step, info
 
 
 def cpu_decode_sample(batch: int, ctx: int, budget_s: float):
     step, info = cpu_sample_setup(batch, ctx)
-    best = None
+    vals = []
     t_start = time.perf_counter()
-    n = 0
-    while n < 3 and (n == 0 or (time.perf_counter() - t_start) * (n + 1) / n < budget_s):
-        t_step, t_layer, t_head = step()
-        best = t_step if best is None else min(best, t_step)
-        n += 1
+    while len(vals) < 3 and (not vals or (time.perf_counter() - t_start) * (len(vals) + 1) / len(vals) < budget_s):
+        vals.append(step()[0])
+    mean = statistics.mean(vals)
     info = dict(info)
-    info["sample"] += f"; best of {n}: {best:.2f} s/step"
-    return batch / best, best, info
+    info["sample"] += f"; {len(vals)} samples, mean {mean:.2f} s/step (min {min(vals):.2f}, max {max(vals):.2f})"
+    return batch / mean, mean, info
 
 
 def run_reference(args):
@@ -162,8 +156,8 @@ def run_reference(args):
             vals.append((args.batch / t_step, t_step))
         if vals and (time.perf_counter() - t_begin) > 150:       # keep the whole run within a few minutes
             break
-    tps = statistics.mean(v[0] for v in vals)
-    ms = statistics.mean(v[1] for v in vals) * 1e3
+    ms = statistics.mean(v[1] for v in vals) * 1e3                  # same statistic as the cpu_baseline leg: mean seconds per step
+    tps = args.batch / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "q4_k weights x q8_k activations (int8 dot), f32 attention", "data": "synthetic",
@@ -239,21 +233,31 @@ def run_b200(args):
 
     B, bs = args.batch, 64
     K, W = args.steps, args.warmup
-    args.max_ctx = max(args.max_ctx, args.ctx + 2 * (K + W) + 8)      # room for resident + e2e steps
+    PS = args.parity_steps
+    args.max_ctx = max(args.max_ctx, args.ctx + 3 * (K + W) + PS + 16, 4608 + 2 * (K + W) + 16)      # room for every leg below
     blocks_per_seq = -(-args.max_ctx // bs)
     cfg = pkg.LlamaConfig(num_layers=args.layers, max_num_seqs=B, max_blocks_per_seq=blocks_per_seq, max_pos=args.max_ctx + 64,
                           block_size=bs)
     kv_dtype = pkg.DType.FP8_E4M3 if args.kv == "fp8" else pkg.DType.BF16
-    weights = synthetic.make_weights(cfg, dev, seed=0, tp_rank=rank, tp_world=world)
     num_blocks = B * blocks_per_seq + 16
-    eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim,
-                          pkg.CacheConfig(bs, num_blocks, kvcache_dtype="fp8" if args.kv == "fp8" else "auto"),
-                          device=dev, num_shards=world)
-    synthetic.fill_kv_cache(eng.gpu_cache, seed=1 + rank)
     tables = synthetic.random_block_tables(B, blocks_per_seq, num_blocks, seed=2)
-    model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, tp_rank=rank, tp_world=world,
-                          nccl_comm=comm.handle.value if comm else None)
-    stream = model.stream
+    tables_np = np.asarray(tables, np.int32)              # rectangular tables: prepare_decode's vectorised path
+    stream = torch.cuda.Stream()
+
+    def build(tp_rank, tp_world, nccl):
+        """model + KV state for (tp_rank, tp_world): same seeds on every rank and for every tp_world, so a TP run and the TP = 1
+        run see the same global weights and the same global KV cache (each rank holds its shard of both)."""
+        weights = synthetic.make_weights(cfg, dev, seed=0, tp_rank=tp_rank, tp_world=tp_world)
+        eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim,
+                              pkg.CacheConfig(bs, num_blocks, kvcache_dtype="fp8" if args.kv == "fp8" else "auto"),
+                              device=dev, num_shards=tp_world)
+        synthetic.fill_kv_cache(eng.gpu_cache, seed=1, tp_rank=tp_rank, tp_world=tp_world, num_kv_heads=cfg.num_kv_heads)
+        torch.cuda.synchronize()
+        model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, tp_rank=tp_rank, tp_world=tp_world, nccl_comm=nccl,
+                              stream=stream)
+        return model, eng, weights
+
+    model, eng, weights = build(rank, world, comm.handle.value if comm else None)
     inboxes = None
     if world > 1:
         # row-parallel all-reduce + residual add + next RMSNorm as one kernel over NVLink peer memory (falls back to NCCL if
@@ -275,40 +279,86 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    toks0 = [int(t) for t in np.random.default_rng(3).integers(0, cfg.vocab, B)]
+
+    # ---- (0) parity, OUTSIDE every timed region: the first PS decode steps of this run (graph replay, fused all-reduce and
+    # all) against the same steps of a TP = 1 engine with the same seeds on rank 0: greedy tokens and full-vocabulary logits.
+    # At N = 1 the second engine runs eagerly (no graph) -- that leg checks graph capture / replay and bounds the run-to-run
+    # spread of the red.add reductions.
+    def parity_steps(mdl, want):
+        lens, toks, out_t, out_l = np.full(B, args.ctx + 1), list(toks0), [], []
+        for _ in range(PS):
+            nxt, lg = mdl.decode(pkg.prepare_decode(lens, toks, tables_np, bs), want_logits=want)
+            out_t.append(np.asarray(nxt).copy()); out_l.append(lg)
+            toks, lens = [int(t) for t in nxt], lens + 1
+        return np.stack(out_t), out_l
+
+    parity = None
+    if PS > 0:
+        got_t, got_l = parity_steps(model, True)                    # collective at N > 1 (logits all-gather)
+        barrier()
+        if rank == 0:
+            if world == 1:
+                ref_model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, use_graph=False, stream=stream)
+                ref_eng = None                                      # same cache: the steps rewrite the same slots with the same values
+            else:
+                ref_model, ref_eng, ref_w = build(0, 1, None)
+            ref_t, ref_l = parity_steps(ref_model, True)
+            scale = max(float(np.abs(l).max()) for l in ref_l)
+            err = max(float(np.abs(a - b).max()) for a, b in zip(got_l, ref_l)) / scale
+            # a greedy token may differ only on a near-tie inside the logit error
+            flips = 0
+            for st in range(PS):
+                for b in np.nonzero(got_t[st] != ref_t[st])[0]:
+                    margin = float(ref_l[st][b].max() - ref_l[st][b, got_t[st][b]])
+                    flips += int(margin > 2 * err * scale + 1e-6)
+                if not np.array_equal(got_t[st], ref_t[st]):
+                    break                                           # later steps decode different tokens by construction
+            parity = {"steps": PS, "logits_max_err": err, "tokens_equal_tp1": bool(np.array_equal(got_t, ref_t)),
+                      "token_mismatches_beyond_logit_error": flips, "logit_scale": scale,
+                      "reference": "TP=1 engine, same seeds, rank 0" + (" (eager, no CUDA graph)" if world == 1 else ""),
+                      "tolerance": "logits within 1e-3 of max|logit|"}
+            del ref_model, ref_l
+            if world > 1:
+                del ref_eng, ref_w
+            torch.cuda.empty_cache()
+        barrier()
+
     # ---- (1) device-resident: metadata advanced on the device, graph replay only ----------------
-    lens = [args.ctx + 1] * B          # context INCLUDING the token being decoded
-    toks = [int(t) for t in np.random.default_rng(3).integers(0, cfg.vocab, B)]
-    prep = pkg.prepare_decode(lens, toks, tables, bs)
-    model.decode(prep)                                     # loads the static buffers, captures the graph
-    for _ in range(W):
-        model.decode_resident(B, advance=True)
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
-    l0 = model.kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(K):
+    def resident_leg(ctx0):
+        prep = pkg.prepare_decode([ctx0 + 1] * B, toks0, tables, bs)   # context INCLUDING the token being decoded
+        model.decode(prep)                                     # loads the static buffers (captures the graph on first use)
+        for _ in range(W):
             model.decode_resident(B, advance=True)
-        e1.record(stream)
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
-    launches = model.kernel_launches() - l0
-    ms_step = ms_total / K
+        barrier()
+        sampler = ClockSampler(local); sampler.start()
+        l0 = model.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(K):
+                model.decode_resident(B, advance=True)
+            e1.record(stream)
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        return ms_total / K, sampler.stop(), model.kernel_launches() - l0, (ctx0 + 1 + W + 1, ctx0 + 1 + W + K)
+
+    ms_step, clocks, launches, (ctx_first, ctx_last) = resident_leg(args.ctx + PS)
     value = B / (ms_step * 1e-3)
-    ctx_first, ctx_last = args.ctx + 1 + W + 1, args.ctx + 1 + W + K
+    # the metric is quoted over ctx 4096 -> 5120 (mean 4608): the same leg centred on the mean context
+    mid0 = max(args.ctx, 4608 - (W + K) // 2 - 1)
+    ms_mid, clocks_mid, _, (mid_first, mid_last) = resident_leg(mid0)
 
     # ---- (2) end to end through the host API -------------------------------------------------------
-    cur = ctx_last + 1
+    cur = mid_last + 1
     nxt = model.read_next_tokens(B)
     h2d = B * (8 + 8 + 8 + 4) + B * blocks_per_seq * 4
     d2h = B * 4
-    tables_np = np.asarray(tables, np.int32)              # rectangular tables: prepare_decode's vectorised path
     for _ in range(min(W, 3)):
         prep = pkg.prepare_decode(np.full(B, cur), nxt, tables_np, bs)
         nxt, _ = model.decode(prep); cur += 1
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(K):
@@ -320,11 +370,15 @@ def run_b200(args):
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / K
     e2e = B / (e2e_ms * 1e-3)
 
-    # ---- (3) roofline of the dominant kernel: paged-attention decode, timed alone per layer ---------
+    # ---- (3) rooflines: paged-attention decode alone per layer; the weight stream of all projections alone ---------
     roof = attention_roofline(pkg, model, cfg, eng, B, cur, tables, world, stream, dev)
+    roof_gemm = gemm_roofline(model, cfg, B, world, stream)
     peer_ar = inboxes is not None and inboxes.active
     if inboxes is not None:
+        timed_out = inboxes.timed_out()
         inboxes.close()                            # collective (barrier): before any rank leaves
+        if timed_out:
+            raise SystemExit("bench: the fused all-reduce timed out on a peer -- numbers invalid")
 
     if rank != 0:
         if world > 1:
@@ -336,8 +390,9 @@ def run_b200(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    roof.update(peak=hbm_peak, peak_source="MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s",
-                frac=roof["achieved"] / hbm_peak)
+    src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s"
+    roof.update(peak=hbm_peak, peak_source=src, frac=roof["achieved"] / hbm_peak)
+    roof_gemm.update(peak=hbm_peak, peak_source=src, frac=roof_gemm["achieved"] / hbm_peak)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 activations x q4_k/q6_k weights (fp32 accumulate), bf16 attention", "data": "synthetic",
@@ -345,9 +400,15 @@ def run_b200(args):
                                    f"block_size {bs}, {args.kv} paged KV, random non-contiguous block tables",
                        "parallelism": f"tp{world}" + ("" if world == 1 else (" (fused all-reduce + add + norm over NVLink peer memory)" if peer_ar else " (NCCL all-reduce)")), "global_batch": B, "layers": cfg.num_layers,
                        "l2_policy": "inputs larger than L2 (KV 17+ GB and weights 4.4 GB streamed per step; 126 MB L2)"},
+            "value_mean_ctx": {"value": B / (ms_mid * 1e-3), "unit": UNIT, "ms_per_step": ms_mid, "ctx": f"{mid_first}->{mid_last}",
+                               "note": "same leg centred on the metric's mean context 4608 (attention bytes +12 % over ctx 4096)",
+                               "clocks": clocks_mid},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ctx": f"{cur - K}->{cur - 1}",
                     "api": "prepare_decode (host) + GGUFLLaMa.decode -> b200_llama_decode (C ABI, host buffers)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_gemm": roof_gemm}
+    if parity is not None:
+        line["parity"] = parity
     if cfg.num_layers != 32:
         line["invalid"] = "debug run with fewer layers"
     if not args.no_cpu_baseline and world == 1:
@@ -356,6 +417,65 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(csv_name: str, kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch of `kernel_substr` in a TRACKED `ncu --page raw --csv`
+    export under profiles/ (None when the file or the metrics are missing): roofline.traffic is computed, never hard-coded."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    try:
+        rows = list(csv.reader(open(path, newline="")))
+    except OSError:
+        return None, None
+    hdr = next((r for r in rows if "Kernel Name" in r), None)
+    if hdr is None:
+        return None, None
+    ik = hdr.index("Kernel Name")
+    units = rows[rows.index(hdr) + 1]
+    def col(name):
+        return hdr.index(name) if name in hdr else None
+    ir, iw = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    if ir is None or iw is None:
+        return None, None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[rows.index(hdr) + 2:]:
+        if len(r) > max(ik, ir, iw) and kernel_substr in r[ik]:
+            try:
+                rd = float(r[ir].replace(",", "")) * mult.get(units[ir], 1.0)
+                wr = float(r[iw].replace(",", "")) * mult.get(units[iw], 1.0)
+                return rd + wr, os.path.join("profiles", csv_name)
+            except ValueError:
+                return None, None
+    return None, None
+
+
+def gemm_roofline(model, cfg, B, world, stream):
+    """The weight stream alone: every quantised projection of every layer + the lm_head + the small ops between them, without
+    RoPE / cache write / attention (b200_llama_linear_chain), timed eagerly with CUDA events on the launching stream.  4.36 GB
+    of weights per pass at TP = 1: far beyond the 126 MB L2."""
+    import torch
+    H, F, V = cfg.hidden, cfg.ffn, cfg.vocab
+    qd, kd = cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim
+    q4 = (H * (qd + 2 * kd) + qd * H + 3 * H * F) * cfg.num_layers * 144 // 256
+    q6 = V * H * 210 // 256
+    alg = (q4 + q6) // world
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            model.linear_chain(B)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        stream.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            model.linear_chain(B)
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"kernel": "all quantised projections of one decode step (QKV, wo, gate|up, w2 per layer + lm_head) incl. norm / SiLU between them, eager launches",
+            "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
+            "ms_per_launch": ms, "launch": "one pass over all layers (weights 4.36 GB / world)",
+            "traffic": None}
 
 
 def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev):
@@ -390,11 +510,18 @@ def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev)
     return {"kernel": "paged_attention_decode (one layer: split-KV kernel + merge)", "bound": "hbm",
             "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
             "ms_per_launch": ms, "ctx": ctx,
-            # dram__bytes_read + dram__bytes_write of ONE `ncu --set full` capture of this kernel inside this benchmark
-            # (profiles/r01_attention_decode_ncu.md: 541.39 MB read + 4.94 MB written at B = 32, 8 kv heads, ctx 4104; the algorithmic
-            # bytes of that launch are 538.4 MB); only quoted for the configuration it was captured on
-            "traffic": 546327808 if (world == 1 and B == 32 and esz == 2) else None,
-            "traffic_note": "ncu capture at ctx 4104 where the algorithmic bytes are 538.4 MB: reads 1.006 x, reads + the 4.9 MB of fp32 split-KV partials 1.015 x"}
+            # dram__bytes_read + dram__bytes_write of ONE `ncu --set full` capture of this kernel inside this benchmark, parsed
+            # from the tracked raw export (profiles/); only quoted for the configuration it was captured on
+            **traffic_fields(world, B, esz)}
+
+
+def traffic_fields(world, B, esz):
+    if not (world == 1 and B == 32 and esz == 2):
+        return {"traffic": None}
+    t, src = ncu_traffic("r02_attention_decode_raw.csv", "paged_attn_decode_kernel")
+    if not t:
+        t, src = ncu_traffic("r01_attention_decode_raw.csv", "paged_attn_decode_kernel")
+    return {"traffic": t, "traffic_source": src} if t else {"traffic": None, "traffic_source": "no tracked ncu export found"}
 
 
 def main():

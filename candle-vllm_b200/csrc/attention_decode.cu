@@ -447,11 +447,7 @@ int pick_chunk_pages(int num_seqs, int kvh, int max_blocks) {
 template <typename T, typename TOut, int kGroup, bool kK4 = false>
 void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, cudaStream_t st) {
     auto kern = paged_attn_decode_kernel<T, kGroup>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::kTotal);
-        attr_set = true;
-    }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SmemLayout::kTotal);
     const int64_t max_items = (int64_t)a.num_seqs * a.num_kv_heads * p.max_chunks;
     const int64_t want = (max_items + kWarps - 1) / kWarps;
     const int grid = (int)(want < sm_count() ? want : sm_count());

@@ -7,6 +7,9 @@
 // /root/reference/src/scheduler/cache_engine.rs:345-399,527-535 (swap / copy),
 // /root/reference/src/openai/models/layers/attention.rs:707-718,983-994 (cache write inside
 // PagedAttention::forward); slot arithmetic /root/reference/src/openai/pipelines/inputs.rs:410-423.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -14,9 +17,12 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 // copy_blocks: grid.y = layer*2 + {K,V}; grid.x strides over (pair, 16-byte chunk).
 // The (src,dst) table and the per-layer base pointers arrive as HOST arrays (cache.rs:112-114);
-// they are packed into a kernel-parameter struct when small (the common CoW case: a handful of
-// pairs), else staged through a stream-ordered async copy from a pinned ring.  No allocation, no
-// host sync -> capture-safe for the param path.
+// they travel as a kernel-parameter struct (<= 192 pairs x 128 layers per launch; larger calls are cut into several
+// launches).  No allocation, no device-side table, no host sync -> capture-safe.
+// Semantics = the reference kernel's: every pair is an independent block copy and all pairs of a call run concurrently,
+// so a block may not be both a source and a destination in one call (CoW never produces such chains,
+// block_engine.rs).  Because a multi-launch call would silently turn that race into an ordering, a call whose pairs
+// chain ACROSS launches is rejected instead.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxParamLayers = 128;
 constexpr int kMaxParamPairs = 192;
@@ -70,9 +76,19 @@ static void copy_blocks_impl(void* key_cache_ptrs, void* value_cache_ptrs, const
     for (int i = 0; i < num_pairs; ++i)
         B200_REQUIRE(map[2 * i] >= 0 && map[2 * i + 1] >= 0 && map[2 * i] <= INT32_MAX && map[2 * i + 1] <= INT32_MAX,
                      kErrBadArg, "copy_blocks: block id out of range in pair %d", i);
-    // Pairs are applied in chunks; within a chunk a dst never aliases a later src's *old* value
-    // requirement: vLLM/candle semantics copy from the pre-call state only when src blocks are not
-    // also dst blocks (CoW never produces chains), so chunking is safe.
+    if (num_pairs > kMaxParamPairs) {
+        // several launches: a destination of one launch that is a source (or destination) of another would make the result
+        // depend on how we cut the call -- refuse (see the header comment)
+        std::vector<int64_t> srcs, dsts;
+        srcs.reserve(num_pairs); dsts.reserve(num_pairs);
+        for (int i = 0; i < num_pairs; ++i) { srcs.push_back(map[2 * i]); dsts.push_back(map[2 * i + 1]); }
+        std::sort(srcs.begin(), srcs.end());
+        std::sort(dsts.begin(), dsts.end());
+        B200_REQUIRE(std::adjacent_find(dsts.begin(), dsts.end()) == dsts.end(), kErrBadArg, "copy_blocks: a block is the destination of two pairs");
+        for (int64_t d : dsts)
+            B200_REQUIRE(!std::binary_search(srcs.begin(), srcs.end(), d), kErrBadArg,
+                         "copy_blocks: block %lld is both a source and a destination in one call of %d pairs", (long long)d, num_pairs);
+    }
     for (int l0 = 0; l0 < num_layers; l0 += kMaxParamLayers) {
         const int nl = num_layers - l0 < kMaxParamLayers ? num_layers - l0 : kMaxParamLayers;
         for (int p0 = 0; p0 < num_pairs; p0 += kMaxParamPairs) {
@@ -145,6 +161,43 @@ reshape_and_cache_flash_vec_kernel(const int4* __restrict__ key, const int4* __r
     for (int i = threadIdx.x; i < row_vecs; i += blockDim.x) {
         kc[slot * row_vecs + i] = __ldg(key + t * key_stride_vecs + i);
         vc[slot * row_vecs + i] = __ldg(value + t * value_stride_vecs + i);
+    }
+}
+
+// vectorised FP8 (e4m3) flash-layout path: one thread converts 16 consecutive elements of a token row and writes them with ONE
+// 16-byte store (K and V), instead of 16 single-byte stores.  Same cast as the scalar kernel (RNE, saturating, scale 1.0).
+template <typename TIn>
+__global__ void __launch_bounds__(128)
+reshape_and_cache_flash_fp8_vec_kernel(const TIn* __restrict__ key, const TIn* __restrict__ value, uint8_t* __restrict__ kc,
+                                       uint8_t* __restrict__ vc, const int64_t* __restrict__ slot_mapping, int n,
+                                       int64_t key_stride, int64_t value_stride) {
+    const int t = blockIdx.x;
+    const int64_t slot = slot_mapping[t];
+    if (slot < 0) return;
+    for (int i = threadIdx.x * 16; i < n; i += blockDim.x * 16) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const TIn* src = (which ? value + t * value_stride : key + t * key_stride) + i;
+            float f[16];
+            if constexpr (sizeof(TIn) == 4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float4 q = reinterpret_cast<const float4*>(src)[j]; f[4 * j] = q.x; f[4 * j + 1] = q.y; f[4 * j + 2] = q.z; f[4 * j + 3] = q.w; }
+            } else {
+                TIn h[16];
+                reinterpret_cast<uint4*>(h)[0] = reinterpret_cast<const uint4*>(src)[0];
+                reinterpret_cast<uint4*>(h)[1] = reinterpret_cast<const uint4*>(src)[1];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = to_f32(h[j]);
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t lo = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[4 * j], f[4 * j + 1]), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t hi = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[4 * j + 2], f[4 * j + 3]), __NV_SATFINITE, __NV_E4M3);
+                w[j] = lo | (hi << 16);
+            }
+            *reinterpret_cast<uint4*>((which ? vc : kc) + slot * n + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
@@ -222,6 +275,17 @@ void reshape_and_cache(const void* key, const void* value, void* key_cache, void
         reshape_and_cache_flash_vec_kernel<<<num_tokens, 128, 0, st>>>(
             (const int4*)key, (const int4*)value, (int4*)key_cache, (int4*)value_cache, slot_mapping, n / 8,
             key_stride / 8, value_stride / 8);
+    } else if (layout == B200_KV_FLASH && fp8 && n % 16 == 0 && (key_stride * (in_dtype == B200_F32 ? 4 : 2)) % 16 == 0 &&
+               (value_stride * (in_dtype == B200_F32 ? 4 : 2)) % 16 == 0 &&
+               ((((uintptr_t)key | (uintptr_t)value | (uintptr_t)key_cache | (uintptr_t)value_cache)) & 15) == 0 &&
+               (in_dtype == B200_F32 || in_dtype == B200_BF16 || in_dtype == B200_F16)) {
+        const int threads = n / 16 >= 128 ? 128 : ((n / 16 + 31) / 32) * 32;
+        if (in_dtype == B200_F32)
+            reshape_and_cache_flash_fp8_vec_kernel<float><<<num_tokens, threads, 0, st>>>((const float*)key, (const float*)value, (uint8_t*)key_cache, (uint8_t*)value_cache, slot_mapping, n, key_stride, value_stride);
+        else if (in_dtype == B200_BF16)
+            reshape_and_cache_flash_fp8_vec_kernel<__nv_bfloat16><<<num_tokens, threads, 0, st>>>((const __nv_bfloat16*)key, (const __nv_bfloat16*)value, (uint8_t*)key_cache, (uint8_t*)value_cache, slot_mapping, n, key_stride, value_stride);
+        else
+            reshape_and_cache_flash_fp8_vec_kernel<__half><<<num_tokens, threads, 0, st>>>((const __half*)key, (const __half*)value, (uint8_t*)key_cache, (uint8_t*)value_cache, slot_mapping, n, key_stride, value_stride);
     } else if (in_dtype == B200_F32) {
         launch_rac<float>(key, value, key_cache, value_cache, slot_mapping, num_tokens, num_kv_heads, head_dim, block_size, key_stride, value_stride, cache_dtype, in_dtype, layout, st);
     } else if (in_dtype == B200_BF16) {

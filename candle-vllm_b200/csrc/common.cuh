@@ -15,7 +15,11 @@ namespace b200 {
 void set_error(int code, const char* fmt, ...);
 bool check_launch(const char* what);   // records cudaGetLastError() if any; returns true when ok
 void count_launch(int n = 1);          // library-wide launch counter (gpu_launches evidence)
-int  sm_count();
+int  sm_count();                        // SM count of the CURRENT device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize, applied once per (device, kernel): the attribute is per device, so a
+// per-process `static bool` would leave every device but the first without it (threaded.rs runs one thread per rank in
+// one process, /root/reference/src/openai/pipelines/threaded.rs:33-134)
+void ensure_dynamic_smem(const void* kernel, int bytes);
 
 #define B200_REQUIRE(cond, code, ...)                  \
     do {                                               \

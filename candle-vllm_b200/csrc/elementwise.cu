@@ -147,6 +147,110 @@ rope_and_cache_kernel(float* __restrict__ qkv, T16* __restrict__ q_out, void* __
     }
 }
 
+// Vectorised form of the above for head_dim % 32 == 0 (every Llama / Qwen / DeepSeek head size): one thread owns 16 rotation
+// pairs = 32 elements of one (token, head slot) -- interleaved: 32 consecutive elements; NeoX: [16u, 16u+16) and
+// [half+16u, half+16u+16) -- so q and the bf16 / f16 cache get 16-byte stores and an FP8 (e4m3) cache gets 16-byte stores of 16
+// values (north_star: "reshape_and_cache writes FP8 KV as coalesced vectorised HBM stores").  Same arithmetic and the same two
+// roundings (f32 -> model dtype -> e4m3, attention.rs:971-975 then the cache write) as the scalar kernel.
+template <typename T16> __device__ __forceinline__ uint32_t pack16(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack16<__half>(float a, float b) { const __half2 v = __halves2half2(from_f32<__half>(a), from_f32<__half>(b)); return *reinterpret_cast<const uint32_t*>(&v); }
+template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float a, float b) { const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&v); }
+template <typename T16> __device__ __forceinline__ float round16(float a) { return to_f32(from_f32<T16>(a)); }
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    const uint32_t lo = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+// store 16 f32 values as 16 T16 (two 16-byte stores) or, kFp8, as 16 e4m3 bytes (one 16-byte store) after rounding to T16
+template <typename T16, bool kFp8>
+__device__ __forceinline__ void store16(void* base, int64_t elem_off, const float (&v)[16]) {
+    if constexpr (kFp8) {
+        uint4 o;
+        o.x = pack_e4m3x4(round16<T16>(v[0]), round16<T16>(v[1]), round16<T16>(v[2]), round16<T16>(v[3]));
+        o.y = pack_e4m3x4(round16<T16>(v[4]), round16<T16>(v[5]), round16<T16>(v[6]), round16<T16>(v[7]));
+        o.z = pack_e4m3x4(round16<T16>(v[8]), round16<T16>(v[9]), round16<T16>(v[10]), round16<T16>(v[11]));
+        o.w = pack_e4m3x4(round16<T16>(v[12]), round16<T16>(v[13]), round16<T16>(v[14]), round16<T16>(v[15]));
+        *reinterpret_cast<uint4*>(static_cast<uint8_t*>(base) + elem_off) = o;
+    } else {
+        uint4 a, b;
+        a.x = pack16<T16>(v[0], v[1]); a.y = pack16<T16>(v[2], v[3]); a.z = pack16<T16>(v[4], v[5]); a.w = pack16<T16>(v[6], v[7]);
+        b.x = pack16<T16>(v[8], v[9]); b.y = pack16<T16>(v[10], v[11]); b.z = pack16<T16>(v[12], v[13]); b.w = pack16<T16>(v[14], v[15]);
+        uint4* o = reinterpret_cast<uint4*>(static_cast<T16*>(base) + elem_off);
+        o[0] = a; o[1] = b;
+    }
+}
+__device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float4 t = reinterpret_cast<const float4*>(p)[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+}
+__device__ __forceinline__ void zero16(float* p) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// one work item = (token t, head slot hs, unit u): callable from the stand-alone kernel below and from the fused layer kernel
+template <typename T16, bool kFp8, bool kZeroSrc>
+__device__ __forceinline__ void rope_cache_item(int item, float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
+                                                const float* __restrict__ cos_t, const float* __restrict__ sin_t, const int64_t* __restrict__ positions,
+                                                const int64_t* __restrict__ slot_mapping, int num_heads, int num_kv_heads, int head_dim, int interleaved) {
+    const int units = head_dim >> 5, slots_per_tok = num_heads + 2 * num_kv_heads;
+    const int u = item % units, hs = (item / units) % slots_per_tok, t = item / (units * slots_per_tok);
+    const int half = head_dim >> 1;
+    const int64_t pos = positions[t], slot = slot_mapping[t];
+    float* src = qkv + ((int64_t)t * slots_per_tok + hs) * head_dim;
+    const int64_t kvn = (int64_t)num_kv_heads * head_dim;
+    // element ranges of this unit: A = [a0, a0 + 16), B = [b0, b0 + 16)
+    const bool rot = hs < num_heads + num_kv_heads;
+    const int a0 = (rot && !interleaved) ? 16 * u : 32 * u, b0 = (rot && !interleaved) ? half + 16 * u : 32 * u + 16;
+    float a[16], b[16];
+    load16(src + a0, a);
+    load16(src + b0, b);
+    if (rot) {
+        float c[16], sn[16];
+        load16(cos_t + pos * half + 16 * u, c);
+        load16(sin_t + pos * half + 16 * u, sn);
+        if (interleaved) {              // pair j = 16u + i lives at elements (2j, 2j + 1): i < 8 in A, i >= 8 in B
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float x0 = a[2 * i], x1 = a[2 * i + 1], y0 = b[2 * i], y1 = b[2 * i + 1];
+                a[2 * i] = x0 * c[i] - x1 * sn[i]; a[2 * i + 1] = x0 * sn[i] + x1 * c[i];
+                b[2 * i] = y0 * c[8 + i] - y1 * sn[8 + i]; b[2 * i + 1] = y0 * sn[8 + i] + y1 * c[8 + i];
+            }
+        } else {                        // pair j = 16u + i lives at (j, j + half) = (A[i], B[i])
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = a[i], x1 = b[i];
+                a[i] = x0 * c[i] - x1 * sn[i]; b[i] = x0 * sn[i] + x1 * c[i];
+            }
+        }
+    }
+    if (hs < num_heads) {
+        T16* o = q_out + ((int64_t)t * num_heads + hs) * head_dim;
+        store16<T16, false>(o, a0, a);
+        store16<T16, false>(o, b0, b);
+    } else if (slot >= 0) {
+        const bool is_k = hs < num_heads + num_kv_heads;
+        const int64_t base = slot * kvn + (int64_t)(hs - num_heads - (is_k ? 0 : num_kv_heads)) * head_dim;
+        void* cache = is_k ? kc_ : vc_;
+        store16<T16, kFp8>(cache, base + a0, a);
+        store16<T16, kFp8>(cache, base + b0, b);
+    }
+    if constexpr (kZeroSrc) { zero16(src + a0); zero16(src + b0); }     // leave the split-K accumulator zeroed for the next QKV GEMM
+}
+
+template <typename T16, bool kFp8, bool kZeroSrc>
+__global__ void __launch_bounds__(128)
+rope_and_cache_vec_kernel(float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
+                          const float* __restrict__ cos_t, const float* __restrict__ sin_t, const int64_t* __restrict__ positions,
+                          const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads, int num_kv_heads, int head_dim, int interleaved) {
+    pdl_wait();
+    pdl_trigger();
+    const int items = num_tokens * (num_heads + 2 * num_kv_heads) * (head_dim >> 5);
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < items)
+        rope_cache_item<T16, kFp8, kZeroSrc>(item, qkv, q_out, kc_, vc_, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved);
+}
+
 template <typename TOut, bool kK4 = false, bool kZeroSrc = false>
 __global__ void silu_mul_kernel(float* __restrict__ g, float* __restrict__ u, TOut* __restrict__ out, int64_t n) {
     pdl_wait();
@@ -221,13 +325,13 @@ argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int n)
 // stage 1 of greedy sampling: pairs[chunk][row] = (max logit, global index) over column chunk blockIdx.y of this rank's vocab
 // shard.  Stage 2 (argmax_reduce_pairs_kernel) reduces over chunks -- and, tensor-parallel, over the ranks' gathered pairs.
 __global__ void __launch_bounds__(256)
-argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int n, int index_offset) {
+argmax_pair_kernel(const float* __restrict__ x, float2* __restrict__ pairs, int ld, int n, int index_offset) {
     pdl_wait();
     pdl_trigger();
     const int row = blockIdx.x, rows = gridDim.x;
     const int per = (((n + (int)gridDim.y - 1) / (int)gridDim.y) + 3) & ~3;
     const int c0 = blockIdx.y * per, c1 = min(n, c0 + per);
-    const float* xr = x + (int64_t)row * n;
+    const float* xr = x + (int64_t)row * ld;
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
@@ -274,8 +378,9 @@ __global__ void argmax_reduce_pairs_kernel(const float2* __restrict__ gathered, 
     out[row] = bi == 0x7fffffff ? 0 : bi;
 }
 
-void argmax_pairs(const float* logits, void* pairs, int rows, int n, int chunks, int index_offset, cudaStream_t st) {
-    launch_pdl(argmax_pair_kernel, dim3(rows, chunks), dim3(256), 0, st, logits, static_cast<float2*>(pairs), n, index_offset);
+// logits [rows, ld]; only the first n columns of a row take part (vocab-parallel padding columns are never sampled)
+void argmax_pairs(const float* logits, void* pairs, int rows, int ld, int n, int chunks, int index_offset, cudaStream_t st) {
+    launch_pdl(argmax_pair_kernel, dim3(rows, chunks), dim3(256), 0, st, logits, static_cast<float2*>(pairs), ld, n, index_offset);
     count_launch();
     check_launch("argmax_pairs");
 }
@@ -283,6 +388,24 @@ void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world
     launch_pdl(argmax_reduce_pairs_kernel, dim3(ceil_div(rows, 128)), dim3(128), 0, st, static_cast<const float2*>(gathered), out, rows, world);
     count_launch();
     check_launch("argmax_reduce_pairs");
+}
+
+// VocabParallelLinear's gather epilogue (distributed.rs:1648-1664): gathered [world, rows, vocab_l] -> out [rows, vocab]
+// (transpose(0, 1), reshape, narrow to the original vocab)
+__global__ void gather_logits_transpose_kernel(const float* __restrict__ g, float* __restrict__ out, int world, int rows, int vocab_l, int vocab) {
+    pdl_wait();
+    pdl_trigger();
+    const int64_t total = (int64_t)rows * vocab;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / vocab), col = (int)(i - (int64_t)r * vocab);
+        const int w = col / vocab_l, c = col - w * vocab_l;
+        out[i] = g[((int64_t)w * rows + r) * vocab_l + c];
+    }
+}
+void gather_logits_transpose(const float* gathered, float* out, int world, int rows, int vocab_l, int vocab, cudaStream_t st) {
+    launch_pdl(gather_logits_transpose_kernel, dim3(sm_count() * 4), dim3(256), 0, st, gathered, out, world, rows, vocab_l, vocab);
+    count_launch();
+    check_launch("gather_logits");
 }
 
 static inline int ew_grid(int64_t n) {
@@ -335,7 +458,11 @@ void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_c
     const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
     B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "rope_and_cache: cache dtype %d vs dtype %d", cache_dtype, dtype);
     cudaStream_t st = as_stream(stream);
-#define LAUNCH(T16, F8, Z) launch_pdl(rope_and_cache_kernel<T16, F8, Z>, dim3(num_tokens, num_heads + 2 * num_kv_heads), dim3(64), 0, st, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved)
+    // 16-byte loads / stores need 16-byte aligned rows: head_dim % 32 == 0 and aligned bases (cudaMalloc gives 256)
+    const bool vec = head_dim % 32 == 0 && ((((uintptr_t)qkv | (uintptr_t)q_out | (uintptr_t)key_cache | (uintptr_t)value_cache | (uintptr_t)cos_t | (uintptr_t)sin_t) & 15) == 0);
+    const int items = num_tokens * (num_heads + 2 * num_kv_heads) * (head_dim >> 5);
+#define LAUNCH(T16, F8, Z) do { if (vec) launch_pdl(rope_and_cache_vec_kernel<T16, F8, Z>, dim3(ceil_div(items, 128)), dim3(128), 0, st, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, (int)num_tokens, (int)num_heads, (int)num_kv_heads, (int)head_dim, (int)interleaved); \
+        else launch_pdl(rope_and_cache_kernel<T16, F8, Z>, dim3(num_tokens, num_heads + 2 * num_kv_heads), dim3(64), 0, st, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved); } while (0)
 #define LAUNCH2(T16, F8) do { if (zero_src) LAUNCH(T16, F8, true); else LAUNCH(T16, F8, false); } while (0)
     if (dtype == B200_BF16) { if (fp8) LAUNCH2(__nv_bfloat16, true); else LAUNCH2(__nv_bfloat16, false); }
     else if (dtype == B200_F16) { if (fp8) LAUNCH2(__half, true); else LAUNCH2(__half, false); }

@@ -13,7 +13,9 @@
 // fp16 (include/b200_backend.h); q,k,v -> bf16 before the cache write / attention; attention output
 // rounded to bf16, handed to wo as fp16 (exact: bf16 subset of fp16 range here); logits f32.
 // The residual adds are fused into the wo / w2 GEMM epilogues (accumulate into x).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -27,10 +29,11 @@ namespace b200 {
 void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st);
 void tp_allgather_bytes(void* comm, const void* src, void* dst, size_t bytes_per_rank, cudaStream_t st);
 size_t tp_peer_inbox_bytes(int world, int rows_max, int n);
-size_t tp_peer_timeout_offset(int world, int rows_max, int n);
+void tp_set_timeout_ms(long long ms);
 void tp_allreduce_add_norm(float* partial, float* x, const float* norm_w, void* xn_f16_k4, void* const* peers, int rank, int world,
-                           int rows, int n, int rows_max, float eps, cudaStream_t st);
-void argmax_pairs(const float* logits, void* pairs, int rows, int n, int chunks, int index_offset, cudaStream_t st);
+                           int rows, int n, int rows_max, float eps, uint32_t* timeout_word, cudaStream_t st);
+void gather_logits_transpose(const float* gathered, float* out, int world, int rows, int vocab_l, int vocab, cudaStream_t st);
+void argmax_pairs(const float* logits, void* pairs, int rows, int ld, int n, int chunks, int index_offset, cudaStream_t st);
 void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st);
 }
 
@@ -60,9 +63,17 @@ struct b200_llama {
     float* cos_t = nullptr; float* sin_t = nullptr;
     void* attn_ws = nullptr; size_t attn_ws_bytes = 0;
 
-    // pinned staging for the host metadata (one slab)
-    char* h_stage = nullptr; size_t stage_bytes = 0;
+    // pinned staging for the host metadata: two slabs used alternately, each guarded by an event recorded after its H2D copy, so
+    // a caller that does not read results back (both host pointers NULL) can queue the next step without overwriting a slab
+    // whose copy is still in flight
+    char* h_stage[2] = {nullptr, nullptr}; cudaEvent_t stage_ev[2] = {nullptr, nullptr}; int stage_idx = 0;
+    size_t stage_bytes = 0;
     int32_t* h_next = nullptr;
+    // fused all-reduce give-up flag: host-mapped pinned word written by the kernel (tp.cu), read by the host after a stream sync
+    uint32_t* h_timeout = nullptr; uint32_t* d_timeout = nullptr;
+    // vocab-parallel lm_head (distributed.rs:1448-1454): vocab padded to 64 and split; gathered logits on request
+    int vocab_pad = 0;
+    float* logits_gathered = nullptr; float* logits_full = nullptr;
 
     std::map<int, cudaGraphExec_t> graphs;       // batch size -> captured step
     std::map<int, int> launches_per_step;
@@ -94,7 +105,10 @@ __global__ void advance_metadata_kernel(int64_t* tokens, const int32_t* next_tok
     const int64_t pos = positions[b] + 1;
     positions[b] = pos;
     ctx[b] += 1;
-    slots[b] = (int64_t)tables[(int64_t)b * max_blocks + pos / block_size] * block_size + pos % block_size;
+    // a sequence that outgrows its table row gets the pad slot (no cache write) instead of an out-of-bounds table read
+    const int64_t blk = pos / block_size;
+    slots[b] = blk < max_blocks ? (int64_t)tables[(int64_t)b * max_blocks + blk] * block_size + pos % block_size : -1;
+    if (blk >= max_blocks) ctx[b] = (uint32_t)max_blocks * (uint32_t)block_size;
 }
 
 __global__ void zero_f32_kernel(float* p, int64_t n) {
@@ -104,7 +118,9 @@ __global__ void zero_f32_kernel(float* p, int64_t n) {
 }
 
 // One decode forward on `st` for B sequences.  Returns number of kernel launches issued.
-int forward(b200_llama* m, int B, cudaStream_t st) {
+// linear_only: skip RoPE + cache write + attention (the measurement leg behind bench.py's roofline_gemm: the weight stream
+// of all quantised projections and the small ops between them, without the KV stream)
+int forward(b200_llama* m, int B, cudaStream_t st, bool linear_only = false) {
     const b200_llama_config& c = m->cfg;
     const int64_t s = reinterpret_cast<int64_t>(st);
     const int H = c.hidden, hd = c.head_dim;
@@ -116,7 +132,7 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
     // one kernel over NVLink peer memory (tp.cu); `partial` is left zeroed by that kernel for the next split-K GEMM
     const bool fused_ar = c.tp_world > 1 && (int)m->peers.size() == c.tp_world;
     auto residual_fused = [&](const float* next_norm) {
-        tp_allreduce_add_norm(m->partial, m->x, next_norm, m->xn, m->peers.data(), c.tp_rank, c.tp_world, B, H, c.max_num_seqs, c.rms_eps, st);
+        tp_allreduce_add_norm(m->partial, m->x, next_norm, m->xn, m->peers.data(), c.tp_rank, c.tp_world, B, H, c.max_num_seqs, c.rms_eps, m->d_timeout, st);
     };
     for (int l = 0; l < c.num_layers; ++l) {
         const b200_llama_layer& w = m->layers[l];
@@ -129,12 +145,14 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
             // accumulate = 0: whole tiles are plain stores, split tiles red.add into the zeroed buffer
             qmatmul_dispatch_multi(m->xn, 3, ws, ts, ys, ns, m->qkv_row, B, H, 0, st);
         }
+        if (linear_only) { launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->qkv, (int64_t)B * m->qkv_row); count_launch(); } else {
         // (also re-zeroes qkv: the split-K GEMMs accumulate into it)
         rope_and_cache_impl(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
                             m->heads_l, m->kv_l, hd, /*interleaved=*/1, B200_BF16, c.kv_dtype, /*zero_src=*/true, s);
         paged_attention_decode(m->attn16, m->q16, m->kc[l], m->vc[l], m->d_tables, m->d_ctx, B, m->heads_l, m->kv_l, hd,
                                c.block_size, c.max_blocks_per_seq, m->num_blocks, 1.0f / sqrtf((float)hd), 0.f, 0,
                                B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16_K4, m->attn_ws, m->attn_ws_bytes, s);
+        }
         if (c.tp_world == 1) {
             qmatmul_dispatch(m->attn16, w.wo, m->x, H, B, H, qd, w.to, 1, st);          // x += wo(attn)
         } else if (fused_ar) {
@@ -175,7 +193,9 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
     qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
     // greedy sampling in two stages; vocab-parallel lm_head (distributed.rs:1632-1667): gather (max, global index) pairs
     // instead of the logits
-    argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, kArgmaxChunks, c.tp_rank * m->vocab_l, st);
+    // vocab-parallel: this rank's columns are [tp_rank * vocab_l, ...); columns at or beyond `vocab` are padding (never sampled)
+    const int live_cols = std::max(0, std::min(m->vocab_l, c.vocab - c.tp_rank * m->vocab_l));
+    argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, live_cols, kArgmaxChunks, c.tp_rank * m->vocab_l, st);
     if (c.tp_world == 1) {
         argmax_reduce_pairs(m->tp_pairs, m->next_tokens, B, kArgmaxChunks, st);
     } else {
@@ -183,6 +203,20 @@ int forward(b200_llama* m, int B, cudaStream_t st) {
         argmax_reduce_pairs(m->tp_gathered, m->next_tokens, B, c.tp_world * kArgmaxChunks, st);
     }
     return (int)(b200_total_kernel_launches() - n0);
+}
+
+// captured graphs bake in weight / cache / communicator pointers: every setter that changes one drops them
+void invalidate_graphs(b200_llama* m) {
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    m->graphs.clear();
+    m->launches_per_step.clear();
+}
+
+// a row of the fused all-reduce gave up waiting for a peer: the step's outputs are NaN -- report it instead of returning them
+bool peer_timed_out(b200_llama* m, const char* who) {
+    if (!m->h_timeout || *reinterpret_cast<volatile uint32_t*>(m->h_timeout) == 0u) return false;
+    set_error(kErrCuda, "%s: the fused tensor-parallel all-reduce timed out waiting for a peer rank (B200_TP_TIMEOUT_MS); this step's outputs are invalid", who);
+    return true;
 }
 
 bool ready(b200_llama* m) {
@@ -236,10 +270,11 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
         set_error(kErrBadArg, "b200_llama_create: bad config");
         return nullptr;
     }
-    if (c.num_heads % c.tp_world || c.ffn % c.tp_world || c.vocab % c.tp_world) {
-        set_error(kErrBadArg, "b200_llama_create: heads/ffn/vocab not divisible by tp_world=%d", c.tp_world);
+    if (c.num_heads % c.tp_world || c.ffn % c.tp_world) {
+        set_error(kErrBadArg, "b200_llama_create: heads/ffn not divisible by tp_world=%d", c.tp_world);
         return nullptr;
     }
+    if (c.max_blocks_per_seq > (1 << 20) || (int64_t)c.max_blocks_per_seq * c.block_size > INT32_MAX) { set_error(kErrBadArg, "b200_llama_create: table too wide"); return nullptr; }
     if (b200_device_cc() < 100) { set_error(kErrNoDevice, "b200_llama_create: no sm_100 device (cc=%d)", b200_device_cc()); return nullptr; }
     b200_llama* m = new b200_llama();
     m->cfg = c;
@@ -249,7 +284,15 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
     // kv_head_shard (/root/reference/src/openai/distributed.rs:725-765): split, or replicate when kvh < world
     m->kv_l = c.num_kv_heads >= c.tp_world ? c.num_kv_heads / c.tp_world : 1;
     m->ffn_l = c.ffn / c.tp_world;
-    m->vocab_l = c.vocab / c.tp_world;
+    // pad_vocab_size (/root/reference/src/openai/distributed.rs:1448-1454): multiple of 64, of the world size, of 64 again; every
+    // rank owns vocab_pad / world rows of the lm_head (rows past `vocab` are padding the caller fills with zeros)
+    {
+        const int64_t padded = ((int64_t)c.vocab + 63) / 64 * 64;
+        const int64_t per_rank = (padded + c.tp_world - 1) / c.tp_world * c.tp_world;
+        m->vocab_pad = c.tp_world == 1 ? c.vocab : (int)((per_rank + 63) / 64 * 64);
+        if (m->vocab_pad % c.tp_world) { set_error(kErrBadArg, "b200_llama_create: padded vocab %d not divisible by tp_world %d", m->vocab_pad, c.tp_world); delete m; return nullptr; }
+    }
+    m->vocab_l = m->vocab_pad / c.tp_world;
     m->qkv_row = (m->heads_l + 2 * m->kv_l) * c.head_dim;
     const size_t B = c.max_num_seqs;
     constexpr size_t kChunks = 16;
@@ -286,8 +329,19 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
         cudaMemcpy(m->cos_t, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(m->sin_t, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
     }
-    ok = ok && cudaMallocHost((void**)&m->h_stage, m->stage_bytes) == cudaSuccess &&
-         cudaMallocHost((void**)&m->h_next, B * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&m->h_stage[0], m->stage_bytes) == cudaSuccess &&
+         cudaMallocHost((void**)&m->h_stage[1], m->stage_bytes) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->stage_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&m->stage_ev[1], cudaEventDisableTiming) == cudaSuccess &&
+         cudaMallocHost((void**)&m->h_next, B * 4) == cudaSuccess &&
+         cudaHostAlloc((void**)&m->h_timeout, 64, cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer((void**)&m->d_timeout, m->h_timeout, 0) == cudaSuccess;
+    if (ok) *m->h_timeout = 0u;
+    if (ok && c.tp_world > 1) {
+        ok = dmalloc(m->logits_gathered, B * (size_t)m->vocab_pad) && dmalloc(m->logits_full, B * (size_t)c.vocab);
+        static const long long tmo = [] { const char* e = getenv("B200_TP_TIMEOUT_MS"); return e ? atoll(e) : 120000ll; }();
+        tp_set_timeout_ms(tmo);
+    }
     if (!ok) {
         if (!b200_last_error()) set_error(kErrCuda, "b200_llama_create: allocation failed");
         b200_llama_destroy(m);
@@ -303,8 +357,11 @@ void b200_llama_destroy(b200_llama* m) {
     void* ptrs[] = {m->d_meta, m->x, m->xn, m->qkv, m->q16, m->attn16,
                     m->gate, m->up, m->act16, m->partial, m->logits, m->next_tokens, m->cos_t, m->sin_t, m->attn_ws, m->tp_pairs, m->tp_gathered};
     for (void* p : ptrs) if (p) cudaFree(p);
-    if (m->h_stage) cudaFreeHost(m->h_stage);
+    for (int i = 0; i < 2; ++i) { if (m->h_stage[i]) cudaFreeHost(m->h_stage[i]); if (m->stage_ev[i]) cudaEventDestroy(m->stage_ev[i]); }
     if (m->h_next) cudaFreeHost(m->h_next);
+    if (m->h_timeout) cudaFreeHost(m->h_timeout);
+    if (m->logits_gathered) cudaFree(m->logits_gathered);
+    if (m->logits_full) cudaFree(m->logits_full);
     delete m;
 }
 
@@ -313,11 +370,13 @@ void b200_llama_set_layer(b200_llama* m, int32_t layer, const b200_llama_layer* 
     B200_REQUIRE(w->attn_norm && w->ffn_norm && w->wq && w->wk && w->wv && w->wo && w->w1 && w->w2 && w->w3, kErrBadArg,
                  "b200_llama_set_layer: null weight in layer %d", layer);
     m->layers[layer] = *w;
+    invalidate_graphs(m);
 }
 
 void b200_llama_set_globals(b200_llama* m, const float* tok_embeddings, const float* norm, const void* output_w, int32_t output_type) {
     B200_REQUIRE(m && tok_embeddings && norm && output_w, kErrBadArg, "b200_llama_set_globals: null pointer");
     m->tok_embeddings = tok_embeddings; m->norm = norm; m->output_w = output_w; m->output_type = output_type;
+    invalidate_graphs(m);
 }
 
 void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const* value_caches, int64_t num_blocks) {
@@ -325,8 +384,7 @@ void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const
     m->kc.assign(key_caches, key_caches + m->cfg.num_layers);
     m->vc.assign(value_caches, value_caches + m->cfg.num_layers);
     m->num_blocks = num_blocks;
-    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);    // pointers are baked into captured graphs
-    m->graphs.clear();
+    invalidate_graphs(m);                                        // pointers are baked into captured graphs
 }
 
 size_t b200_llama_peer_inbox_bytes(const b200_llama* m) {
@@ -343,24 +401,30 @@ void b200_llama_set_peer_inboxes(b200_llama* m, void* const* inboxes, int32_t co
         m->peers.assign(inboxes, inboxes + count);
     }
     cudaMemset(m->partial, 0, (size_t)m->cfg.max_num_seqs * m->cfg.hidden * sizeof(float));     // the fused kernel keeps it zeroed from here on
-    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);    // the forward changes shape
-    m->graphs.clear();
+    if (m->h_timeout) *m->h_timeout = 0u;
+    invalidate_graphs(m);                                        // the forward changes shape
 }
 
 int32_t b200_llama_peer_timeouts(b200_llama* m) {
-    if (!m || m->peers.empty()) return 0;
-    uint32_t v = 0;
-    const char* mine = static_cast<const char*>(m->peers[m->cfg.tp_rank]);
-    if (cudaMemcpy(&v, mine + tp_peer_timeout_offset(m->cfg.tp_world, m->cfg.max_num_seqs, m->cfg.hidden), 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
-        set_error(kErrCuda, "b200_llama_peer_timeouts: %s", cudaGetErrorString(cudaGetLastError()));
-        return -1;
-    }
-    return (int32_t)v;
+    if (!m || !m->h_timeout) return 0;
+    return (int32_t)*reinterpret_cast<volatile uint32_t*>(m->h_timeout);
 }
 
 void b200_llama_set_comm(b200_llama* m, void* nccl_comm) {
     B200_REQUIRE(m, kErrBadArg, "b200_llama_set_comm: null model");
     m->comm = nccl_comm;
+    invalidate_graphs(m);
+}
+
+// full-vocabulary logits [n, vocab] on the device: the local buffer at TP = 1; vocab-parallel (VocabParallelLinear::forward,
+// /root/reference/src/openai/distributed.rs:1632-1667): all-gather the [n, vocab_l] shards -> [world, n, vocab_l] -> transpose ->
+// [n, world * vocab_l] -> narrow to the original vocab.  A collective: every rank must ask for logits in the same step.
+static const float* full_logits(b200_llama* m, int n, cudaStream_t st) {
+    if (m->cfg.tp_world == 1) return m->logits;
+    tp_allgather_bytes(m->comm, m->logits, m->logits_gathered, (size_t)n * m->vocab_l * sizeof(float), st);
+    gather_logits_transpose(m->logits_gathered, m->logits_full, m->cfg.tp_world, n, m->vocab_l, m->cfg.vocab, st);
+    m->launches += 1;
+    return m->logits_full;
 }
 
 void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* positions,
@@ -375,31 +439,45 @@ void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* pos
                  "b200_llama_decode: block table width %d out of (0, %d]", table_width, c.max_blocks_per_seq);
     cudaStream_t st = as_stream(stream);
     const int B = num_seqs, W = c.max_blocks_per_seq;
+    const int64_t slots_total = m->num_blocks * (int64_t)c.block_size;
+    for (int b = 0; b < B; ++b) {
+        B200_REQUIRE(tokens[b] < (uint32_t)c.vocab, kErrBadArg, "b200_llama_decode: token id %u >= vocab", tokens[b]);
+        B200_REQUIRE(positions[b] >= 0 && positions[b] < c.max_pos, kErrBadArg, "b200_llama_decode: position out of range");
+        // the attention kernel walks ceil(ctx / block_size) entries of this sequence's table row
+        B200_REQUIRE(context_lens[b] >= 1 && (int64_t)context_lens[b] <= (int64_t)table_width * c.block_size, kErrBadArg,
+                     "b200_llama_decode: context_lens[%d] = %u exceeds the block table (%d blocks of %d)", b, context_lens[b], table_width, c.block_size);
+        B200_REQUIRE(slot_mapping[b] < slots_total, kErrBadArg, "b200_llama_decode: slot_mapping[%d] = %lld beyond the cache (%lld slots)", b,
+                     (long long)slot_mapping[b], (long long)slots_total);
+    }
     // stage into pinned memory (same layout as the device slab); block tables are re-padded with zeros to the static
-    // width (graph.rs:732-738)
+    // width (graph.rs:732-738).  Two slabs alternate; a slab is reused only after the copy that read it has finished.
+    const int si = m->stage_idx;
+    m->stage_idx ^= 1;
+    cudaEventSynchronize(m->stage_ev[si]);                       // no-op unless this slab's previous copy is still in flight
+    char* stage = m->h_stage[si];
     const size_t Bp = ((size_t)c.max_num_seqs + 3) & ~(size_t)3;
-    int64_t* h_tok = (int64_t*)m->h_stage;
+    int64_t* h_tok = (int64_t*)stage;
     int64_t* h_pos = h_tok + Bp;
     int64_t* h_slot = h_pos + Bp;
     uint32_t* h_ctx = (uint32_t*)(h_slot + Bp);
     uint32_t* h_tab = h_ctx + Bp;
     for (int b = 0; b < B; ++b) {
-        B200_REQUIRE(tokens[b] < (uint32_t)c.vocab, kErrBadArg, "b200_llama_decode: token id %u >= vocab", tokens[b]);
-        B200_REQUIRE(positions[b] >= 0 && positions[b] < c.max_pos, kErrBadArg, "b200_llama_decode: position out of range");
         h_tok[b] = tokens[b]; h_pos[b] = positions[b]; h_slot[b] = slot_mapping[b]; h_ctx[b] = context_lens[b];
         for (int j = 0; j < W; ++j) h_tab[(size_t)b * W + j] = j < table_width ? block_tables[(size_t)b * table_width + j] : 0u;
     }
-    cudaMemcpyAsync(m->d_meta, m->h_stage, (size_t)((char*)(h_tab + (size_t)B * W) - m->h_stage), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(m->d_meta, stage, (size_t)((char*)(h_tab + (size_t)B * W) - stage), cudaMemcpyHostToDevice, st);
+    cudaEventRecord(m->stage_ev[si], st);
     run_step(m, B, st);
-    if (logits_host) cudaMemcpyAsync(logits_host, m->logits, (size_t)B * m->vocab_l * 4, cudaMemcpyDeviceToHost, st);
-    if (next_tokens_host) {
-        cudaMemcpyAsync(m->h_next, m->next_tokens, 4 * B, cudaMemcpyDeviceToHost, st);
+    if (logits_host) {
+        const float* src = full_logits(m, B, st);
+        cudaMemcpyAsync(logits_host, src, (size_t)B * c.vocab * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (next_tokens_host) cudaMemcpyAsync(m->h_next, m->next_tokens, 4 * B, cudaMemcpyDeviceToHost, st);
+    if (next_tokens_host || logits_host) {
         cudaError_t e = cudaStreamSynchronize(st);                 // graph.rs:297-301
         if (e != cudaSuccess) { set_error(kErrCuda, "b200_llama_decode: %s", cudaGetErrorString(e)); return; }
-        for (int b = 0; b < B; ++b) next_tokens_host[b] = m->h_next[b];
-    } else if (logits_host) {
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { set_error(kErrCuda, "b200_llama_decode: %s", cudaGetErrorString(e)); return; }
+        if (peer_timed_out(m, "b200_llama_decode")) return;
+        if (next_tokens_host) for (int b = 0; b < B; ++b) next_tokens_host[b] = m->h_next[b];
     }
 }
 
@@ -416,18 +494,27 @@ void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance
     run_step(m, num_seqs, st);
 }
 
+void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream) {
+    if (!ready(m)) return;
+    B200_REQUIRE(num_seqs > 0 && num_seqs <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_linear_chain: bad num_seqs");
+    m->launches += forward(m, num_seqs, as_stream(stream), /*linear_only=*/true);
+}
+
 void b200_llama_read_next_tokens(b200_llama* m, int32_t* host, int32_t n, int64_t stream) {
     B200_REQUIRE(m && host && n > 0 && n <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_read_next_tokens: bad arguments");
     cudaMemcpyAsync(host, m->next_tokens, (size_t)n * 4, cudaMemcpyDeviceToHost, as_stream(stream));
     cudaError_t e = cudaStreamSynchronize(as_stream(stream));
-    if (e != cudaSuccess) set_error(kErrCuda, "b200_llama_read_next_tokens: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { set_error(kErrCuda, "b200_llama_read_next_tokens: %s", cudaGetErrorString(e)); return; }
+    peer_timed_out(m, "b200_llama_read_next_tokens");
 }
 
 void b200_llama_read_logits(b200_llama* m, float* host, int32_t n, int64_t stream) {
     B200_REQUIRE(m && host && n > 0 && n <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_read_logits: bad arguments");
-    cudaMemcpyAsync(host, m->logits, (size_t)n * m->vocab_l * 4, cudaMemcpyDeviceToHost, as_stream(stream));
+    const float* src = full_logits(m, n, as_stream(stream));
+    cudaMemcpyAsync(host, src, (size_t)n * m->cfg.vocab * 4, cudaMemcpyDeviceToHost, as_stream(stream));
     cudaError_t e = cudaStreamSynchronize(as_stream(stream));
-    if (e != cudaSuccess) set_error(kErrCuda, "b200_llama_read_logits: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { set_error(kErrCuda, "b200_llama_read_logits: %s", cudaGetErrorString(e)); return; }
+    peer_timed_out(m, "b200_llama_read_logits");
 }
 
 const float* b200_llama_logits(b200_llama* m) { return m ? m->logits : nullptr; }

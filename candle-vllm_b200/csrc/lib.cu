@@ -3,6 +3,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -36,18 +39,32 @@ bool pdl_enabled() {
     return on != 0;
 }
 
+constexpr int kMaxDevices = 64;
+
 int sm_count() {
-    static int cached = -1;
-    if (cached < 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    static std::atomic<int> cached[kMaxDevices];          // zero-initialised: 0 = not probed yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return 148; }
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
             cudaGetLastError();
             return 148;   // B200; only used to size grids
         }
-        cached = n;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
+}
+
+void ensure_dynamic_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count({dev, kernel})) return;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess) done.insert({dev, kernel});
+    else cudaGetLastError();
 }
 
 }  // namespace b200

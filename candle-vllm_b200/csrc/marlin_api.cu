@@ -11,6 +11,10 @@
 // repacks to Marlin (linear.rs:319-325) -- symmetric GPTQ (marlin_4bit_*) and AWQ with zero points (awq_repack +
 // marlin_awq_4bit_*, zero points in the layout of examples/convert_awq_marlin.py).  Everything else (act-order, asymmetric GPTQ,
 // 8 bit) takes the shape-generic gemm_half_q_half_alt kernel, as in the reference (gptq.rs:182-197).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "qmatmul.cuh"
 
 namespace b200 {
@@ -93,27 +97,39 @@ gptq_alt_kernel(const __half* __restrict__ x, const uint32_t* __restrict__ qw, c
         if (m0 + i < m) out[(int64_t)(m0 + i) * n + col] = __float2half_rn(acc[i]);
 }
 
-// activation scratch (fp16, K4 order): the reference ABI has no slot for it (its `workspace` is N words of locks),
-// so the library owns one buffer per device, grown outside stream capture (the reference warms every shape up
-// eagerly before capturing, graph.rs:471-661) or provided once with b200_set_scratch().
-static void* g_scratch = nullptr;      // (fp16 activation copy + fp32 partial-sum slabs of the 16-bit-output GEMMs)
-static size_t g_scratch_bytes = 0;
-static bool g_scratch_owned = false;
+// activation scratch (fp16, K4 order) + fp32 partial-sum slabs: the reference ABI has no slot for it (its `workspace` is N
+// words of locks), so the library owns one buffer per (device, stream) -- two streams or two devices (threaded.rs runs one
+// thread per rank in one process) never share scratch -- grown outside stream capture (the reference warms every shape up
+// eagerly before capturing, graph.rs:471-661), or one caller-provided buffer per device set with b200_set_scratch().
+struct Scratch { void* ptr = nullptr; size_t bytes = 0; bool owned = false; };
+static std::mutex g_scratch_mu;
+static std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;      // library-owned, per (device, stream)
+static std::map<int, Scratch> g_user_scratch;                          // b200_set_scratch, per device
 
 void* get_scratch(size_t bytes, cudaStream_t st) {
-    if (bytes <= g_scratch_bytes) return g_scratch;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error(kErrCuda, "scratch: no current device"); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    auto u = g_user_scratch.find(dev);
+    if (u != g_user_scratch.end() && u->second.ptr) {
+        if (bytes <= u->second.bytes) return u->second.ptr;
+        set_error(kErrBadArg, "scratch: the buffer given to b200_set_scratch holds %zu bytes, %zu needed", u->second.bytes, bytes);
+        return nullptr;
+    }
+    Scratch& sc = g_scratch[{dev, st}];
+    if (bytes <= sc.bytes) return sc.ptr;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
     if (cs != cudaStreamCaptureStatusNone) {
-        set_error(kErrBadArg, "marlin: activation scratch too small (%zu < %zu) during stream capture; run the shape once eagerly or call b200_set_scratch", g_scratch_bytes, bytes);
+        set_error(kErrBadArg, "marlin: activation scratch too small (%zu < %zu) during stream capture; run the shape once eagerly or call b200_set_scratch", sc.bytes, bytes);
         return nullptr;
     }
-    cudaStreamSynchronize(st);
-    if (g_scratch_owned && g_scratch) cudaFree(g_scratch);
+    cudaStreamSynchronize(st);                               // nothing on this stream still reads the old buffer
+    if (sc.ptr) cudaFree(sc.ptr);
     const size_t want = bytes < (4u << 20) ? (4u << 20) : bytes;
-    if (cudaMalloc(&g_scratch, want) != cudaSuccess) { g_scratch = nullptr; g_scratch_bytes = 0; set_error(kErrCuda, "marlin: scratch cudaMalloc(%zu) failed", want); return nullptr; }
-    g_scratch_bytes = want; g_scratch_owned = true;
-    return g_scratch;
+    if (cudaMalloc(&sc.ptr, want) != cudaSuccess) { sc = Scratch{}; cudaGetLastError(); set_error(kErrCuda, "marlin: scratch cudaMalloc(%zu) failed", want); return nullptr; }
+    sc.bytes = want; sc.owned = true;
+    return sc.ptr;
 }
 
 static void marlin_4bit(const void* x, const void* qweight, const void* scales, const void* qzeros, const void* g_idx, void* out,
@@ -122,7 +138,12 @@ static void marlin_4bit(const void* x, const void* qweight, const void* scales, 
     B200_REQUIRE(x && qweight && scales && out, kErrBadArg, "marlin_4bit: null pointer");
     B200_REQUIRE(!awq || qzeros, kErrBadArg, "marlin_awq_4bit: qzeros (marlin zero-point layout, examples/convert_awq_marlin.py) is required");
     B200_REQUIRE(m > 0 && n > 0 && k > 0, kErrBadArg, "marlin_4bit: bad sizes m=%d k=%d n=%d", m, k, n);
-    B200_REQUIRE(g_idx == nullptr, kErrUnsupported, "marlin_4bit: act-order (g_idx) is not supported (linear.rs:319-325 never repacks it)");
+    // g_idx: the reference hands the checkpoint's g_idx to this symbol for EVERY quant_method == "gptq" layer
+    // (linear.rs:298-337 loads it as Some(..) even with desc_act = false; gptq.rs:27-35,139-152 forwards the pointer), and only
+    // repacks to Marlin when desc_act is false (linear.rs:319-325), where g_idx is the trivial k / group_size sequence.  Marlin
+    // never reads it on that path and neither do we (reading a device array here would force a host sync and break graph
+    // capture); real act-order checkpoints take gemm_half_q_half_alt, as in the reference (gptq.rs:182-197).
+    (void)g_idx;
     if (!awq) qzeros = nullptr;                        // symmetric: zero point 8 (the reference passes qzeros but Marlin ignores them)
     B200_REQUIRE(group_size == -1 || group_size == 64 || group_size == 128, kErrUnsupported, "marlin_4bit: group size %d (64, 128, -1)", group_size);
     B200_REQUIRE(k % 256 == 0 && n % 64 == 0, kErrUnsupported, "marlin_4bit: k %% 256 and n %% 64 must be 0 (k=%d n=%d)", k, n);
@@ -149,8 +170,11 @@ using namespace b200;
 extern "C" {
 
 void b200_set_scratch(void* ptr, size_t bytes) {
-    if (g_scratch_owned && g_scratch) cudaFree(g_scratch);
-    g_scratch = ptr; g_scratch_bytes = bytes; g_scratch_owned = false;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error(kErrCuda, "b200_set_scratch: no current device"); return; }
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (ptr && bytes) g_user_scratch[dev] = Scratch{ptr, bytes, false};
+    else g_user_scratch.erase(dev);
 }
 
 void gptq_repack(const void* in, void* out, int32_t k_packed, int32_t n, int64_t stream) {

@@ -776,8 +776,7 @@ int gemm_grid(int64_t n_tiles, int nsb, bool whole_tiles, bool slab_mode) {
 template <int kMB, int kType>
 void launch(const CUtensorMap* wm, const CUtensorMap& xm, const GemmParams& p, cudaStream_t st) {
     auto kern = qmatmul_tc_kernel<kMB, kType>;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<kMB, kType>::kTotal); attr = true; }
+    ensure_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg<kMB, kType>::kTotal);
     const int grid = gemm_grid(p.n_tiles, p.nsb, p.whole_tiles != 0, p.slabs > 0);
     launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg<kMB, kType>::kTotal, st, wm[0], wm[1], wm[2], xm, p);
     count_launch();

@@ -67,9 +67,12 @@ __device__ __forceinline__ uint4 ld_ll(const void* addr) {
     return v;
 }
 
-// bounded spin: a peer that never shows up (crashed rank) must not wedge the GPU -- after ~4 s the row gives up, poisons its
-// output with NaN and raises the inbox's timeout word (host-visible through b200_llama_peer_timeouts)
-__device__ __forceinline__ bool ll_wait(const void* addr, uint32_t e, uint4& w, uint32_t* timeout_word) {
+// bounded spin: a peer that never shows up (crashed rank) must not wedge the GPU -- after `timeout_ns` (B200_TP_TIMEOUT_MS,
+// default 120 s: long enough for a peer that is lazily capturing a graph, paused in a debugger or collecting garbage) the
+// row gives up, poisons its output with NaN and raises the timeout word.  The word lives in host-mapped pinned memory, so
+// b200_llama_decode / read_* see it right after their stream sync and report an error instead of returning token 0.
+__device__ unsigned long long g_tp_timeout_ns = 120000000000ull;
+__device__ __forceinline__ bool ll_wait(const void* addr, uint32_t e, uint4& w, volatile uint32_t* timeout_word) {
     w = ld_ll(addr);
     if (w.y == e && w.w == e) return true;
     unsigned long long t0 = 0;
@@ -80,7 +83,7 @@ __device__ __forceinline__ bool ll_wait(const void* addr, uint32_t e, uint4& w, 
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) { *timeout_word = 1u; w = make_uint4(0x7fc00000u, e, 0x7fc00000u, e); return false; }
+            else if (now - t0 > g_tp_timeout_ns) { *timeout_word = 1u; __threadfence_system(); w = make_uint4(0x7fc00000u, e, 0x7fc00000u, e); return false; }
         }
     }
 }
@@ -94,13 +97,14 @@ struct InboxLayout {
         bcast_off = (gather_bytes + 255) & ~(size_t)255;
         const size_t bcast_bytes = (size_t)2 * rows_max * (n / 2) * 8;       // [par][row][n/2] x {half2, epoch}
         epoch_off = (bcast_off + bcast_bytes + 255) & ~(size_t)255;
-        total = epoch_off + (((size_t)rows_max * 4 + 4 + 255) & ~(size_t)255);        // epochs + one timeout word
+        total = epoch_off + (((size_t)rows_max * 4 + 4 + 255) & ~(size_t)255);        // epochs (+ one spare word)
     }
 };
 
 __global__ void __launch_bounds__(256)
 tp_allreduce_add_norm_kernel(float* __restrict__ partial, float* __restrict__ x, const float* __restrict__ norm_w, __half* __restrict__ xn,
-                             PeerSet peers, int rank, int world, int n, int rows_max, float eps) {
+                             const __grid_constant__ PeerSet peers, int rank, int world, int n, int rows_max, float eps,
+                             uint32_t* __restrict__ timeout_word) {
     pdl_wait();
     pdl_trigger();
     constexpr int kMaxIt = 8;                                 // rows up to 8192 columns stay in registers
@@ -139,7 +143,7 @@ tp_allreduce_add_norm_kernel(float* __restrict__ partial, float* __restrict__ x,
             const int i = threadIdx.x + it * 256;            // 4 halves = 2 words = one 16-byte LL pair
             if (i < nv) {
                 uint4 w;
-                ll_wait(src + (size_t)i * 16, e, w, epoch + rows_max);
+                ll_wait(src + (size_t)i * 16, e, w, timeout_word);
                 *reinterpret_cast<uint2*>(o + 4 * i) = make_uint2(w.x, w.z);
             }
         }
@@ -156,8 +160,8 @@ tp_allreduce_add_norm_kernel(float* __restrict__ partial, float* __restrict__ x,
                     if (p == rank) { a.x += v[it].x; a.y += v[it].y; a.z += v[it].z; a.w += v[it].w; continue; }
                     const char* src = mine + (((size_t)par * world + p) * lay.rows_owned + lrow) * n * 8 + (size_t)i * 32;
                     uint4 w0, w1;
-                    ll_wait(src, e, w0, epoch + rows_max);
-                    ll_wait(src + 16, e, w1, epoch + rows_max);
+                    ll_wait(src, e, w0, timeout_word);
+                    ll_wait(src + 16, e, w1, timeout_word);
                     a.x += __uint_as_float(w0.x); a.y += __uint_as_float(w0.z); a.z += __uint_as_float(w1.x); a.w += __uint_as_float(w1.z);
                 }
                 xr[i] = a;
@@ -193,15 +197,18 @@ tp_allreduce_add_norm_kernel(float* __restrict__ partial, float* __restrict__ x,
 }
 
 size_t tp_peer_inbox_bytes(int world, int rows_max, int n) { return InboxLayout(world, rows_max, n).total; }
-size_t tp_peer_timeout_offset(int world, int rows_max, int n) { return InboxLayout(world, rows_max, n).epoch_off + (size_t)rows_max * 4; }
+void tp_set_timeout_ms(long long ms) {
+    const unsigned long long ns = (unsigned long long)(ms > 0 ? ms : 1) * 1000000ull;
+    cudaMemcpyToSymbol(g_tp_timeout_ns, &ns, sizeof(ns));
+}
 
 void tp_allreduce_add_norm(float* partial, float* x, const float* norm_w, void* xn_f16_k4, void* const* peers, int rank, int world,
-                           int rows, int n, int rows_max, float eps, cudaStream_t st) {
+                           int rows, int n, int rows_max, float eps, uint32_t* timeout_word, cudaStream_t st) {
     if (world < 2 || world > 8 || n % 4 || n > 8192 || rows > 128) { set_error(kErrUnsupported, "tp_allreduce_add_norm: world %d, n %d, rows %d", world, n, rows); return; }
     PeerSet ps{};
     for (int i = 0; i < world; ++i) ps.p[i] = static_cast<char*>(peers[i]);
     launch_pdl(tp_allreduce_add_norm_kernel, dim3(rows), dim3(256), 0, st, partial, x, norm_w, static_cast<__half*>(xn_f16_k4), ps, rank, world, n,
-               rows_max, eps);
+               rows_max, eps, timeout_word);
     count_launch();
     check_launch("tp_allreduce_add_norm");
 }

@@ -34,6 +34,15 @@ class LlamaConfig:
         return cls(**kw)
 
 
+def padded_vocab(vocab: int, world: int) -> int:
+    """pad_vocab_size (/root/reference/src/openai/distributed.rs:1448-1454); identity at world 1."""
+    if world == 1:
+        return vocab
+    padded = -(-vocab // 64) * 64
+    per_rank = -(-padded // world) * world
+    return -(-per_rank // 64) * 64
+
+
 class _CCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("hidden", "num_layers", "num_heads", "num_kv_heads", "head_dim", "ffn", "vocab",
                                           "block_size", "max_num_seqs", "max_blocks_per_seq", "max_pos")] + \
@@ -55,9 +64,12 @@ class GGUFLLaMa:
                  nccl_comm: Optional[int] = None):
         require_device()
         self.cfg, self.weights, self.kv_cache = cfg, weights, kv_cache
-        self.stream = stream or torch.cuda.Stream()
+        # Default = torch's current stream: every other op of this package (CacheEngine swap / copy, PagedAttention prefill,
+        # the weight and KV uploads) is issued there, so a private stream would race them (decode reading blocks a swap-in
+        # is still writing).  A caller that passes its own stream owns the ordering against those ops.
+        self.stream = stream or torch.cuda.current_stream()
         self.tp_world = tp_world
-        self.vocab_local = cfg.vocab // tp_world
+        self.vocab_local = padded_vocab(cfg.vocab, tp_world) // tp_world
         c = _CCfg(cfg.hidden, cfg.num_layers, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.ffn, cfg.vocab,
                   cfg.block_size, cfg.max_num_seqs, cfg.max_blocks_per_seq, cfg.max_pos, cfg.rms_eps, cfg.rope_theta,
                   kv_dtype, tp_rank, tp_world, 1 if use_graph else 0)
@@ -94,7 +106,8 @@ class GGUFLLaMa:
 
     def decode(self, prep: dict, want_logits: bool = False):
         """One decode step from HOST metadata (``inputs.prepare_decode`` output).  Returns
-        (next_tokens i32[B] numpy, logits f32 [B, vocab_local] numpy or None)."""
+        (next_tokens i32[B] numpy, logits f32 [B, vocab] numpy or None); with tp_world > 1 the logits are the gathered full
+        vocabulary (a collective: every rank passes want_logits in the same step)."""
         B = len(prep["tokens"])
         tokens = np.ascontiguousarray(prep["tokens"], np.uint32)
         pos = np.ascontiguousarray(prep["positions"], np.int64)
@@ -102,7 +115,7 @@ class GGUFLLaMa:
         ctx = np.ascontiguousarray(prep["context_lens"]).astype(np.uint32)
         bt = np.ascontiguousarray(prep["block_tables"]).astype(np.uint32)
         nxt = np.empty(B, np.int32)
-        logits = np.empty((B, self.vocab_local), np.float32) if want_logits else None
+        logits = np.empty((B, self.cfg.vocab), np.float32) if want_logits else None
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         lib().b200_llama_decode(self._h, p(tokens), p(pos), p(slots), p(ctx), p(bt), C.c_int32(bt.shape[1]), C.c_int32(B),
                                 p(nxt), p(logits) if want_logits else C.c_void_p(0), C.c_int64(self.stream.cuda_stream))
@@ -115,6 +128,11 @@ class GGUFLLaMa:
                                          C.c_int64(self.stream.cuda_stream))
         check("b200_llama_decode_resident")
 
+    def linear_chain(self, num_seqs: int) -> None:
+        """Measurement aid (``b200_llama_linear_chain``): every projection of the model without the attention / KV stream."""
+        lib().b200_llama_linear_chain(self._h, C.c_int32(num_seqs), C.c_int64(self.stream.cuda_stream))
+        check("b200_llama_linear_chain")
+
     def read_next_tokens(self, n: int) -> np.ndarray:
         out = np.empty(n, np.int32)
         lib().b200_llama_read_next_tokens(self._h, out.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_int64(self.stream.cuda_stream))
@@ -122,7 +140,7 @@ class GGUFLLaMa:
         return out
 
     def read_logits(self, n: int) -> np.ndarray:
-        out = np.empty((n, self.vocab_local), np.float32)
+        out = np.empty((n, self.cfg.vocab), np.float32)
         lib().b200_llama_read_logits(self._h, out.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_int64(self.stream.cuda_stream))
         check("b200_llama_read_logits")
         return out

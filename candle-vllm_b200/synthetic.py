@@ -51,6 +51,16 @@ def shard_rows(w: QTensor, rank: int, world: int) -> QTensor:
     return QTensor(rows[rank * nl:(rank + 1) * nl].contiguous().reshape(-1), w.ggml_type, (nl, k), allow_cpu=True)
 
 
+def pad_rows(w: QTensor, n_pad: int) -> QTensor:
+    """append all-zero GGML blocks (d = 0 -> weights 0) so that the tensor has n_pad rows."""
+    n, k = w.shape
+    if n_pad == n:
+        return w
+    be, bb = GgmlType.BLOCK[w.ggml_type]
+    extra = torch.zeros((n_pad - n) * (k // be) * bb, dtype=torch.uint8, device=w.data.device)
+    return QTensor(torch.cat([w.data, extra]), w.ggml_type, (n_pad, k), allow_cpu=True)
+
+
 def shard_cols(w: QTensor, rank: int, world: int) -> QTensor:
     """row-parallel: split dim 1 along whole blocks (raw-byte shard, quantized_var_builder.rs:234-269)."""
     n, k = w.shape
@@ -73,8 +83,13 @@ def make_weights(cfg: LlamaConfig, device="cuda", seed: int = 0, tp_rank: int = 
     qd, kd = cfg.num_heads * hd, cfg.num_kv_heads * hd
     col = (lambda w: shard_rows(w, tp_rank, tp_world)) if tp_world > 1 else (lambda w: w)
     row = (lambda w: shard_cols(w, tp_rank, tp_world)) if tp_world > 1 else (lambda w: w)
+    kcol = col
     if tp_world > 1 and cfg.num_kv_heads < tp_world:
-        raise ValueError("kv-head replication (kvh < world) not wired in the synthetic generator")
+        # kv_head_shard with fewer kv heads than ranks (/root/reference/src/openai/distributed.rs:753-764): every rank holds ONE
+        # kv head, replicated over world / kvh consecutive ranks
+        if tp_world % cfg.num_kv_heads:
+            raise ValueError(f"world {tp_world} not a multiple of {cfg.num_kv_heads} kv heads")
+        kcol = lambda w: shard_rows(w, tp_rank * cfg.num_kv_heads // tp_world, cfg.num_kv_heads)
     w = dict(tok_embeddings=torch.randn((cfg.vocab, H), device=device, generator=gen, dtype=torch.float32),
              norm=torch.rand(H, device=device, generator=gen) + 0.5, layers=[])
     for _ in range(cfg.num_layers):
@@ -82,28 +97,45 @@ def make_weights(cfg: LlamaConfig, device="cuda", seed: int = 0, tp_rank: int = 
             attn_norm=torch.rand(H, device=device, generator=gen) + 0.5,
             ffn_norm=torch.rand(H, device=device, generator=gen) + 0.5,
             wq=col(random_qtensor(gen, linear_type, qd, H, device)),
-            wk=col(random_qtensor(gen, linear_type, kd, H, device)),
-            wv=col(random_qtensor(gen, linear_type, kd, H, device)),
+            wk=kcol(random_qtensor(gen, linear_type, kd, H, device)),
+            wv=kcol(random_qtensor(gen, linear_type, kd, H, device)),
             wo=row(random_qtensor(gen, linear_type, H, qd, device)),
             w1=col(random_qtensor(gen, linear_type, cfg.ffn, H, device)),
             w2=row(random_qtensor(gen, linear_type, H, cfg.ffn, device)),
             w3=col(random_qtensor(gen, linear_type, cfg.ffn, H, device)),
         ))
-    w["output"] = col(random_qtensor(gen, output_type, cfg.vocab, H, device))
+    out = random_qtensor(gen, output_type, cfg.vocab, H, device)
+    if tp_world > 1:
+        # vocab-parallel lm_head: rows padded with zero blocks to pad_vocab_size (distributed.rs:1448-1454), then split
+        from .llama import padded_vocab
+        out = shard_rows(pad_rows(out, padded_vocab(cfg.vocab, tp_world)), tp_rank, tp_world)
+    w["output"] = out
     return w
 
 
-def fill_kv_cache(kv_cache, seed: int = 1) -> None:
-    """KV contents N(0,1) in the cache dtype (bf16, or e4m3 bits for u8 caches)."""
-    gen = torch.Generator(device=kv_cache[0][0].device)
+def fill_kv_cache(kv_cache, seed: int = 1, tp_rank: int = 0, tp_world: int = 1, num_kv_heads: int = 0) -> None:
+    """KV contents N(0,1) in the cache dtype (bf16, or e4m3 bits for u8 caches).  With tp_world > 1 (and the model's total
+    ``num_kv_heads``) every rank draws the FULL layer [nb, bs, kvh, hd] from the same seeded stream and keeps its own kv heads
+    (kv_head_shard: a slice, or one replicated head when kvh < world), so the sharded caches are exactly the shards of the
+    tp_world = 1 cache -- which is what lets bench.py compare a TP run with a TP = 1 run of the same seed."""
+    dev = kv_cache[0][0].device
+    gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
     for k, v in kv_cache:
         for t in (k, v):
+            if tp_world > 1 and num_kv_heads > 0:
+                nb, bs, kl, hd = t.shape
+                full = torch.randn((nb, bs, num_kv_heads, hd), device=dev, generator=gen, dtype=torch.float32)
+                h0 = tp_rank * kl if num_kv_heads >= tp_world else tp_rank * num_kv_heads // tp_world
+                r = full[:, :, h0:h0 + kl, :]
+                del full
+            else:
+                r = torch.randn(t.shape, device=dev, generator=gen, dtype=torch.float32)
             if t.dtype == torch.uint8:
-                r = torch.randn(t.shape, device=t.device, generator=gen, dtype=torch.float32)
                 t.copy_(r.to(torch.float8_e4m3fn).view(torch.uint8))
             else:
-                t.normal_(0.0, 1.0, generator=gen)
+                t.copy_(r)
+            del r
 
 
 def random_block_tables(num_seqs: int, blocks_per_seq: int, num_blocks: int, seed: int = 2):

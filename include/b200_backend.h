@@ -151,9 +151,10 @@ void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggm
  *   private int4 layout (the reference reshapes the result to [K/16, 2n], gptq.rs:283-297; only marlin_4bit_* reads it).
  * marlin_4bit_{f16,bf16}: out[m,n] = x[m,k] . ((q - 8) * scale)^T; scales [k/group, n] in the order produced by the
  *   reference's marlin_permute_scales (/root/reference/src/openai/models/linear.rs:354-379); qzeros ignored (symmetric),
- *   g_idx must be NULL; group_size 64 / 128 / -1; k % 256 == 0; n % 64 == 0; any m (64 rows per tensor-core pass).  `workspace` (n zeroed u32 of
- *   locks in Marlin) is unused.  The fp16 copy of x lives in a library-owned scratch buffer, grown outside stream
- *   capture or handed over once with b200_set_scratch().
+ *   g_idx is accepted and NOT read (the reference passes the checkpoint's trivial k / group_size sequence on this path, linear.rs:298-337;
+ *   act-order goes to gemm_half_q_half_alt); group_size 64 / 128 / -1; k % 256 == 0; n % 64 == 0; any m (64 rows per tensor-core pass).  `workspace` (n zeroed u32 of
+ *   locks in Marlin) is unused.  The fp16 copy of x lives in a library-owned scratch buffer per (device, stream), grown outside
+ *   stream capture, or in the per-device buffer handed over with b200_set_scratch().
  * awq_repack: AWQ qweight u32 [k, n_packed = N/8] (nibble i of a word = column 8j + [0,2,4,6,1,3,5,7][i]) -> the same private layout.
  * marlin_awq_4bit_{f16,bf16}: as marlin_4bit_* with zero points: out = x . ((q - z) * scale)^T; qzeros u32 [k/group, n/8] in the
  *   layout the reference's offline converter writes (examples/convert_awq_marlin.py:75-113: scale_perm inside 64-column blocks,
@@ -260,7 +261,9 @@ void b200_llama_set_comm(b200_llama* m, void* nccl_comm);
  * uses NCCL on the communicator of b200_llama_set_comm.  count = 0 switches back. */
 size_t b200_llama_peer_inbox_bytes(const b200_llama* m);
 void b200_llama_set_peer_inboxes(b200_llama* m, void* const* inboxes, int32_t count);
-/* 1 when a row of the fused all-reduce gave up waiting for a peer (~4 s: a rank died); its outputs are NaN from then on */
+/* 1 when a row of the fused all-reduce gave up waiting for a peer (B200_TP_TIMEOUT_MS, default 120 s: a rank died).  The flag is a
+ * host-mapped word: b200_llama_decode / read_next_tokens / read_logits check it after their stream sync and record an error
+ * (b200_last_error) instead of handing back the poisoned step's tokens. */
 int32_t b200_llama_peer_timeouts(b200_llama* m);
 void* b200_ipc_alloc(size_t bytes, void* handle_out_64_bytes);
 void* b200_ipc_open(const void* handle_64_bytes);
@@ -271,7 +274,11 @@ void b200_ipc_free(void* allocated);
  * block_tables u32[B, table_width].  Copies them into the static device buffers (async, pinned
  * staging), replays the graph, and (if next_tokens_host != NULL) returns greedy argmax token ids
  * after synchronising the stream, like GraphCapturer::replay (graph.rs:297-301).
- * logits_host (optional): f32 [B, vocab] copied back. */
+ * logits_host (optional): f32 [B, vocab] copied back -- the FULL vocabulary at any tp_world: vocab-parallel shards are all-gathered,
+ * transposed and narrowed like VocabParallelLinear::forward (distributed.rs:1632-1667), so with tp_world > 1 asking for logits is a
+ * collective (every rank asks in the same step).  Vocab-parallel lm_head: each rank holds pad_vocab_size(vocab, world) / world rows
+ * (distributed.rs:1448-1454; rows past `vocab` are zero padding supplied by the caller and are never sampled).
+ * context_lens[b] must fit the table (<= table_width * block_size) and slot_mapping[b] the cache; violations are argument errors. */
 void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* positions,
                        const int64_t* slot_mapping, const uint32_t* context_lens,
                        const uint32_t* block_tables, int32_t table_width, int32_t num_seqs,
@@ -279,10 +286,15 @@ void b200_llama_decode(b200_llama* m, const uint32_t* tokens, const int64_t* pos
 /* Device-resident variant: metadata already in the static buffers; advance positions/slots on the
  * device (fixed block tables) and replay.  Used for the HBM-resident `value` measurement. */
 void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance, int64_t stream);
-const float* b200_llama_logits(b200_llama* m);        /* device f32 [max_num_seqs, vocab_local] */
+/* Measurement aid: one forward WITHOUT RoPE / cache write / attention, eagerly on `stream` -- every quantised projection of every
+ * layer, the lm_head and the small ops between them (bench.py's roofline_gemm times the weight stream with it).  Leaves the
+ * activations of the static buffers meaningless; never call it between decode steps whose results matter. */
+void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream);
+const float* b200_llama_logits(b200_llama* m);        /* device f32 [max_num_seqs, vocab_local]: this rank's shard */
 const int32_t* b200_llama_next_tokens(b200_llama* m); /* device i32 [max_num_seqs] */
 int64_t b200_llama_kernel_launches(b200_llama* m);    /* kernels launched by this model so far */
-/* copy the last step's greedy tokens (i32[n]) / logits (f32 [n, vocab_local]) to the host; syncs the stream */
+/* copy the last step's greedy tokens (i32[n]) / full-vocabulary logits (f32 [n, vocab]; a collective when tp_world > 1) to the host;
+ * syncs the stream */
 void b200_llama_read_next_tokens(b200_llama* m, int32_t* host, int32_t n, int64_t stream);
 void b200_llama_read_logits(b200_llama* m, float* host, int32_t n, int64_t stream);
 

@@ -61,6 +61,27 @@ def test_marlin_matmul_matches_oracle(dtype, m, k, n, g):
     assert rel < (4e-3 if dtype == torch.bfloat16 else 1e-3), rel
 
 
+@pytest.mark.gpu
+def test_marlin_matmul_with_checkpoint_g_idx_and_qzeros_like_the_reference_call_site():
+    """The reference hands the checkpoint's g_idx (trivial k // group_size when desc_act = false, linear.rs:298-337) and qzeros to
+    marlin_4bit_* for every quant_method == "gptq" layer (gptq.rs:27-35,139-152): the result must be the same as without them."""
+    rng = np.random.default_rng(11)
+    m, k, n, g = 9, 1024, 256, 128
+    q = rng.integers(0, 16, (k, n), dtype=np.uint8)
+    st = torch.from_numpy(rng.uniform(0.005, 0.02, (k // g, n)).astype(np.float32)).cuda().half()
+    xt = torch.from_numpy(rng.standard_normal((m, k)).astype(np.float32)).cuda().half()
+    w_m = pkg.marlin_weight_repack(torch.from_numpy(OG.pack_gptq(q).view(np.int32)).cuda(), 4, False)
+    s_m = pkg.marlin_permute_scales(st, k, n, g)
+    ws = torch.zeros(n, dtype=torch.int32, device="cuda")
+    g_idx = torch.arange(k, dtype=torch.int32, device="cuda") // g
+    qzeros = torch.full((k // g, n // 8), 0x77777777, dtype=torch.int32, device="cuda")      # GPTQ v1 symmetric: zero - 1 = 7
+    y0 = pkg.gptq_matmul(xt, w_m, s_m, None, None, ws, 4, g)
+    y1 = pkg.gptq_matmul(xt, w_m, s_m, qzeros, g_idx, ws, 4, g)
+    assert torch.equal(y0, y1)
+    ref = OG.gptq_matmul(xt.float().cpu().numpy(), OG.pack_gptq(q), st.float().cpu().numpy(), g)
+    assert np.linalg.norm(y1.float().cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-3
+
+
 def test_awq_zero_point_layout_matches_reference_converter():
     """oracle restatement of examples/convert_awq_marlin.py:75-113 against vectors produced by EXECUTING that script
     (tests/golden/make_golden.py: awq_zero_points), plus pack / unpack round trips."""

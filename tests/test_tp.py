@@ -81,8 +81,10 @@ def _nccl_worker(rank, world, port, out):
     try:
         from candle_vllm_b200.distributed import Comm
         comm = Comm(rank, world)
-        cfg = pkg.LlamaConfig(hidden=512, num_layers=2, num_heads=8, num_kv_heads=4, head_dim=128, ffn=1024, vocab=768,
-                              max_pos=512, block_size=64, max_num_seqs=8, max_blocks_per_seq=8)
+        # world 8: 16 q heads over 4 kv heads -> kv heads replicated over pairs of ranks (kv_head_shard), ffn 2048 keeps K / world a
+        # multiple of 256; vocab 776 is NOT a multiple of 64 * world: the lm_head is padded (pad_vocab_size) and the pad never sampled
+        cfg = pkg.LlamaConfig(hidden=512, num_layers=2, num_heads=16 if world == 8 else 8, num_kv_heads=4, head_dim=128,
+                              ffn=2048 if world == 8 else 1024, vocab=776, max_pos=512, block_size=64, max_num_seqs=8, max_blocks_per_seq=8)
         nb = 24
         tables = synthetic.random_block_tables(4, 4, nb, seed=2)
         lens, toks = [10, 64, 65, 200], [5, 9, 700, 33]
@@ -100,20 +102,27 @@ def _nccl_worker(rank, world, port, out):
                 from candle_vllm_b200.distributed import PeerInboxes
                 inbox = PeerInboxes(model, tp_rank, tp_world)
                 assert inbox.active
-            outs, L, T = [], [1, 1, 1, 1], list(toks)
-            for _ in range(12 if peer else 6):                  # decode from an empty cache: context grows 1..
-                nxt, _ = model.decode(pkg.prepare_decode(L, T, tables, cfg.block_size))
+            outs, L, T, lg = [], [1, 1, 1, 1], list(toks), None
+            for i in range(12 if peer else 6):                  # decode from an empty cache: context grows 1..
+                nxt, lg_i = model.decode(pkg.prepare_decode(L, T, tables, cfg.block_size), want_logits=(i == 5))
+                lg = lg_i if lg_i is not None else lg
                 outs.append(nxt.copy()); T = [int(t) for t in nxt]; L = [x + 1 for x in L]
             if inbox is not None:
+                assert not inbox.timed_out()
                 inbox.close()
-            return np.stack(outs)
+            return np.stack(outs), lg
 
-        tp = run(rank, world, comm.handle.value)
-        tp_peer = run(rank, world, comm.handle.value, peer=True)
+        tp, tp_lg = run(rank, world, comm.handle.value)
+        tp_peer, peer_lg = run(rank, world, comm.handle.value, peer=True)
         if rank == 0:
-            ref = run(0, 1, None)
-            # NCCL path; peer-memory path (its first 6 steps are the same decode, then 6 more graph replays: epochs, parity)
-            out.put(bool(np.array_equal(tp, ref)) and bool(np.array_equal(tp_peer[:6], ref)))
+            ref, ref_lg = run(0, 1, None)
+            # NCCL path; peer-memory path (its first 6 steps are the same decode, then 6 more graph replays: epochs, parity);
+            # gathered full-vocabulary logits (VocabParallelLinear + AllGather, distributed.rs:1632-1667) against TP = 1
+            ok = bool(np.array_equal(tp, ref)) and bool(np.array_equal(tp_peer[:6], ref))
+            scale = float(np.abs(ref_lg).max())
+            ok = ok and tp_lg.shape == ref_lg.shape == (4, cfg.vocab)
+            ok = ok and float(np.abs(tp_lg - ref_lg).max()) / scale < 1e-3 and float(np.abs(peer_lg - ref_lg).max()) / scale < 1e-3
+            out.put(ok)
         dist.barrier()
         comm.destroy()
     finally:
@@ -121,7 +130,7 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_tp_decode_matches_tp1(world):
     """NCCL all-reduce path and the fused peer-memory all-reduce (CUDA IPC inboxes) against the unsharded model: same greedy
     tokens.  world = 4 also exercises rows owned by ranks that hold no sequence (4 sequences, owners r % 4) and epoch parity."""
