@@ -8,6 +8,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "mega.cuh"
 
 namespace b200 {
 
@@ -189,8 +190,19 @@ __device__ __forceinline__ void zero16(float* p) {
 }
 
 // one work item = (token t, head slot hs, unit u): callable from the stand-alone kernel below and from the fused layer kernel
+// 16 consecutive f32 of row `p` summed over the slabs of their tile (layer_mega.cu: split-K partial sums, added in slab order)
+__device__ __forceinline__ void load16_slabs(const float* p, int64_t slab_stride, int slabs, float (&v)[16]) {
+    load16(p, v);
+    for (int s = 1; s < slabs; ++s) {
+        float t[16];
+        load16(p + (int64_t)s * slab_stride, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += t[i];
+    }
+}
+
 template <typename T16, bool kFp8, bool kZeroSrc>
-__device__ __forceinline__ void rope_cache_item(int item, float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
+__device__ __forceinline__ void rope_cache_item(int item, const SlabInfo& si, float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
                                                 const float* __restrict__ cos_t, const float* __restrict__ sin_t, const int64_t* __restrict__ positions,
                                                 const int64_t* __restrict__ slot_mapping, int num_heads, int num_kv_heads, int head_dim, int interleaved) {
     const int units = head_dim >> 5, slots_per_tok = num_heads + 2 * num_kv_heads;
@@ -203,8 +215,18 @@ __device__ __forceinline__ void rope_cache_item(int item, float* __restrict__ qk
     const bool rot = hs < num_heads + num_kv_heads;
     const int a0 = (rot && !interleaved) ? 16 * u : 32 * u, b0 = (rot && !interleaved) ? half + 16 * u : 32 * u + 16;
     float a[16], b[16];
-    load16(src + a0, a);
-    load16(src + b0, b);
+    if (si.slab_stride == 0) {
+        load16(src + a0, a);
+        load16(src + b0, b);
+    } else {
+        // which 128-row tile of the fused QKV GEMM these columns belong to -> how many CTAs split it -> that many slabs
+        const int sg = hs < num_heads ? 0 : (hs < num_heads + num_kv_heads ? 1 : 2);
+        const int hl = hs - (sg == 0 ? 0 : (sg == 1 ? num_heads : num_heads + num_kv_heads));
+        const uint32_t total = (uint32_t)si.n_tiles * (uint32_t)si.nsb;
+        const uint32_t ta = (uint32_t)(si.seg_tile0[sg] + (hl * head_dim + a0) / 128), tb = (uint32_t)(si.seg_tile0[sg] + (hl * head_dim + b0) / 128);
+        load16_slabs(src + a0, si.slab_stride, tile_slabs(ta, (uint32_t)si.nsb, total, (uint32_t)si.grid), a);
+        load16_slabs(src + b0, si.slab_stride, tile_slabs(tb, (uint32_t)si.nsb, total, (uint32_t)si.grid), b);
+    }
     if (rot) {
         float c[16], sn[16];
         load16(cos_t + pos * half + 16 * u, c);
@@ -240,7 +262,7 @@ __device__ __forceinline__ void rope_cache_item(int item, float* __restrict__ qk
 
 template <typename T16, bool kFp8, bool kZeroSrc>
 __global__ void __launch_bounds__(128)
-rope_and_cache_vec_kernel(float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
+rope_and_cache_vec_kernel(const SlabInfo si, float* __restrict__ qkv, T16* __restrict__ q_out, void* __restrict__ kc_, void* __restrict__ vc_,
                           const float* __restrict__ cos_t, const float* __restrict__ sin_t, const int64_t* __restrict__ positions,
                           const int64_t* __restrict__ slot_mapping, int num_tokens, int num_heads, int num_kv_heads, int head_dim, int interleaved) {
     pdl_wait();
@@ -248,7 +270,7 @@ rope_and_cache_vec_kernel(float* __restrict__ qkv, T16* __restrict__ q_out, void
     const int items = num_tokens * (num_heads + 2 * num_kv_heads) * (head_dim >> 5);
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (item < items)
-        rope_cache_item<T16, kFp8, kZeroSrc>(item, qkv, q_out, kc_, vc_, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved);
+        rope_cache_item<T16, kFp8, kZeroSrc>(item, si, qkv, q_out, kc_, vc_, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved);
 }
 
 template <typename TOut, bool kK4 = false, bool kZeroSrc = false>
@@ -448,7 +470,7 @@ void fused_rope_f32(float* q, float* k, const float* cos_t, const float* sin_t, 
 }  // extern "C"
 
 namespace b200 {
-void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_cache,
+static void rope_and_cache_any(float* qkv, const SlabInfo& si, void* q_out, void* key_cache, void* value_cache,
                     const float* cos_t, const float* sin_t, const int64_t* positions,
                     const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads,
                     int32_t num_kv_heads, int32_t head_dim, int32_t interleaved,
@@ -459,9 +481,10 @@ void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_c
     B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "rope_and_cache: cache dtype %d vs dtype %d", cache_dtype, dtype);
     cudaStream_t st = as_stream(stream);
     // 16-byte loads / stores need 16-byte aligned rows: head_dim % 32 == 0 and aligned bases (cudaMalloc gives 256)
+    B200_REQUIRE(si.slab_stride == 0 || head_dim % 32 == 0, kErrUnsupported, "rope_and_cache: slab input needs head_dim %% 32 == 0");
     const bool vec = head_dim % 32 == 0 && ((((uintptr_t)qkv | (uintptr_t)q_out | (uintptr_t)key_cache | (uintptr_t)value_cache | (uintptr_t)cos_t | (uintptr_t)sin_t) & 15) == 0);
     const int items = num_tokens * (num_heads + 2 * num_kv_heads) * (head_dim >> 5);
-#define LAUNCH(T16, F8, Z) do { if (vec) launch_pdl(rope_and_cache_vec_kernel<T16, F8, Z>, dim3(ceil_div(items, 128)), dim3(128), 0, st, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, (int)num_tokens, (int)num_heads, (int)num_kv_heads, (int)head_dim, (int)interleaved); \
+#define LAUNCH(T16, F8, Z) do { if (vec) launch_pdl(rope_and_cache_vec_kernel<T16, F8, Z>, dim3(ceil_div(items, 128)), dim3(128), 0, st, si, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, (int)num_tokens, (int)num_heads, (int)num_kv_heads, (int)head_dim, (int)interleaved); \
         else launch_pdl(rope_and_cache_kernel<T16, F8, Z>, dim3(num_tokens, num_heads + 2 * num_kv_heads), dim3(64), 0, st, qkv, (T16*)q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_heads, num_kv_heads, head_dim, interleaved); } while (0)
 #define LAUNCH2(T16, F8) do { if (zero_src) LAUNCH(T16, F8, true); else LAUNCH(T16, F8, false); } while (0)
     if (dtype == B200_BF16) { if (fp8) LAUNCH2(__nv_bfloat16, true); else LAUNCH2(__nv_bfloat16, false); }
@@ -471,6 +494,21 @@ void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_c
 #undef LAUNCH
     count_launch();
     check_launch("rope_and_cache");
+}
+
+void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_cache, const float* cos_t, const float* sin_t,
+                         const int64_t* positions, const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads, int32_t num_kv_heads,
+                         int32_t head_dim, int32_t interleaved, int32_t dtype, int32_t cache_dtype, bool zero_src, int64_t stream) {
+    SlabInfo si{};
+    rope_and_cache_any(qkv, si, q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_tokens, num_heads, num_kv_heads, head_dim,
+                       interleaved, dtype, cache_dtype, zero_src, stream);
+}
+// the packed QKV row arrives as split-K slabs of the persistent layer kernel (nothing to re-zero)
+void rope_and_cache_slabs(float* qkv, const SlabInfo& si, void* q_out, void* key_cache, void* value_cache, const float* cos_t, const float* sin_t,
+                          const int64_t* positions, const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads, int32_t num_kv_heads,
+                          int32_t head_dim, int32_t interleaved, int32_t dtype, int32_t cache_dtype, int64_t stream) {
+    rope_and_cache_any(qkv, si, q_out, key_cache, value_cache, cos_t, sin_t, positions, slot_mapping, num_tokens, num_heads, num_kv_heads, head_dim,
+                       interleaved, dtype, cache_dtype, false, stream);
 }
 
 void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, int64_t stream) {

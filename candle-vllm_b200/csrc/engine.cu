@@ -16,10 +16,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <vector>
 
 #include "attention.cuh"
+#include "mega.cuh"
 #include "qmatmul.cuh"
 
 using namespace b200;
@@ -32,6 +34,9 @@ size_t tp_peer_inbox_bytes(int world, int rows_max, int n);
 void tp_set_timeout_ms(long long ms);
 void tp_allreduce_add_norm(float* partial, float* x, const float* norm_w, void* xn_f16_k4, void* const* peers, int rank, int world,
                            int rows, int n, int rows_max, float eps, uint32_t* timeout_word, cudaStream_t st);
+void rope_and_cache_slabs(float* qkv, const SlabInfo& si, void* q_out, void* key_cache, void* value_cache, const float* cos_t, const float* sin_t,
+                          const int64_t* positions, const int64_t* slot_mapping, int32_t num_tokens, int32_t num_heads, int32_t num_kv_heads,
+                          int32_t head_dim, int32_t interleaved, int32_t dtype, int32_t cache_dtype, int64_t stream);
 void gather_logits_transpose(const float* gathered, float* out, int world, int rows, int vocab_l, int vocab, cudaStream_t st);
 void argmax_pairs(const float* logits, void* pairs, int rows, int ld, int n, int chunks, int index_offset, cudaStream_t st);
 void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world, cudaStream_t st);
@@ -74,6 +79,13 @@ struct b200_llama {
     // vocab-parallel lm_head (distributed.rs:1448-1454): vocab padded to 64 and split; gathered logits on request
     int vocab_pad = 0;
     float* logits_gathered = nullptr; float* logits_full = nullptr;
+
+    // persistent layer kernel (layer_mega.cu): per-tile partial-sum slabs of the GEMM phases and the grid-wide counters
+    bool use_mega = false;
+    long long tp_timeout_ms = 120000;
+    int mega_G = 0, s_qkv = 1, s_ro = 1, s_gu = 1;                // slabs per buffer (max CTAs sharing one tile)
+    float* qkv_slabs = nullptr; float* ro_slabs = nullptr; float* gate_slabs = nullptr; float* up_slabs = nullptr;
+    uint32_t* mega_counters = nullptr; size_t mega_counter_bytes = 0;
 
     std::map<int, cudaGraphExec_t> graphs;       // batch size -> captured step
     std::map<int, int> launches_per_step;
@@ -118,9 +130,134 @@ __global__ void zero_f32_kernel(float* p, int64_t n) {
 }
 
 // One decode forward on `st` for B sequences.  Returns number of kernel launches issued.
+// ---- forward on the persistent layer kernel (layer_mega.cu) --------------------------------------------------------------------
+// Per layer: {RoPE + cache write, attention, merge, ONE launch for wo -> +x, norm -> gate|up -> SiLU -> w2 -> +x, norm -> QKV of the
+// next layer}.  Split-K partial sums travel in slabs and are added in slab order by their consumer: bitwise reproducible.
+bool mega_usable(const b200_llama* m, int B) {
+    const b200_llama_config& c = m->cfg;
+    if (!m->use_mega || !m->qkv_slabs) return false;
+    if (c.tp_world > 1 && (int)m->peers.size() != c.tp_world) return false;          // NCCL all-reduce: legacy launches
+    if (!mega_supported(B, c.hidden, std::max(c.hidden, m->ffn_l))) return false;
+    if ((m->heads_l * c.head_dim) % 256 || m->ffn_l % 256 || c.head_dim % 32) return false;
+    for (const auto& w : m->layers)
+        for (int t : {w.tq, w.tk, w.tv, w.to, w.t1, w.t2, w.t3})
+            if (t != B200_GGML_Q4_K) return false;
+    return true;
+}
+
+int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
+    const b200_llama_config& c = m->cfg;
+    const int64_t s = reinterpret_cast<int64_t>(st);
+    const int H = c.hidden, hd = c.head_dim, L = c.num_layers;
+    const int qd = m->heads_l * hd, kd = m->kv_l * hd, F = m->ffn_l;
+    const long long n0 = b200_total_kernel_launches();
+    const int G = m->mega_G;
+    constexpr int kArgmaxChunks = 16;
+    const bool fused_ar = c.tp_world > 1;
+    const int64_t Bm = c.max_num_seqs;
+    auto tiles = [](int n) { return (n + 127) / 128; };
+
+    cudaMemsetAsync(m->mega_counters, 0, m->mega_counter_bytes, st);
+    embedding_f32(m->tok_embeddings, m->d_tokens, m->x, B, H, s);
+    rms_norm(m->x, m->layers[0].attn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+
+    auto base_params = [&](MegaParams& P, int launch) {
+        memset(&P, 0, sizeof(P));
+        P.m = B; P.hidden = H; P.eps = c.rms_eps; P.x = m->x;
+        P.counters = m->mega_counters + (size_t)launch * 2 * kMegaMaxPhases;
+        P.error_word = m->d_timeout + 1;
+        P.tp_rank = c.tp_rank; P.tp_world = c.tp_world; P.rows_max = c.max_num_seqs;
+        P.tp_timeout_ns = (unsigned long long)m->tp_timeout_ms * 1000000ull;
+        P.timeout_word = m->d_timeout;
+        if (fused_ar) for (int i = 0; i < c.tp_world; ++i) P.peers.p[i] = static_cast<char*>(m->peers[i]);
+    };
+    auto qkv_phase = [&](MegaParams& P, MegaPhase& ph, const b200_llama_layer& w, int map0) -> bool {
+        if (!mega_make_w_map(&P.maps[map0], w.wq, qd, H) || !mega_make_w_map(&P.maps[map0 + 1], w.wk, kd, H) ||
+            !mega_make_w_map(&P.maps[map0 + 2], w.wv, kd, H)) return false;
+        ph.w_map[0] = map0; ph.w_map[1] = map0 + 1; ph.w_map[2] = map0 + 2;
+        ph.n[0] = qd; ph.n[1] = kd; ph.n[2] = kd;
+        ph.tile_end[0] = tiles(qd); ph.tile_end[1] = tiles(qd) + tiles(kd); ph.tile_end[2] = tiles(qd) + 2 * tiles(kd);
+        ph.y[0] = m->qkv_slabs; ph.y[1] = m->qkv_slabs + qd; ph.y[2] = m->qkv_slabs + qd + kd;
+        ph.ldy = m->qkv_row; ph.slab_stride = Bm * m->qkv_row;
+        ph.nsb = H / 256; ph.n_tiles = ph.tile_end[2];
+        return true;
+    };
+    SlabInfo qkv_si{};
+    qkv_si.slab_stride = Bm * m->qkv_row; qkv_si.nsb = H / 256; qkv_si.n_tiles = tiles(qd) + 2 * tiles(kd);
+    qkv_si.grid = std::min(G, qkv_si.n_tiles * qkv_si.nsb);                       // effective grid of the QKV phase
+    qkv_si.seg_tile0[0] = 0; qkv_si.seg_tile0[1] = tiles(qd); qkv_si.seg_tile0[2] = tiles(qd) + tiles(kd);
+
+    {   // QKV of layer 0: a one-phase launch (its activations come from the rms_norm above)
+        MegaParams P;
+        base_params(P, 0);
+        if (!mega_make_x_map(&P.maps[0], m->xn, B, H)) return 0;
+        MegaPhase& p0 = P.phase[0];
+        p0.x_map = 0; p0.eop = kEopNone;
+        if (!qkv_phase(P, p0, m->layers[0], 1)) return 0;
+        P.n_phases = 1;
+        mega_launch(P, st);
+    }
+    for (int l = 0; l < L; ++l) {
+        const b200_llama_layer& w = m->layers[l];
+        if (!linear_only) {
+            rope_and_cache_slabs(m->qkv_slabs, qkv_si, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
+                                 m->heads_l, m->kv_l, hd, /*interleaved=*/1, B200_BF16, c.kv_dtype, s);
+            paged_attention_decode(m->attn16, m->q16, m->kc[l], m->vc[l], m->d_tables, m->d_ctx, B, m->heads_l, m->kv_l, hd,
+                                   c.block_size, c.max_blocks_per_seq, m->num_blocks, 1.0f / sqrtf((float)hd), 0.f, 0,
+                                   B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16_K4, m->attn_ws, m->attn_ws_bytes, s);
+        }
+        MegaParams P;
+        base_params(P, l + 1);
+        // maps: 0 attn16 [B, qd], 1 xn [B, H], 2 act16 [B, F], 3 wo, 4 w1, 5 w3, 6 w2, 7..9 q, k, v of the next layer
+        if (!mega_make_x_map(&P.maps[0], m->attn16, B, qd) || !mega_make_x_map(&P.maps[1], m->xn, B, H) ||
+            !mega_make_x_map(&P.maps[2], m->act16, B, F) || !mega_make_w_map(&P.maps[3], w.wo, H, qd) ||
+            !mega_make_w_map(&P.maps[4], w.w1, F, H) || !mega_make_w_map(&P.maps[5], w.w3, F, H) || !mega_make_w_map(&P.maps[6], w.w2, H, F)) return 0;
+        const int norm_op = fused_ar ? kEopTpNorm : kEopNorm;
+        MegaPhase& a = P.phase[0];        // x (+)= wo(attn): partial sums -> ro_slabs
+        a.x_map = 0; a.w_map[0] = a.w_map[1] = a.w_map[2] = 3; a.n[0] = a.n[1] = a.n[2] = H;
+        a.tile_end[0] = tiles(H); a.tile_end[1] = a.tile_end[2] = 0x7fffffff;
+        a.y[0] = a.y[1] = a.y[2] = m->ro_slabs; a.ldy = H; a.slab_stride = Bm * H; a.nsb = qd / 256; a.n_tiles = tiles(H); a.eop = kEopNone;
+        MegaPhase& b = P.phase[1];        // gate | up on xn = norm(x + wo partials)
+        b.x_map = 1; b.w_map[0] = 4; b.w_map[1] = b.w_map[2] = 5; b.n[0] = b.n[1] = b.n[2] = F;
+        b.tile_end[0] = tiles(F); b.tile_end[1] = 2 * tiles(F); b.tile_end[2] = 0x7fffffff;
+        b.y[0] = m->gate_slabs; b.y[1] = b.y[2] = m->up_slabs; b.ldy = F; b.slab_stride = Bm * F; b.nsb = H / 256; b.n_tiles = 2 * tiles(F);
+        b.eop = norm_op; b.norm_w = w.ffn_norm; b.act_out = m->xn;
+        MegaPhase& d = P.phase[2];        // w2 on act = silu(gate) * up
+        d.x_map = 2; d.w_map[0] = d.w_map[1] = d.w_map[2] = 6; d.n[0] = d.n[1] = d.n[2] = H;
+        d.tile_end[0] = tiles(H); d.tile_end[1] = d.tile_end[2] = 0x7fffffff;
+        d.y[0] = d.y[1] = d.y[2] = m->ro_slabs; d.ldy = H; d.slab_stride = Bm * H; d.nsb = F / 256; d.n_tiles = tiles(H);
+        d.eop = kEopSilu; d.act_out = m->act16;
+        MegaPhase& e = P.phase[3];        // x += w2 partials, next norm; QKV of the next layer (last layer: the final norm only)
+        e.x_map = 1; e.eop = norm_op; e.act_out = m->xn;
+        if (l + 1 < L) {
+            e.norm_w = m->layers[l + 1].attn_norm;
+            if (!qkv_phase(P, e, m->layers[l + 1], 7)) return 0;
+        } else {
+            e.norm_w = m->norm;
+            e.n_tiles = 0; e.nsb = 0; e.tile_end[0] = e.tile_end[1] = e.tile_end[2] = 0x7fffffff;
+        }
+        P.n_phases = 4;
+        mega_launch(P, st);
+    }
+    if (qmatmul_tc_supported(B, m->vocab_l, H, m->output_type) && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) {
+        launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
+    }
+    qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
+    const int live_cols = std::max(0, std::min(m->vocab_l, c.vocab - c.tp_rank * m->vocab_l));
+    argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, live_cols, kArgmaxChunks, c.tp_rank * m->vocab_l, st);
+    if (c.tp_world == 1) {
+        argmax_reduce_pairs(m->tp_pairs, m->next_tokens, B, kArgmaxChunks, st);
+    } else {
+        tp_allgather_bytes(m->comm, m->tp_pairs, m->tp_gathered, (size_t)B * kArgmaxChunks * 8, st);
+        argmax_reduce_pairs(m->tp_gathered, m->next_tokens, B, c.tp_world * kArgmaxChunks, st);
+    }
+    return (int)(b200_total_kernel_launches() - n0);
+}
+
 // linear_only: skip RoPE + cache write + attention (the measurement leg behind bench.py's roofline_gemm: the weight stream
 // of all quantised projections and the small ops between them, without the KV stream)
 int forward(b200_llama* m, int B, cudaStream_t st, bool linear_only = false) {
+    if (mega_usable(m, B)) return forward_mega(m, B, st, linear_only);
     const b200_llama_config& c = m->cfg;
     const int64_t s = reinterpret_cast<int64_t>(st);
     const int H = c.hidden, hd = c.head_dim;
@@ -214,6 +351,10 @@ void invalidate_graphs(b200_llama* m) {
 
 // a row of the fused all-reduce gave up waiting for a peer: the step's outputs are NaN -- report it instead of returning them
 bool peer_timed_out(b200_llama* m, const char* who) {
+    if (m->h_timeout && reinterpret_cast<volatile uint32_t*>(m->h_timeout)[1] != 0u) {
+        set_error(kErrCuda, "%s: a grid-wide wait of the persistent layer kernel gave up (CTAs not co-resident?)", who);
+        return true;
+    }
     if (!m->h_timeout || *reinterpret_cast<volatile uint32_t*>(m->h_timeout) == 0u) return false;
     set_error(kErrCuda, "%s: the fused tensor-parallel all-reduce timed out waiting for a peer rank (B200_TP_TIMEOUT_MS); this step's outputs are invalid", who);
     return true;
@@ -336,11 +477,28 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
          cudaMallocHost((void**)&m->h_next, B * 4) == cudaSuccess &&
          cudaHostAlloc((void**)&m->h_timeout, 64, cudaHostAllocMapped) == cudaSuccess &&
          cudaHostGetDevicePointer((void**)&m->d_timeout, m->h_timeout, 0) == cudaSuccess;
-    if (ok) *m->h_timeout = 0u;
+    if (ok) { m->h_timeout[0] = 0u; m->h_timeout[1] = 0u; }
+    static const long long tmo = [] { const char* e = getenv("B200_TP_TIMEOUT_MS"); return e ? atoll(e) : 120000ll; }();
+    m->tp_timeout_ms = tmo > 0 ? tmo : 1;
     if (ok && c.tp_world > 1) {
         ok = dmalloc(m->logits_gathered, B * (size_t)m->vocab_pad) && dmalloc(m->logits_full, B * (size_t)c.vocab);
-        static const long long tmo = [] { const char* e = getenv("B200_TP_TIMEOUT_MS"); return e ? atoll(e) : 120000ll; }();
-        tp_set_timeout_ms(tmo);
+        tp_set_timeout_ms(m->tp_timeout_ms);
+    }
+    // persistent layer kernel (B200_MEGA=0 keeps the one-launch-per-GEMM path): slab buffers sized for the worst tile split
+    static const int mega_on = [] { const char* e = getenv("B200_MEGA"); return e ? atoi(e) : 1; }();
+    if (ok && mega_on && c.hidden % 256 == 0 && c.hidden <= 8192 && (m->heads_l * c.head_dim) % 256 == 0 && m->ffn_l % 256 == 0) {
+        auto tiles = [](int n) { return (n + 127) / 128; };
+        const int G = mega_grid();
+        const int qd = m->heads_l * c.head_dim, kd = m->kv_l * c.head_dim;
+        m->mega_G = G;
+        m->s_qkv = mega_phase_slabs(tiles(qd) + 2 * tiles(kd), c.hidden / 256, G);
+        m->s_ro = std::max(mega_phase_slabs(tiles(c.hidden), qd / 256, G), mega_phase_slabs(tiles(c.hidden), m->ffn_l / 256, G));
+        m->s_gu = mega_phase_slabs(2 * tiles(m->ffn_l), c.hidden / 256, G);
+        m->mega_counter_bytes = (size_t)(c.num_layers + 1) * 2 * kMegaMaxPhases * sizeof(uint32_t);
+        ok = dmalloc(m->qkv_slabs, (size_t)m->s_qkv * B * m->qkv_row) && dmalloc(m->ro_slabs, (size_t)m->s_ro * B * c.hidden) &&
+             dmalloc(m->gate_slabs, (size_t)m->s_gu * B * m->ffn_l) && dmalloc(m->up_slabs, (size_t)m->s_gu * B * m->ffn_l) &&
+             dmalloc(m->mega_counters, m->mega_counter_bytes / sizeof(uint32_t));
+        m->use_mega = ok;
     }
     if (!ok) {
         if (!b200_last_error()) set_error(kErrCuda, "b200_llama_create: allocation failed");
@@ -362,6 +520,7 @@ void b200_llama_destroy(b200_llama* m) {
     if (m->h_timeout) cudaFreeHost(m->h_timeout);
     if (m->logits_gathered) cudaFree(m->logits_gathered);
     if (m->logits_full) cudaFree(m->logits_full);
+    for (void* p : {(void*)m->qkv_slabs, (void*)m->ro_slabs, (void*)m->gate_slabs, (void*)m->up_slabs, (void*)m->mega_counters}) if (p) cudaFree(p);
     delete m;
 }
 
@@ -498,6 +657,10 @@ void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream) {
     if (!ready(m)) return;
     B200_REQUIRE(num_seqs > 0 && num_seqs <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_linear_chain: bad num_seqs");
     m->launches += forward(m, num_seqs, as_stream(stream), /*linear_only=*/true);
+}
+
+int32_t b200_llama_uses_layer_kernel(b200_llama* m, int32_t num_seqs) {
+    return m && ready(m) && mega_usable(m, num_seqs) ? 1 : 0;
 }
 
 void b200_llama_read_next_tokens(b200_llama* m, int32_t* host, int32_t n, int64_t stream) {

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "mega.cuh"
 
 namespace b200 {
 
@@ -56,7 +57,6 @@ void tp_allreduce_f32(void* comm, float* buf, int64_t n, cudaStream_t st) {
 //     (w-1) for its own rows: 1.35 MB at world 8, B = 32, against 3.6 MB for a one-shot exchange.
 // Buffers are double-buffered by epoch parity: a rank cannot be two all-reduces ahead of a peer because each one needs that
 // peer's words.  One CTA per row; every CTA of a launch is resident (rows <= 148).
-struct PeerSet { char* p[8]; };
 
 __device__ __forceinline__ void st_ll(void* addr, uint32_t a, uint32_t b, uint32_t e) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(e), "r"(b), "r"(e) : "memory");
@@ -88,18 +88,7 @@ __device__ __forceinline__ bool ll_wait(const void* addr, uint32_t e, uint4& w, 
     }
 }
 
-struct InboxLayout {
-    size_t gather_bytes, bcast_off, epoch_off, total;
-    int rows_owned;
-    __host__ __device__ InboxLayout(int world, int rows_max, int n) {
-        rows_owned = (rows_max + world - 1) / world;
-        gather_bytes = (size_t)2 * world * rows_owned * n * 8;              // [par][src][owned row][n] x {f32, epoch}
-        bcast_off = (gather_bytes + 255) & ~(size_t)255;
-        const size_t bcast_bytes = (size_t)2 * rows_max * (n / 2) * 8;       // [par][row][n/2] x {half2, epoch}
-        epoch_off = (bcast_off + bcast_bytes + 255) & ~(size_t)255;
-        total = epoch_off + (((size_t)rows_max * 4 + 4 + 255) & ~(size_t)255);        // epochs (+ one spare word)
-    }
-};
+using InboxLayout = TpInboxLayout;
 
 __global__ void __launch_bounds__(256)
 tp_allreduce_add_norm_kernel(float* __restrict__ partial, float* __restrict__ x, const float* __restrict__ norm_w, __half* __restrict__ xn,

@@ -128,6 +128,10 @@ class GGUFLLaMa:
                                          C.c_int64(self.stream.cuda_stream))
         check("b200_llama_decode_resident")
 
+    def uses_layer_kernel(self, num_seqs: int) -> bool:
+        """True when decode steps of this batch size run on the persistent layer kernel (deterministic split-K reduction)."""
+        return bool(lib().b200_llama_uses_layer_kernel(self._h, C.c_int32(num_seqs)))
+
     def linear_chain(self, num_seqs: int) -> None:
         """Measurement aid (``b200_llama_linear_chain``): every projection of the model without the attention / KV stream."""
         lib().b200_llama_linear_chain(self._h, C.c_int32(num_seqs), C.c_int64(self.stream.cuda_stream))

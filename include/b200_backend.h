@@ -290,6 +290,10 @@ void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance
  * layer, the lm_head and the small ops between them (bench.py's roofline_gemm times the weight stream with it).  Leaves the
  * activations of the static buffers meaningless; never call it between decode steps whose results matter. */
 void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream);
+/* 1 when a step of `num_seqs` sequences runs on the persistent layer kernel (csrc/layer_mega.cu: one launch per layer for wo -> norm ->
+ * gate|up -> SiLU -> w2 -> norm -> next QKV, split-K sums reduced in a fixed order => bitwise reproducible logits), 0 when it runs one
+ * launch per GEMM (mixed weight types, NCCL all-reduce, B200_MEGA=0: split-K sums then meet in fp32 atomics, run-to-run spread ~1e-6). */
+int32_t b200_llama_uses_layer_kernel(b200_llama* m, int32_t num_seqs);
 const float* b200_llama_logits(b200_llama* m);        /* device f32 [max_num_seqs, vocab_local]: this rank's shard */
 const int32_t* b200_llama_next_tokens(b200_llama* m); /* device i32 [max_num_seqs] */
 int64_t b200_llama_kernel_launches(b200_llama* m);    /* kernels launched by this model so far */
