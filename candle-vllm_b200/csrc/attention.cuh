@@ -27,6 +27,7 @@ struct DecodeArgs {
     float scale;
     int dtype, out_dtype;
     void* workspace; size_t workspace_bytes;
+    bool fp8 = false;                 // the cache holds e4m3 bytes (scale 1.0)
 };
 bool paged_attention_decode_tma_supported(const DecodeArgs& a, float softcap, int window, int cache_dtype, int layout);
 size_t paged_attention_decode_tma_workspace(int num_seqs, int num_heads, int head_dim, int max_blocks, int block_size);

@@ -34,6 +34,7 @@ void paged_attention_decode(void* out, const void* q, const void* key_cache, con
     cudaStream_t st = as_stream(stream);
     DecodeArgs d{out, q, key_cache, value_cache, block_tables, context_lens, num_seqs, num_heads, num_kv_heads,
                  head_dim, block_size, max_blocks_per_seq, num_blocks, scale, dtype, out_dtype, workspace, workspace_bytes};
+    d.fp8 = fp8;
     if (paged_attention_decode_tma_supported(d, softcap, sliding_window, cache_dtype, layout)) {
         paged_attention_decode_tma(d, st);
         return;

@@ -41,20 +41,28 @@ namespace {
 constexpr int kHeadDim = 128;
 constexpr int kPage = 64;                     // tokens per KV block (main.rs:364-366 default)
 constexpr int kTile = 32;                     // tokens per pipeline stage (half a page)
-constexpr int kWarps = 6;                     // independent warp pipelines per CTA
-constexpr int kStagesPerWarp = 2;
-constexpr int kThreads = kWarps * 32;
 constexpr int kMaxChunkPages = 8;
 constexpr int kSubTileBytes = kTile * 64 * 2;             // 32 tokens x 64 dims x 2 B = 4 KB
-constexpr int kStageBytes = 4 * kSubTileBytes;            // K lo, K hi, V lo, V hi = 16 KB
 constexpr int kMaxSeqs = 1024;
 
-struct SmemLayout {
-    // stages first (1024-byte aligned for the 128B swizzle): [warp][stage][K lo | K hi | V lo | V hi]
-    static constexpr int kBars = kWarps * kStagesPerWarp * kStageBytes;             // full[kWarps][kStagesPerWarp]
-    static constexpr int kHdr = kBars + kWarps * kStagesPerWarp * 8;                // int[kWarps][4][8] item headers
-    static constexpr int kPrefix = kHdr + kWarps * 4 * 8 * 4;                       // int[kMaxSeqs + 1]
+// Shared-memory plan.  16-bit KV: 6 independent warp pipelines x 2 stages of 16 KB (K lo, K hi, V lo, V hi sub-tiles) = 192 KB of KV
+// reads in flight per SM.  FP8 (e4m3) KV: a tile is half the bytes (one 4 KB box for K, one for V: 32 tokens x 128 B), so the ring
+// is 3 stages of 8 KB per warp, plus one 16 KB f16 staging tile per warp into which the warp expands a landed stage (cvt e4m3x2 ->
+// f16x2, exact) in the sub-tile layout the ldmatrix code below reads; 5 warps x (24 + 16) KB = 200 KB, 120 KB of reads in flight.
+template <bool kFp8>
+struct Plan {
+    static constexpr int kWarps = kFp8 ? 5 : 6;
+    static constexpr int kStages = kFp8 ? 3 : 2;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kStageBytes = kFp8 ? 2 * kTile * kHeadDim : 4 * kSubTileBytes;      // 8 KB / 16 KB
+    static constexpr int kConvBytes = kFp8 ? 4 * kSubTileBytes : 0;                          // f16 staging tile per warp
+    static constexpr int kWarpBytes = kStages * kStageBytes + kConvBytes;
+    // stages first (1024-byte aligned for the 128B swizzle): [warp][stage...][conv]
+    static constexpr int kBars = kWarps * kWarpBytes;                               // full[kWarps][kStages]
+    static constexpr int kHdr = kBars + kWarps * kStages * 8;                       // int[kWarps][8][8] item headers (the producer cursor runs <= kStages + 2 items ahead)
+    static constexpr int kPrefix = kHdr + kWarps * 8 * 8 * 4;                       // int[kMaxSeqs + 1]
     static constexpr int kTotal = kPrefix + (kMaxSeqs + 1) * 4;
+    static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -145,17 +153,23 @@ struct DecodeParams {
 // ids from the block table, issues its own TMA loads two tiles ahead into a private 2-stage ring
 // (completion on an mbarrier) and consumes them with ldmatrix + mma.sync.  No CTA-wide barrier in the
 // steady state, and a warp only ever waits on a barrier phase it armed itself (no phase aliasing).
-template <typename T, int kGroup>
-__global__ void __launch_bounds__(kThreads, 1)
+// T = model dtype (q, and the cache when kFp8 is false).  kFp8: the cache holds e4m3 bytes (scale 1.0, the reference passes none);
+// K / V are expanded to f16 (exact), q is converted bf16 -> f16 and the MMAs run in f16.
+template <typename T, int kGroup, bool kFp8>
+__global__ void __launch_bounds__(Plan<kFp8>::kThreads, 1)
 paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                          const DecodeParams p) {
+    using PL = Plan<kFp8>;
+    using TM = typename std::conditional<kFp8, __half, T>::type;          // MMA operand type
+    constexpr int kStagesPerWarp = PL::kStages, kStageBytes = PL::kStageBytes, kThreads = PL::kThreads;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    int* prefix = reinterpret_cast<int*>(smem + SmemLayout::kPrefix);
-    int* hdr = reinterpret_cast<int*>(smem + SmemLayout::kHdr) + warp * 32;          // [4][8]
-    const uint32_t my_stages = smem_base + warp * kStagesPerWarp * kStageBytes;
-    const uint32_t my_bars = smem_base + SmemLayout::kBars + warp * kStagesPerWarp * 8;
+    int* prefix = reinterpret_cast<int*>(smem + PL::kPrefix);
+    int* hdr = reinterpret_cast<int*>(smem + PL::kHdr) + warp * 64;          // [8][8]
+    const uint32_t my_stages = smem_base + warp * PL::kWarpBytes;
+    const uint32_t my_conv = my_stages + kStagesPerWarp * kStageBytes;       // kFp8: this warp's f16 staging tile
+    const uint32_t my_bars = smem_base + PL::kBars + warp * kStagesPerWarp * 8;
 
     if (lane == 0) {
         for (int s = 0; s < kStagesPerWarp; ++s) mbar_init(my_bars + s * 8, 1);
@@ -184,7 +198,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         unsigned int id = 0;
         if (lane == 0) id = atomicAdd(p.counter, 1u);
         id = __shfl_sync(0xffffffffu, id, 0);
-        int* hd = hdr + (n_claimed & 3) * 8;
+        int* hd = hdr + (n_claimed & 7) * 8;
         ++n_claimed;
         valid = id < (unsigned int)total_items;
         h = 0; ntiles = 0;
@@ -223,10 +237,15 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             const int tok = (p_tile & 1) * kTile;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // our generic accesses to this stage are done
             mbar_expect_tx(bar, kStageBytes);
-            tma_load_4d(dst, &kmap, bar, 0, pc_h, tok, blk, policy);
-            tma_load_4d(dst + kSubTileBytes, &kmap, bar, 64, pc_h, tok, blk, policy);
-            tma_load_4d(dst + 2 * kSubTileBytes, &vmap, bar, 0, pc_h, tok, blk, policy);
-            tma_load_4d(dst + 3 * kSubTileBytes, &vmap, bar, 64, pc_h, tok, blk, policy);
+            if constexpr (kFp8) {               // one {128 B, 32 tokens} box each for K and V
+                tma_load_4d(dst, &kmap, bar, 0, pc_h, tok, blk, policy);
+                tma_load_4d(dst + kTile * kHeadDim, &vmap, bar, 0, pc_h, tok, blk, policy);
+            } else {
+                tma_load_4d(dst, &kmap, bar, 0, pc_h, tok, blk, policy);
+                tma_load_4d(dst + kSubTileBytes, &kmap, bar, 64, pc_h, tok, blk, policy);
+                tma_load_4d(dst + 2 * kSubTileBytes, &vmap, bar, 0, pc_h, tok, blk, policy);
+                tma_load_4d(dst + 3 * kSubTileBytes, &vmap, bar, 64, pc_h, tok, blk, policy);
+            }
         }
         ++issued;
         if (++p_tile == pc_ntiles) {
@@ -243,7 +262,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     unsigned int consumed = 0;
     for (int c_slot = 0;; ++c_slot) {
         __syncwarp();
-        const int* hd = hdr + (c_slot & 3) * 8;
+        const int* hd = hdr + (c_slot & 7) * 8;
         if (hd[0] == 0) break;
         const int b = hd[1], h = hd[2], c = hd[3], ctx = hd[4], ntiles = hd[5];
 
@@ -253,8 +272,13 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         for (int ks = 0; ks < 8; ++ks) {
             if (g < kGroup) {
                 const T* qr = qbase + ((int64_t)b * p.num_heads + h * kGroup + g) * kHeadDim + ks * 16 + 2 * t;
-                qa[ks][0] = *reinterpret_cast<const uint32_t*>(qr);
-                qa[ks][1] = *reinterpret_cast<const uint32_t*>(qr + 8);
+                if constexpr (std::is_same<T, TM>::value) {
+                    qa[ks][0] = *reinterpret_cast<const uint32_t*>(qr);
+                    qa[ks][1] = *reinterpret_cast<const uint32_t*>(qr + 8);
+                } else {                        // model dtype bf16, f16 MMAs (FP8 cache): q -> f16 (saturating; exact for |q| in fp16's normal range)
+                    qa[ks][0] = pack2<TM>(to_f32(qr[0]), to_f32(qr[1]));
+                    qa[ks][1] = pack2<TM>(to_f32(qr[8]), to_f32(qr[9]));
+                }
             } else { qa[ks][0] = qa[ks][1] = 0u; }
         }
         float o[16][4];
@@ -265,7 +289,35 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         for (int tl = 0; tl < ntiles; ++tl) {
             const int s = consumed % kStagesPerWarp;
             mbar_wait(my_bars + s * 8, (consumed / kStagesPerWarp) & 1);
-            const uint32_t kt = my_stages + s * kStageBytes, vt = kt + 2 * kSubTileBytes;
+            uint32_t kt = my_stages + s * kStageBytes;
+            if constexpr (kFp8) {
+                // expand the landed stage (K then V: 32 tokens x 128 e4m3 each, 128-byte swizzled rows) into this warp's f16 tile:
+                // lane -> one 16-byte chunk (16 dims) per step = two 16-byte f16 chunks of sub-tile (dim / 64), same swizzle
+                const uint8_t* raw = smem + (kt - smem_base);
+                uint8_t* conv = smem + (my_conv - smem_base);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int id = (i & 7) * 32 + lane, row = id >> 3, rc = id & 7;
+                    const uint4 v = *reinterpret_cast<const uint4*>(raw + (i >> 3) * (kTile * kHeadDim) + row * 128 + ((rc ^ (row & 7)) << 4));
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[j] & 0xffffu), __NV_E4M3);
+                        const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[j] >> 16), __NV_E4M3);
+                        o[2 * j] = (uint32_t)lo.x | ((uint32_t)lo.y << 16);
+                        o[2 * j + 1] = (uint32_t)hi.x | ((uint32_t)hi.y << 16);
+                    }
+                    uint8_t* dst = conv + ((i >> 3) * 2 + (rc >> 2)) * kSubTileBytes + row * 128;
+                    const int c0 = (2 * rc) & 7;
+                    *reinterpret_cast<uint4*>(dst + ((c0 ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(dst + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                __syncwarp();
+                issue_one();                                 // the raw stage is free again: refill it now (tile consumed + kStages)
+                kt = my_conv;
+            }
+            const uint32_t vt = kt + 2 * kSubTileBytes;
             const int valid = min(kTile, ctx - (c * chunk_tokens + tl * kTile));
 
             // ---- S = Q K^T : 4 n-tiles (8 tokens each) x 8 k-steps --------------------------------
@@ -283,8 +335,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
                     ldmatrix_x4(kb, addr);
                     const uint32_t a0[4] = {qa[2 * kp][0], 0u, qa[2 * kp][1], 0u};
                     const uint32_t a1[4] = {qa[2 * kp + 1][0], 0u, qa[2 * kp + 1][1], 0u};
-                    mma_16816<T>(sacc[nt], a0, kb[0], kb[1]);
-                    mma_16816<T>(sacc[nt], a1, kb[2], kb[3]);
+                    mma_16816<TM>(sacc[nt], a0, kb[0], kb[1]);
+                    mma_16816<TM>(sacc[nt], a1, kb[2], kb[3]);
                 }
             }
             // ---- mask + online softmax (rows g; rows g+8 are padding) -----------------------------
@@ -307,7 +359,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             for (int nt = 0; nt < 4; ++nt) {
                 const float p0 = fast_exp2(sacc[nt][0] - m_new), p1 = fast_exp2(sacc[nt][1] - m_new);
                 l_run += p0 + p1;
-                pa[nt] = pack2<T>(p0, p1);
+                pa[nt] = pack2<TM>(p0, p1);
             }
             if (corr != 1.f) {
 #pragma unroll
@@ -333,12 +385,12 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
                     const uint32_t addr = vt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
                     uint32_t vb[4];
                     ldmatrix_x4_trans(vb, addr);
-                    mma_16816<T>(o[2 * np], a, vb[0], vb[1]);
-                    mma_16816<T>(o[2 * np + 1], a, vb[2], vb[3]);
+                    mma_16816<TM>(o[2 * np], a, vb[0], vb[1]);
+                    mma_16816<TM>(o[2 * np + 1], a, vb[2], vb[3]);
                 }
             }
             __syncwarp();
-            issue_one();                                     // refill the stage we just drained (tile consumed + 2)
+            if constexpr (!kFp8) issue_one();                // refill the stage we just drained (tile consumed + 2)
             ++consumed;
         }
 
@@ -415,14 +467,15 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool make_kv_map(CUtensorMap* map, const void* cache, int64_t num_blocks, int kvh, int dtype) {
+bool make_kv_map(CUtensorMap* map, const void* cache, int64_t num_blocks, int kvh, int dtype, bool fp8) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) { set_error(kErrCuda, "paged_attention_decode: cuTensorMapEncodeTiled unavailable"); return false; }
+    const cuuint64_t es = fp8 ? 1 : 2;                  // e4m3 bytes: a token row of one head is 128 B = one swizzle span = ONE box
     const cuuint64_t dims[4] = {(cuuint64_t)kHeadDim, (cuuint64_t)kvh, (cuuint64_t)kPage, (cuuint64_t)num_blocks};
-    const cuuint64_t strides[3] = {(cuuint64_t)kHeadDim * 2, (cuuint64_t)kvh * kHeadDim * 2, (cuuint64_t)kPage * kvh * kHeadDim * 2};
-    const cuuint32_t box[4] = {64, 1, (cuuint32_t)kTile, 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)kHeadDim * es, (cuuint64_t)kvh * kHeadDim * es, (cuuint64_t)kPage * kvh * kHeadDim * es};
+    const cuuint32_t box[4] = {(cuuint32_t)(fp8 ? 128 : 64), 1, (cuuint32_t)kTile, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(map, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+    const CUresult r = enc(map, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 4,
                            const_cast<void*>(cache), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error(kErrCuda, "paged_attention_decode: cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
@@ -438,20 +491,21 @@ int pick_chunk_pages(int num_seqs, int kvh, int max_blocks) {
     // only when the whole problem is tiny.
     auto items = [&](int c) { return (int64_t)num_seqs * kvh * ((max_blocks + c - 1) / c); };
     int chunk = kMaxChunkPages;
-    if (items(chunk) < 2ll * sm_count() * kWarps) chunk >>= 1;
+    if (items(chunk) < 2ll * sm_count() * 6) chunk >>= 1;
     const int64_t want = 3ll * sm_count();
     while (chunk > 1 && items(chunk) < want) chunk >>= 1;
     return chunk;
 }
 
-template <typename T, typename TOut, int kGroup, bool kK4 = false>
+template <typename T, typename TOut, int kGroup, bool kK4, bool kFp8>
 void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, cudaStream_t st) {
-    auto kern = paged_attn_decode_kernel<T, kGroup>;
-    ensure_dynamic_smem(reinterpret_cast<const void*>(kern), SmemLayout::kTotal);
+    using PL = Plan<kFp8>;
+    auto kern = paged_attn_decode_kernel<T, kGroup, kFp8>;
+    ensure_dynamic_smem(reinterpret_cast<const void*>(kern), PL::kTotal);
     const int64_t max_items = (int64_t)a.num_seqs * a.num_kv_heads * p.max_chunks;
-    const int64_t want = (max_items + kWarps - 1) / kWarps;
+    const int64_t want = (max_items + PL::kWarps - 1) / PL::kWarps;
     const int grid = (int)(want < sm_count() ? want : sm_count());
-    launch_pdl(kern, dim3(grid), dim3(kThreads), SmemLayout::kTotal, st, kmap, vmap, p);
+    launch_pdl(kern, dim3(grid), dim3(PL::kThreads), PL::kTotal, st, kmap, vmap, p);
     count_launch();
     launch_pdl(paged_attn_merge_kernel<T, TOut, kK4>, dim3(a.num_heads, a.num_seqs), dim3(kHeadDim), 0, st,
                static_cast<TOut*>(a.out), (const float*)p.part_o, (const float*)p.part_ml, a.context_lens, p.counter, (int)a.num_heads,
@@ -459,13 +513,25 @@ void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vma
     count_launch();
 }
 
-template <typename T, typename TOut, bool kK4 = false>
+template <typename T, typename TOut, bool kK4, bool kFp8>
 void launch_group(const DecodeArgs& a, const CUtensorMap& km, const CUtensorMap& vm, const DecodeParams& p, int group, cudaStream_t st) {
     switch (group) {
-        case 1: launch<T, TOut, 1, kK4>(a, km, vm, p, st); break;
-        case 2: launch<T, TOut, 2, kK4>(a, km, vm, p, st); break;
-        case 4: launch<T, TOut, 4, kK4>(a, km, vm, p, st); break;
-        case 8: launch<T, TOut, 8, kK4>(a, km, vm, p, st); break;
+        case 1: launch<T, TOut, 1, kK4, kFp8>(a, km, vm, p, st); break;
+        case 2: launch<T, TOut, 2, kK4, kFp8>(a, km, vm, p, st); break;
+        case 4: launch<T, TOut, 4, kK4, kFp8>(a, km, vm, p, st); break;
+        case 8: launch<T, TOut, 8, kK4, kFp8>(a, km, vm, p, st); break;
+    }
+}
+
+template <bool kFp8>
+void launch_dtype(const DecodeArgs& a, const CUtensorMap& km, const CUtensorMap& vm, const DecodeParams& p, int group, cudaStream_t st) {
+    if (a.dtype == B200_BF16) {
+        if (a.out_dtype == B200_F16_K4) launch_group<__nv_bfloat16, __half, true, kFp8>(a, km, vm, p, group, st);
+        else if (a.out_dtype == B200_F16) launch_group<__nv_bfloat16, __half, false, kFp8>(a, km, vm, p, group, st);
+        else launch_group<__nv_bfloat16, __nv_bfloat16, false, kFp8>(a, km, vm, p, group, st);
+    } else {
+        if (a.out_dtype == B200_F16_K4) launch_group<__half, __half, true, kFp8>(a, km, vm, p, group, st);
+        else launch_group<__half, __half, false, kFp8>(a, km, vm, p, group, st);
     }
 }
 
@@ -473,7 +539,8 @@ void launch_group(const DecodeArgs& a, const CUtensorMap& km, const CUtensorMap&
 
 bool paged_attention_decode_tma_supported(const DecodeArgs& a, float softcap, int window, int cache_dtype, int layout) {
     const int group = a.num_heads / a.num_kv_heads;
-    return layout == B200_KV_FLASH && a.head_dim == kHeadDim && a.block_size == kPage && cache_dtype == a.dtype &&
+    const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
+    return layout == B200_KV_FLASH && a.head_dim == kHeadDim && a.block_size == kPage && (cache_dtype == a.dtype || fp8) &&
            (a.dtype == B200_BF16 || a.dtype == B200_F16) && softcap <= 0.f && window <= 0 &&
            (group == 1 || group == 2 || group == 4 || group == 8) && a.num_seqs <= kMaxSeqs && a.num_blocks > 0 &&
            ((uintptr_t)a.kc & 15) == 0 && ((uintptr_t)a.vc & 15) == 0 && ((uintptr_t)a.q & 3) == 0;
@@ -504,15 +571,9 @@ void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
     p.part_o = reinterpret_cast<float*>(static_cast<char*>(a.workspace) + 256);
     p.part_ml = p.part_o + n_part * kHeadDim;
     CUtensorMap km, vm;
-    if (!make_kv_map(&km, a.kc, a.num_blocks, a.num_kv_heads, a.dtype) || !make_kv_map(&vm, a.vc, a.num_blocks, a.num_kv_heads, a.dtype)) return;
-    if (a.dtype == B200_BF16) {
-        if (a.out_dtype == B200_F16_K4) launch_group<__nv_bfloat16, __half, true>(a, km, vm, p, group, st);
-        else if (a.out_dtype == B200_F16) launch_group<__nv_bfloat16, __half>(a, km, vm, p, group, st);
-        else launch_group<__nv_bfloat16, __nv_bfloat16>(a, km, vm, p, group, st);
-    } else {
-        if (a.out_dtype == B200_F16_K4) launch_group<__half, __half, true>(a, km, vm, p, group, st);
-        else launch_group<__half, __half>(a, km, vm, p, group, st);
-    }
+    if (!make_kv_map(&km, a.kc, a.num_blocks, a.num_kv_heads, a.dtype, a.fp8) || !make_kv_map(&vm, a.vc, a.num_blocks, a.num_kv_heads, a.dtype, a.fp8)) return;
+    if (a.fp8) launch_dtype<true>(a, km, vm, p, group, st);
+    else launch_dtype<false>(a, km, vm, p, group, st);
     check_launch("paged_attention_decode");
 }
 

@@ -86,6 +86,7 @@ struct b200_llama {
     int mega_G = 0, s_qkv = 1, s_ro = 1, s_gu = 1;                // slabs per buffer (max CTAs sharing one tile)
     float* qkv_slabs = nullptr; float* ro_slabs = nullptr; float* gate_slabs = nullptr; float* up_slabs = nullptr;
     uint32_t* mega_counters = nullptr; size_t mega_counter_bytes = 0;
+    long long* mega_trace = nullptr; int mega_trace_launch = -1;   // B200_MEGA_TRACE=<launch index>: clock64 stamps of that launch
 
     std::map<int, cudaGraphExec_t> graphs;       // batch size -> captured step
     std::map<int, int> launches_per_step;
@@ -170,6 +171,7 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         P.tp_timeout_ns = (unsigned long long)m->tp_timeout_ms * 1000000ull;
         P.timeout_word = m->d_timeout;
         if (fused_ar) for (int i = 0; i < c.tp_world; ++i) P.peers.p[i] = static_cast<char*>(m->peers[i]);
+        P.trace = launch == m->mega_trace_launch ? m->mega_trace : nullptr;
     };
     auto qkv_phase = [&](MegaParams& P, MegaPhase& ph, const b200_llama_layer& w, int map0) -> bool {
         if (!mega_make_w_map(&P.maps[map0], w.wq, qd, H) || !mega_make_w_map(&P.maps[map0 + 1], w.wk, kd, H) ||
@@ -499,6 +501,10 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
              dmalloc(m->gate_slabs, (size_t)m->s_gu * B * m->ffn_l) && dmalloc(m->up_slabs, (size_t)m->s_gu * B * m->ffn_l) &&
              dmalloc(m->mega_counters, m->mega_counter_bytes / sizeof(uint32_t));
         m->use_mega = ok;
+        if (const char* tr = getenv("B200_MEGA_TRACE")) {
+            m->mega_trace_launch = atoi(tr);
+            ok = ok && dmalloc(m->mega_trace, (size_t)G * kMegaMaxPhases * 8);
+        }
     }
     if (!ok) {
         if (!b200_last_error()) set_error(kErrCuda, "b200_llama_create: allocation failed");
@@ -520,6 +526,7 @@ void b200_llama_destroy(b200_llama* m) {
     if (m->h_timeout) cudaFreeHost(m->h_timeout);
     if (m->logits_gathered) cudaFree(m->logits_gathered);
     if (m->logits_full) cudaFree(m->logits_full);
+    if (m->mega_trace) cudaFree(m->mega_trace);
     for (void* p : {(void*)m->qkv_slabs, (void*)m->ro_slabs, (void*)m->gate_slabs, (void*)m->up_slabs, (void*)m->mega_counters}) if (p) cudaFree(p);
     delete m;
 }
@@ -657,6 +664,15 @@ void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream) {
     if (!ready(m)) return;
     B200_REQUIRE(num_seqs > 0 && num_seqs <= m->cfg.max_num_seqs, kErrBadArg, "b200_llama_linear_chain: bad num_seqs");
     m->launches += forward(m, num_seqs, as_stream(stream), /*linear_only=*/true);
+}
+
+// profiling aid: copy the clock64 stamps of the traced launch ([CTAs][4 phases][8] int64) to the host; returns the CTA count
+int32_t b200_llama_mega_trace(b200_llama* m, long long* host, int32_t max_ctas) {
+    if (!m || !m->mega_trace || !host) return 0;
+    const int n = std::min(max_ctas, m->mega_G);
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, m->mega_trace, (size_t)n * kMegaMaxPhases * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return n;
 }
 
 int32_t b200_llama_uses_layer_kernel(b200_llama* m, int32_t num_seqs) {

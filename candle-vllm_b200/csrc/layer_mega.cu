@@ -273,6 +273,13 @@ __device__ __forceinline__ void eop_tp_norm(const MegaParams& P, const MegaPhase
     if (tid == 0) epoch[row] = e;
 }
 
+// profiling aid: stamp k of phase ph of this CTA (0 phase entered, 1 units dequantised ahead / op reached, 2 previous phase complete
+// everywhere, 3 op done, 4 last unit of the phase dequantised, 5 last epilogue stored, 6 first activations landed (MMA warp), 7 first
+// accumulator complete)
+__device__ __forceinline__ void trace_stamp(const MegaParams& P, int ph, int k) {
+    if (P.trace) P.trace[((int64_t)blockIdx.x * kMegaMaxPhases + ph) * 8 + k] = clock64();
+}
+
 // The elementwise op that produces phase ph's activations from phase ph-1's slabs: wait until phase ph-1 is complete on every CTA,
 // run this CTA's share, publish.  Called by all 512 dequant-warp threads at the same point of their loop.
 __device__ __forceinline__ void run_eop(const MegaParams& P, int ph, float* red) {
@@ -280,13 +287,13 @@ __device__ __forceinline__ void run_eop(const MegaParams& P, int ph, float* red)
     const MegaPhase& g = P.phase[ph];
     const MegaPhase& prev = P.phase[ph - 1];
     pdl_wait();                                                                // x / the slabs may still be in use by the previous kernel
-    if (tid == 0) wait_counter(P.counters + 2 * ph, gridDim.x, P.error_word);   // phase ph-1 complete everywhere
+    if (tid == 0) { trace_stamp(P, ph, 1); wait_counter(P.counters + 2 * ph, gridDim.x, P.error_word); trace_stamp(P, ph, 2); }   // phase ph-1 complete everywhere
     named_bar_sync(1, kDeqThreads);
     if (g.eop == kEopNorm) eop_norm(P, prev, g, red, tid);
     else if (g.eop == kEopSilu) eop_silu(P, prev, g, tid);
     else eop_tp_norm(P, prev, g, red, tid);
     named_bar_sync(1, kDeqThreads);                                            // every thread's stores are issued
-    if (tid == 0) { __threadfence(); red_release_gpu_add(P.counters + 2 * ph + 1, 1u); }
+    if (tid == 0) { __threadfence(); red_release_gpu_add(P.counters + 2 * ph + 1, 1u); trace_stamp(P, ph, 3); }
 }
 
 __device__ __forceinline__ int seg_of_tile(const MegaPhase& g, int tile) { return (tile >= g.tile_end[0]) + (tile >= g.tile_end[1]); }
@@ -444,6 +451,7 @@ layer_mega_kernel(const __grid_constant__ MegaParams P) {
                 for (; u < seg_end; ++u, ++it) {
                     const int xs = it % kX, ab = it % kABufs;
                     mbar_wait(x_full(xs), (it / kX) & 1);
+                    if (P.trace && leader && u == u0) trace_stamp(P, ph, 6);
                     mbar_wait(a_ready(ab), (it / kABufs) & 1);
                     tc_fence_after();
                     const uint32_t a_t = tmem + kColA + ab * 128;
@@ -479,6 +487,7 @@ layer_mega_kernel(const __grid_constant__ MegaParams P) {
             range(g, u0, u1);
             const uint32_t nsb = (uint32_t)g.nsb;
             bool eop_pending = g.eop != kEopNone;
+            if (tid == 0) trace_stamp(P, ph, 0);
             // Units of this phase run segment by segment (a segment = this CTA's share of one tile).  The elementwise op that
             // produces the phase's activations is slotted in ONCE: after up to kABufs units have been dequantised ahead (their
             // A buffers only depend on MMAs of the previous phase), at the latest before the first epilogue wait.
@@ -510,6 +519,7 @@ layer_mega_kernel(const __grid_constant__ MegaParams P) {
                 if (u0 == u1) break;                       // no units in this phase: this CTA only took part in the op
                 // ---- epilogue of the segment: D (TMEM) -> this CTA's slab of the tile, plain coalesced stores --------------
                 pdl_wait();                                // the slabs may still be read by the previous kernel (no-op after the first time)
+                if (tid == 0 && u == u1) trace_stamp(P, ph, 4);
                 mbar_wait(d_full, seg & 1);
                 tc_fence_after();
                 {
@@ -550,6 +560,7 @@ layer_mega_kernel(const __grid_constant__ MegaParams P) {
                 named_bar_sync(1, kDeqThreads);
                 if (tid == 0) { __threadfence(); red_release_gpu_add(ctr + 2 * (ph + 1), 1u); }
             }
+            if (tid == 0) trace_stamp(P, ph, 5);
         }
     }
 

@@ -54,6 +54,7 @@ struct MegaParams {
     int tp_rank, tp_world, rows_max;
     unsigned long long tp_timeout_ns;
     uint32_t* timeout_word;
+    long long* trace;                 // profiling aid (B200_MEGA_TRACE): [CTA][phase][8] clock64 stamps, see layer_mega.cu
 };
 
 int mega_grid();

@@ -294,6 +294,9 @@ void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream);
  * gate|up -> SiLU -> w2 -> norm -> next QKV, split-K sums reduced in a fixed order => bitwise reproducible logits), 0 when it runs one
  * launch per GEMM (mixed weight types, NCCL all-reduce, B200_MEGA=0: split-K sums then meet in fp32 atomics, run-to-run spread ~1e-6). */
 int32_t b200_llama_uses_layer_kernel(b200_llama* m, int32_t num_seqs);
+/* Profiling aid (env B200_MEGA_TRACE=<launch index> at model creation): clock64 stamps [CTA][phase 0..3][8] of that launch of the
+ * persistent layer kernel, copied to `host`; returns the number of CTAs.  tools/mega_trace.py prints the timeline. */
+int32_t b200_llama_mega_trace(b200_llama* m, long long* host, int32_t max_ctas);
 const float* b200_llama_logits(b200_llama* m);        /* device f32 [max_num_seqs, vocab_local]: this rank's shard */
 const int32_t* b200_llama_next_tokens(b200_llama* m); /* device i32 [max_num_seqs] */
 int64_t b200_llama_kernel_launches(b200_llama* m);    /* kernels launched by this model so far */

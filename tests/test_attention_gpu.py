@@ -65,6 +65,30 @@ def test_decode_matches_oracle(B, H, kvh, hd, bs, ctx):
     _check(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,H,kvh,ctx", [
+    (4, 32, 8, [1, 64, 65, 300]),                             # ragged, single-tile items (header ring of the 3-stage pipeline)
+    (3, 8, 8, [129, 5, 1000]),                                # group 1
+    (2, 16, 2, [700, 64]),                                    # group 8
+    (6, 8, 2, [31, 32, 33, 95, 96, 97]),                      # tile boundaries: masked V rows in the f16 staging tile
+    (32, 32, 8, [4096 + 7 * i for i in range(32)]),           # metric shape (config 3: FP8 KV), batch 32, ctx ~4k
+])
+def test_decode_fp8_kv_on_the_tma_path_matches_oracle(dtype, B, H, kvh, ctx):
+    """FP8 (e4m3, scale 1.0) KV cache, flash layout, block 64, head 128: the TMA split-KV kernel with the e4m3 -> f16 staging tile.
+    Same tolerance as the 16-bit cache (the expansion is exact; q is bf16 -> f16, P is f16)."""
+    rng = np.random.default_rng(hash((B, H, kvh, len(ctx))) & 0xffff)
+    nb = sum(-(-c // 64) for c in ctx) + 3
+    q, kc, vc, kn, vn, bt = _mk(rng, B, H, kvh, 128, 64, nb, ctx, dtype=dtype, fp8=True)
+    attn = pkg.PagedAttention(H, 128, 128 ** -0.5, kvh, fp8_kvcache=True)
+    meta = pkg.InputMetadata(is_prefill=False, slot_mapping=torch.zeros(0, dtype=torch.int64, device=DEV),
+                             block_tables=torch.from_numpy(bt).to(DEV), context_lens=torch.tensor(ctx, dtype=torch.int32, device=DEV))
+    out = attn.forward(q, None, None, None, kc, vc, meta)
+    ref = OA.paged_attention_decode(q.float().cpu().numpy(), kn, vn, bt, ctx, 128 ** -0.5, fp8=True)
+    _check(out, ref)
+    out2 = attn.forward(q, None, None, None, kc, vc, meta)        # work queue re-zeroed by the merge kernel: repeatable
+    assert torch.equal(out, out2)
+
+
 def test_decode_padded_tables_like_graph_replay():
     # graph.rs:732-738: block tables padded to max_num_blocks; kernel must only read context_lens
     rng = np.random.default_rng(1)
