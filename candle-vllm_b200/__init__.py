@@ -11,7 +11,7 @@ There is no CPU fallback: without the CUDA library / an sm_100 GPU every op rais
 from ._lib import BackendError, lib, lib_path, device_ok  # noqa: F401
 from .backend import (  # noqa: F401
     DType, GgmlType, KvLayout, copy_blocks, swap_blocks, reshape_and_cache, InputMetadata,
-    PagedAttention, QTensor, QMatMul, LnFp8, LnNvfp4, LnMxfp4, rms_norm, fused_rope, silu_mul, argmax, dequantize,
+    PagedAttention, QTensor, QMatMul, Linear, LnFp8, LnNvfp4, LnMxfp4, rms_norm, fused_rope, silu_mul, argmax, dequantize,
 )
 from .cache_engine import CacheConfig, CacheEngine  # noqa: F401
 from .inputs import prepare_decode, prepare_prompt, used_blocks_for_len, PAD_SLOT_ID  # noqa: F401

@@ -386,6 +386,32 @@ def _lin_io(x: torch.Tensor, n: int, k: int, bias, who: str):
     return x2, out
 
 
+class Linear:
+    """Dense 16-bit linear: ``Linear::new(weight [N, K], bias)`` / ``.forward(x)`` (/root/reference/src/openai/models/linear.rs:124-172;
+    the reference reaches cuBLAS through candle's matmul).  f16 or bf16 weights and activations, fp32 accumulation on tcgen05
+    (``linear_16bit``, csrc/dense_gemm.cu)."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        _cuda(weight, "weight")
+        if weight.dim() != 2 or weight.dtype not in (torch.float16, torch.bfloat16):
+            raise BackendError("Linear: weight must be a 2-D f16 / bf16 tensor")
+        self.weight = weight.contiguous()
+        self.bias = None if bias is None else _cuda(bias, "bias").to(weight.dtype).contiguous()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        n, k = self.weight.shape
+        if x.dtype != self.weight.dtype:
+            raise BackendError(f"Linear: activation dtype {x.dtype} != weight dtype {self.weight.dtype}")
+        x2, out = _lin_io(x, n, k, self.bias, "Linear")
+        if k % 8 or n % 8:
+            raise BackendError("Linear: in / out features must be multiples of 8 (16-byte rows for TMA)")
+        with torch.cuda.device(x.device):
+            lib().linear_16bit(_ptr(x2), _ptr(self.weight), _ptr(self.bias), _ptr(out), C.c_int32(x2.shape[0]), C.c_int32(n), C.c_int32(k),
+                               C.c_int32(_dt(x2)), _stream(x.device))
+        check("Linear.forward")
+        return out.reshape(*x.shape[:-1], n)
+
+
 class LnFp8:
     """Block-scaled FP8 linear: ``weight`` e4m3 (torch.float8_e4m3fn or u8) [N, K], ``weight_scale`` f32
     [ceil(N/by), ceil(K/bx)] (linear.rs:944-973); ``forward`` = ``fp8_matmul`` (+ bias)."""

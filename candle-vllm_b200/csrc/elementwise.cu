@@ -192,12 +192,19 @@ __device__ __forceinline__ void zero16(float* p) {
 // one work item = (token t, head slot hs, unit u): callable from the stand-alone kernel below and from the fused layer kernel
 // 16 consecutive f32 of row `p` summed over the slabs of their tile (layer_mega.cu: split-K partial sums, added in slab order)
 __device__ __forceinline__ void load16_slabs(const float* p, int64_t slab_stride, int slabs, float (&v)[16]) {
-    load16(p, v);
-    for (int s = 1; s < slabs; ++s) {
-        float t[16];
-        load16(p + (int64_t)s * slab_stride, t);
+    // all loads first (independent L2 round trips), then the adds in slab order
+    float4 t[kMegaMaxSlabs][4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += t[i];
+    for (int s = 0; s < kMegaMaxSlabs; ++s)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            t[s][i] = s < slabs ? __ldcg(reinterpret_cast<const float4*>(p + (int64_t)s * slab_stride) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 a = t[0][i];
+#pragma unroll
+        for (int s = 1; s < kMegaMaxSlabs; ++s) { a.x += t[s][i].x; a.y += t[s][i].y; a.z += t[s][i].z; a.w += t[s][i].w; }
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
     }
 }
 

@@ -500,7 +500,7 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
         ok = dmalloc(m->qkv_slabs, (size_t)m->s_qkv * B * m->qkv_row) && dmalloc(m->ro_slabs, (size_t)m->s_ro * B * c.hidden) &&
              dmalloc(m->gate_slabs, (size_t)m->s_gu * B * m->ffn_l) && dmalloc(m->up_slabs, (size_t)m->s_gu * B * m->ffn_l) &&
              dmalloc(m->mega_counters, m->mega_counter_bytes / sizeof(uint32_t));
-        m->use_mega = ok;
+        m->use_mega = ok && m->s_qkv <= kMegaMaxSlabs && m->s_ro <= kMegaMaxSlabs && m->s_gu <= 4;
         if (const char* tr = getenv("B200_MEGA_TRACE")) {
             m->mega_trace_launch = atoi(tr);
             ok = ok && dmalloc(m->mega_trace, (size_t)G * kMegaMaxPhases * 8);

@@ -25,6 +25,7 @@ struct TpInboxLayout {
 // ---- persistent layer kernel ------------------------------------------------------------------------------------------------------
 constexpr int kMegaMaxPhases = 4;
 constexpr int kMegaMaxMaps = 10;
+constexpr int kMegaMaxSlabs = 8;              // most CTAs that may share one 128-row tile (wo / w2 / QKV phases); 4 for gate | up
 
 enum MegaEop { kEopNone = 0, kEopNorm = 1, kEopSilu = 2, kEopTpNorm = 3 };
 

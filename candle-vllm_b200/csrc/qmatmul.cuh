@@ -51,6 +51,12 @@ void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void
 // library-owned scratch (marlin_api.cu): grown outside stream capture or set once with b200_set_scratch()
 void* get_scratch(size_t bytes, cudaStream_t st);
 
+// dense 16-bit GEMM on tcgen05 (dense_gemm.cu): y[m,n] = x[m,k] . w[n,k]^T (+ bias); operands f16 / bf16 (`dtype`), out f16 / bf16 / f32
+bool dense_gemm_16(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int64_t ldx, int64_t ldw, int64_t ldy,
+                   int dtype, int out_dtype, cudaStream_t st);
+// GGML blocks -> fp16 [n, k] (natural order), one rounding
+bool dequantize_f16(const void* w, void* out_f16, int64_t n, int64_t k, int ggml_type, cudaStream_t st);
+
 // picks tc or generic; y row stride ldy (elements)
 void qmatmul_dispatch(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k,
                       int ggml_type, int accumulate, cudaStream_t st);

@@ -76,6 +76,41 @@ __global__ void dequantize_kernel(const void* __restrict__ w_, float* __restrict
         out[i] = Q::w(w + i / Q::kElems, (int)(i % Q::kElems));
 }
 
+// W -> fp16 [n, k] (natural k order), 8 weights per thread and one 16-byte store: the "dequantise once" half of the large-m path
+// (dense_gemm.cu reuses the result for every m-tile).  One rounding to fp16, like the decode kernel's dequant-into-TMEM.
+template <int kType>
+__global__ void __launch_bounds__(256)
+dequantize_f16_kernel(const void* __restrict__ w_, __half* __restrict__ out, int64_t total8) {
+    using Q = QType<kType>;
+    const typename Q::Block* w = static_cast<const typename Q::Block*>(w_);
+    pdl_wait();
+    pdl_trigger();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 8;
+        const typename Q::Block* b = w + e / Q::kElems;
+        const int o = (int)(e % Q::kElems);
+        __half h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = from_f32<__half>(Q::w(b, o + j));
+        *reinterpret_cast<uint4*>(out + e) = *reinterpret_cast<const uint4*>(h);
+    }
+}
+
+bool dequantize_f16(const void* w, void* out_f16, int64_t n, int64_t k, int ggml_type, cudaStream_t st) {
+    const int64_t total8 = n * k / 8;
+    int64_t g = (total8 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    switch (ggml_type) {
+        case B200_GGML_Q4_K: launch_pdl(dequantize_f16_kernel<B200_GGML_Q4_K>, dim3((int)g), dim3(256), 0, st, w, (__half*)out_f16, total8); break;
+        case B200_GGML_Q6_K: launch_pdl(dequantize_f16_kernel<B200_GGML_Q6_K>, dim3((int)g), dim3(256), 0, st, w, (__half*)out_f16, total8); break;
+        case B200_GGML_Q8_0: launch_pdl(dequantize_f16_kernel<B200_GGML_Q8_0>, dim3((int)g), dim3(256), 0, st, w, (__half*)out_f16, total8); break;
+        default: set_error(kErrUnsupported, "dequantize: ggml type %d unsupported", ggml_type); return false;
+    }
+    count_launch();
+    return check_launch("dequantize_f16");
+}
+
 template <int kType>
 static void launch(const void* x, bool f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int acc, cudaStream_t st) {
     dim3 grid(ceil_div(n, kRowsPerCta), ceil_div(m, kMTile));
@@ -151,9 +186,14 @@ static bool qmm_check(const char* who, const void* x, const void* w, const float
 
 extern "C" {
 
+// Rows at or above this count take the "dequantise once + dense tensor-core GEMM" path: the 16-bit copy of W costs ~4.6 bytes of
+// traffic per weight (0.56 read, 2 written, 2 read back), a 64-row pass of the decode kernel 0.56 -- break-even at ~8 passes.
+static constexpr int kDenseRows = 512;
+
 size_t qmatmul_workspace_bytes(int32_t m, int32_t n, int32_t k) {
-    (void)n;
-    return (size_t)(m > 0 ? m : 0) * (size_t)(k > 0 ? k : 0) * 2 + 256;    // fp16 copy of the activations
+    size_t b = (size_t)(m > 0 ? m : 0) * (size_t)(k > 0 ? k : 0) * 2 + 256;    // fp16 copy of the activations
+    if (m >= kDenseRows) b += (size_t)(n > 0 ? n : 0) * (size_t)(k > 0 ? k : 0) * 2 + 256;   // + fp16 copy of the weights
+    return b;
 }
 
 void qmatmul_f16act(const void* x_f16, const void* w, float* y, int32_t m, int32_t n, int32_t k,
@@ -182,6 +222,16 @@ void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, 
                  int32_t ggml_type, int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t stream) {
     if (m == 0 || n == 0) return;
     if (!qmm_check("qmatmul_f32", x, w, y, m, n, k, ggml_type)) return;
+    if (m >= kDenseRows && !accumulate && k % 8 == 0 && ((uintptr_t)workspace & 15) == 0 && workspace &&
+        workspace_bytes >= qmatmul_workspace_bytes(m, n, k)) {
+        // prefill chunk: weights -> fp16 once, activations -> fp16, dense tcgen05 GEMM with fp32 output (dense_gemm.cu)
+        char* xs = static_cast<char*>(workspace);
+        char* ws = xs + (((size_t)m * k * 2 + 255) & ~(size_t)255);
+        cast(x, xs, (int64_t)m * k, B200_F32, B200_F16, stream);
+        if (!dequantize_f16(w, ws, n, k, ggml_type, as_stream(stream))) return;
+        dense_gemm_16(xs, ws, nullptr, y, m, n, k, k, k, n, B200_F16, B200_F32, as_stream(stream));
+        return;
+    }
     if (qmatmul_tc_usable(m, n, k, ggml_type)) {
         B200_REQUIRE(workspace && workspace_bytes >= qmatmul_workspace_bytes(m, n, k), kErrBadArg,
                      "qmatmul_f32: workspace too small (%zu < %zu)", workspace_bytes, qmatmul_workspace_bytes(m, n, k));

@@ -123,7 +123,9 @@ void paged_attention_prefill(void* out, const void* q, const void* key_cache, co
  * GGUF bytes (k % 256 == 0 for K-quants, % 32 for Q8_0).  Activations are rounded to fp16
  * (saturating) and products accumulate in fp32 on the tensor cores; the reference quantises
  * activations to 8 bit (Q8_1 / Q8_K), which is coarser.
- * accumulate != 0: y += result (used for the residual add; implies fp32 atomics). */
+ * accumulate != 0: y += result (used for the residual add; implies fp32 atomics).
+ * m <= 64 (decode) runs the dequant-into-TMEM kernel; 64 < m < 512 runs it 64 rows per pass; m >= 512 (prefill chunks) dequantises W once
+ * into the workspace (fp16, same single rounding) and runs the dense tcgen05 GEMM, so every m-tile reuses the dequantised tile. */
 size_t qmatmul_workspace_bytes(int32_t m, int32_t n, int32_t k);
 void qmatmul_f32(const float* x, const void* w, float* y, int32_t m, int32_t n, int32_t k,
                  int32_t ggml_type, int32_t accumulate, void* workspace, size_t workspace_bytes,
@@ -175,6 +177,11 @@ void marlin_awq_4bit_bf16(const void* x, const int32_t* qweight, const void* sca
 void gemm_half_q_half_alt(const void* x, const uint32_t* qweight, const uint32_t* qzeros, const void* scales,
                           const int32_t* g_idx, void* out, int32_t m, int32_t n, int32_t k, int32_t bits, int64_t stream);
 void b200_set_scratch(void* device_ptr, size_t bytes);
+
+/* ---- dense 16-bit Linear::forward -- replaces candle's cuBLAS matmul for unquantised weights (/root/reference/src/openai/models/linear.rs:124-172)
+ * out[m,n] = x[m,k] . weight[n,k]^T (+ bias[n]); x, weight, bias, out of `dtype` (B200_F16 / B200_BF16), contiguous, fp32 accumulation on
+ * tcgen05 (128 x 256 tiles for m > 64; swap-AB weight stream for m <= 64).  k % 8 == 0, n % 8 == 0 (16-byte rows). */
+void linear_16bit(const void* x, const void* weight, const void* bias, void* out, int32_t m, int32_t n, int32_t k, int32_t dtype, int64_t stream);
 
 /* ---- K10 / K11 / K12: weight-only low-precision float linears -- replace attention_rs::{fp8_linear::fp8_matmul,
  * nvfp4_linear::nvfp4_matmul, mxfp4_linear::mxfp4_matmul} (call sites /root/reference/src/openai/models/linear.rs:1190-1221,

@@ -100,14 +100,16 @@ def test_decode_at_metric_shapes_matches_oracle():
                 assert ref[b].max() - ref[b, nxt[b]] <= 2 * err * scale, (step, b)
         tokens = [int(t) for t in ref.argmax(axis=1)]
         lens = [L + 1 for L in lens]
-    # run-to-run: on the persistent layer kernel the split-K partial sums are added in a fixed order -> same bits every run; on the
-    # one-launch-per-GEMM path they meet in fp32 atomics and the logits may move in the last bits
+    # run-to-run: on the persistent layer kernel the split-K partial sums of the layers are added in a fixed order; what is left is the
+    # lm_head, which at THIS vocabulary (128 tiles < 4 per SM) splits its tiles over K and meets in fp32 atomics -- at Llama's 128 256
+    # rows every CTA owns whole tiles and bench.py's parity leg reports bit-identical logits.  The one-launch-per-GEMM path has
+    # atomics in every layer.
     prep = pkg.prepare_decode(lens, tokens, tables, cfg.block_size)
     a = model.decode(prep, want_logits=True)[1].copy()
     b_ = model.decode(prep, want_logits=True)[1]      # same inputs again (the step rewrites the same slots with the same values)
     spread = np.abs(a - b_).max() / np.abs(a).max()
     print(f"run-to-run spread {spread:.2e}")
-    assert spread == 0.0 if model.uses_layer_kernel(B) else spread < 1e-4
+    assert spread < (1e-6 if model.uses_layer_kernel(B) else 1e-4)
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
@@ -117,7 +119,7 @@ def test_decode_with_fp8_kv_cache_matches_oracle(use_graph):
     cfg = _small_cfg(block_size=64, max_blocks_per_seq=8)
     w = synthetic.make_weights(cfg, DEV, seed=0)
     ow = weights_to_oracle(w)
-    nb = 24
+    nb = 32
     eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim, pkg.CacheConfig(cfg.block_size, nb, kvcache_dtype="fp8"))
     synthetic.fill_kv_cache(eng.gpu_cache, seed=1)
     okc = [k.cpu().numpy().copy() for k, _ in eng.gpu_cache]          # u8 e4m3 bits
