@@ -1,5 +1,7 @@
 // attention_api.cu -- C ABI of paged attention (K1 decode, K2 prefill) and dispatch between the
 // TMA-staged split-KV decode kernel and the shape-generic kernel.
+#include <cstdlib>
+
 #include "attention.cuh"
 
 using namespace b200;
@@ -58,6 +60,13 @@ void paged_attention_prefill(void* out, const void* q, const void* key_cache, co
     B200_REQUIRE(dtype == B200_BF16 || dtype == B200_F16, kErrUnsupported, "paged_attention_prefill: dtype %d", dtype);
     const bool fp8 = cache_dtype == B200_FP8_E4M3 || cache_dtype == B200_U8;
     B200_REQUIRE(fp8 || cache_dtype == dtype, kErrUnsupported, "paged_attention_prefill: cache dtype");
+    static const bool force_generic = [] { const char* e = getenv("B200_PREFILL_GENERIC"); return e && atoi(e) != 0; }();
+    if (!force_generic && paged_attention_prefill_tc_supported(head_dim, block_size, dtype, cache_dtype, layout, softcap, 1, q, key_cache, value_cache)) {
+        // the ABI carries no block count (the reference's prefill entry has none either): the tensor map only needs an upper bound
+        paged_attention_prefill_tc(out, q, key_cache, value_cache, block_tables, cu_seqlens_q, cu_seqlens_k, num_seqs, total_q, num_heads, num_kv_heads,
+                                   max_blocks_per_seq, (int64_t)1 << 22, scale, sliding_window, dtype, as_stream(stream));
+        return;
+    }
     GenericAttnArgs a{block_tables, nullptr, cu_seqlens_q, cu_seqlens_k, num_seqs, num_heads, num_kv_heads, head_dim,
                       block_size, max_blocks_per_seq, scale, softcap, sliding_window, layout, 1};
     paged_attention_generic(out, q, key_cache, value_cache, a, total_q, dtype, cache_dtype, dtype, as_stream(stream));

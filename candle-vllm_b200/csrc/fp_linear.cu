@@ -116,8 +116,50 @@ fp_linear_kernel(const T* __restrict__ x, const Dec dec, const T* __restrict__ b
     }
 }
 
+// W -> 16-bit [n, k] in the activation dtype (one rounding of the exactly decoded weight): the "dequantise once" half of the prefill path
+template <typename Dec, typename T>
+__global__ void __launch_bounds__(256)
+fp_dequant_kernel(const Dec dec, T* __restrict__ out, int n, int k) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int P = Dec::kPer;
+    const int64_t per_row = k / P, total = (int64_t)n * per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / per_row), k0 = (int)(i - (int64_t)row * per_row) * P;
+        float wv[P];
+        dec.load(row, k0, wv);
+        T o[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) o[j] = from_f32<T>(wv[j]);
+#pragma unroll
+        for (int j = 0; j < P / 8; ++j) reinterpret_cast<uint4*>(out + (int64_t)row * k + k0)[j] = reinterpret_cast<const uint4*>(o)[j];
+    }
+}
+
+// Rows at or above this count (prefill chunks) dequantise the weights once into the library scratch and run the dense tcgen05 GEMM
+// (dense_gemm.cu) with the bias in its epilogue: every m-tile reuses the 16-bit copy instead of re-decoding the weights per 8 rows.
+constexpr int kDenseRows = 512;
+
+template <typename Dec>
+bool prefill_dense(const Dec& dec, const void* x, const void* bias, void* out, int m, int n, int k, int dtype, cudaStream_t st, const char* who) {
+    if (m < kDenseRows || k % Dec::kPer || k % 8 || n % 8) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    void* w16 = get_scratch((size_t)n * k * 2 + 256, st);
+    if (!w16) { if (cs == cudaStreamCaptureStatusNone) return false; b200_last_error(); return false; }     // capture with a cold scratch: SIMT path
+    int64_t g = ((int64_t)n * (k / Dec::kPer) + 255) / 256;
+    if (g > (int64_t)sm_count() * 16) g = (int64_t)sm_count() * 16;
+    if (dtype == B200_BF16) launch_pdl(fp_dequant_kernel<Dec, __nv_bfloat16>, dim3((int)g), dim3(256), 0, st, dec, (__nv_bfloat16*)w16, n, k);
+    else launch_pdl(fp_dequant_kernel<Dec, __half>, dim3((int)g), dim3(256), 0, st, dec, (__half*)w16, n, k);
+    count_launch();
+    if (!check_launch(who)) return true;
+    dense_gemm_16(x, w16, bias, out, m, n, k, k, k, n, dtype, dtype, st);
+    return true;
+}
+
 template <typename Dec>
 void launch(const Dec& dec, const void* x, const void* bias, void* out, int m, int n, int k, int dtype, cudaStream_t st, const char* who) {
+    if (prefill_dense(dec, x, bias, out, m, n, k, dtype, st, who)) return;
     const dim3 grid(ceil_div(n, kRows), ceil_div(m, kMT));
     if (dtype == B200_BF16)
         launch_pdl(fp_linear_kernel<Dec, __nv_bfloat16>, grid, dim3(kRows * 32), 0, st, (const __nv_bfloat16*)x, dec, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, m, n, k);
@@ -149,6 +191,10 @@ void fp8_matmul(const void* x, const void* weight, const float* weight_scale, co
     if (!common_check("fp8_matmul", x, weight, weight_scale, out, m, n, k, dtype, 16)) return;
     B200_REQUIRE(block_y > 0 && block_x > 0, kErrBadArg, "fp8_matmul: block sizes [%d, %d]", block_y, block_x);
     static const bool force_generic = [] { const char* e = getenv("B200_FP8_GENERIC"); return e && atoi(e) != 0; }();
+    if (!force_generic && m >= kDenseRows) {
+        const Fp8Dec dec{static_cast<const uint8_t*>(weight), weight_scale, k, block_y, block_x, (k + block_x - 1) / block_x};
+        if (prefill_dense(dec, x, bias, out, m, n, k, dtype, as_stream(stream), "fp8_matmul")) return;
+    }
     if (!force_generic && fp8_tc_supported(m > 64 ? 64 : m, n, k, block_y, block_x) && (((uintptr_t)out | (uintptr_t)weight_scale) & 7) == 0) {
         // tcgen05 pipeline (qmatmul_tc.cu), 64 rows per pass.  Scratch = fp16 copy of x (bf16 input) + fp32 partial-sum slabs + norm.
         cudaStream_t st = as_stream(stream);

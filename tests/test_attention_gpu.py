@@ -161,6 +161,44 @@ def test_prefill_chunked_matches_oracle():
     _check(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("H,kvh,qlens,cached,window", [
+    (8, 2, [70, 33, 200], [32, 0, 128], None),       # ragged chunks continuing cached prefixes (bottom-right causal mask)
+    (4, 4, [64, 1, 129], [0, 500, 63], None),         # exact tile, single row deep in a context, one row past two tiles
+    (8, 1, [300], [100], 96),                         # sliding window: pages entirely before the window are skipped
+    (32, 8, [1024], [1024], None),                    # Llama-3-8B head config, 1 K chunk on a 1 K cached prefix
+])
+def test_prefill_on_tensor_cores_matches_oracle(dtype, H, kvh, qlens, cached, window):
+    """Chunked prefill over the paged cache on the tensor-core kernel (block 64, head 128; csrc/attention_prefill.cu): every key and
+    value -- cached prefix and this chunk -- is read from the cache by TMA, one 64-token page per 64-row query tile.  Tolerance as
+    for decode (16-bit P and output).  The generic kernel (B200_PREFILL_GENERIC=1) must agree to the same tolerance."""
+    rng = np.random.default_rng(len(qlens) * 13 + H)
+    bs, hd = 64, 128
+    klens = [q + c for q, c in zip(qlens, cached)]
+    nblk = [-(-k // bs) for k in klens]
+    nb = sum(nblk) + 2
+    perm = rng.permutation(nb)
+    tables, o = [], 0
+    for n in nblk:
+        tables.append([int(x) for x in perm[o:o + n]]); o += n
+    prompts = [list(range(k)) for k in klens]
+    prep = pkg.prepare_prompt(prompts, tables, bs, cached, chunk_size=max(qlens))
+    T = len(prep["tokens"])
+    assert T == sum(qlens)
+    mk = lambda *shape: torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(DEV).to(dtype)
+    kc, vc = mk(nb, bs, kvh, hd), mk(nb, bs, kvh, hd)
+    kc[perm[-1]] = float("nan"); vc[perm[-1]] = float("nan")        # an unowned block: must never be touched
+    q, k, v = mk(T, H, hd), mk(T, kvh, hd), mk(T, kvh, hd)
+    kn, vn = kc.float().cpu().numpy(), vc.float().cpu().numpy()
+    _, _, meta = pkg.inputs.to_device(prep)
+    attn = pkg.PagedAttention(H, hd, hd ** -0.5, kvh, sliding_window=window)
+    out = attn.forward(q, k, v, None, kc, vc, meta)
+    OC.reshape_and_cache_flash(k.float().cpu().numpy(), v.float().cpu().numpy(), kn, vn, prep["slot_mapping"])
+    ref = OA.paged_attention_prefill(q.float().cpu().numpy(), kn, vn, prep["block_tables"], prep["cu_seqlens_q"], prep["cu_seqlens_k"],
+                                     hd ** -0.5, sliding_window=window)
+    _check(out, ref)
+
+
 def test_attention_argument_errors():
     attn = pkg.PagedAttention(8, 128, 0.1, 2)
     q = torch.zeros(2, 8, 128, dtype=torch.float32, device=DEV)

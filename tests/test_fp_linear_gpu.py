@@ -75,6 +75,28 @@ def test_nvfp4_and_mxfp4_matmul(dtype, m, n, k):
     assert rel_fro(y, ref) < TOL[dtype], rel_fro(y, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_prefill_chunks_dequantise_once_and_use_the_dense_tensor_core_gemm(dtype):
+    """m >= 512: weights -> 16 bit once (library scratch) + dense tcgen05 GEMM with the bias in its epilogue, for all three formats.
+    Tolerance: operands rounded to the activation dtype (weights once, exactly decoded first), fp32 accumulate, one output rounding:
+    rel-Frobenius 1e-3 (f16) / 6e-3 (bf16: 8-bit mantissa on weights, activations and output)."""
+    rng = np.random.default_rng(11)
+    m, n, k = 640, 512, 1024
+    tol = 1e-3 if dtype == torch.float16 else 6e-3
+    x, xf = _x(rng, m, k, dtype)
+    bias = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(DEV).to(dtype)
+    w, s = F.random_fp8(rng, n, k, 128, 128)
+    y = pkg.LnFp8(torch.from_numpy(w).to(DEV), torch.from_numpy(s).to(DEV), bias, (128, 128)).forward(x).float().cpu().numpy()
+    assert rel_fro(y, F.linear(xf, F.dequant_fp8_block(w, s, 128, 128), bias.float().cpu().numpy())) < tol
+    blocks = F.random_fp4(rng, n, k)
+    sc = F.random_nvfp4_scales(rng, n, k)
+    y = pkg.LnNvfp4(torch.from_numpy(blocks).to(DEV), torch.from_numpy(sc).to(DEV), 1.0 / 448.0, 1.0, bias).forward(x).float().cpu().numpy()
+    assert rel_fro(y, F.linear(xf, F.dequant_nvfp4(blocks, sc, 1.0 / 448.0), bias.float().cpu().numpy())) < tol
+    se = F.random_mxfp4_scales(rng, n, k)
+    y = pkg.LnMxfp4(torch.from_numpy(blocks).to(DEV), torch.from_numpy(se).to(DEV)).forward(x).float().cpu().numpy()
+    assert rel_fro(y, F.linear(xf, F.dequant_mxfp4(blocks, se))) < tol
+
+
 def test_fp_linear_argument_errors():
     w = torch.zeros((128, 256), dtype=torch.uint8, device=DEV)
     with pytest.raises(pkg.BackendError, match="weight_scale must be f32"):
