@@ -42,7 +42,10 @@ def parse():
     ap.add_argument("--ctx", type=int, default=4096, help="context length at the first decode step")
     ap.add_argument("--max-ctx", type=int, default=5120)
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers => number is INVALID")
-    ap.add_argument("--kv", default="bf16", choices=["bf16", "fp8"])
+    ap.add_argument("--kv", default=None, choices=["bf16", "fp8"])
+    ap.add_argument("--config", default="q4k", choices=["q4k", "dense_bf16", "gptq_fp8kv"],
+                    help="q4k = the metric (BASELINE config: Llama-3-8B Q4_K GGUF); dense_bf16 = BASELINE config 2 (Llama-3-8B BF16); "
+                         "gptq_fp8kv = BASELINE config 3 (GPTQ/Marlin int4 + FP8 KV).  The extra configs are single-GPU.")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--parity-steps", type=int, default=3, help="decode steps compared against a TP=1 engine before timing (0 = off)")
@@ -212,6 +215,17 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+CONFIGS = {
+    "q4k": dict(metric=METRIC, kv="bf16", dtype="f16 activations x q4_k/q6_k weights (fp32 accumulate), bf16 attention",
+                name="Llama-3-8B Q4_K (lm_head Q6_K)"),
+    "dense_bf16": dict(metric="decode tokens/s Llama-3-8B BF16 batch=32 (BASELINE config 2)", kv="bf16",
+                       dtype="bf16 activations x bf16 weights (fp32 accumulate, tcgen05 dense GEMM), bf16 attention", name="Llama-3-8B BF16 (dense)"),
+    "gptq_fp8kv": dict(metric="decode tokens/s Llama-3-8B GPTQ/Marlin int4 + FP8 KV batch=32 (BASELINE config 3)", kv="fp8",
+                       dtype="f16 activations x int4 weights g128 (fp32 accumulate), f16 attention over e4m3 KV",
+                       name="Llama-3-8B GPTQ int4 g128 (Marlin-prepared; lm_head Q6_K)"),
+}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -231,6 +245,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     comm = Comm(rank, world) if world > 1 else None
 
+    conf = CONFIGS[args.config]
+    if args.kv is None:
+        args.kv = conf["kv"]
+    if args.config != "q4k" and world > 1:
+        raise SystemExit(f"bench.py --config {args.config} is a single-GPU configuration")
     B, bs = args.batch, 64
     K, W = args.steps, args.warmup
     PS = args.parity_steps
@@ -247,14 +266,19 @@ def run_b200(args):
     def build(tp_rank, tp_world, nccl):
         """model + KV state for (tp_rank, tp_world): same seeds on every rank and for every tp_world, so a TP run and the TP = 1
         run see the same global weights and the same global KV cache (each rank holds its shard of both)."""
-        weights = synthetic.make_weights(cfg, dev, seed=0, tp_rank=tp_rank, tp_world=tp_world)
+        if args.config == "dense_bf16":
+            weights = synthetic.make_weights_16bit(cfg, dev, seed=0, dtype=torch.bfloat16)
+        elif args.config == "gptq_fp8kv":
+            weights, _ = synthetic.make_weights_gptq(cfg, dev, seed=0, group_size=128, dtype=torch.float16, with_oracle=False)
+        else:
+            weights = synthetic.make_weights(cfg, dev, seed=0, tp_rank=tp_rank, tp_world=tp_world)
         eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim,
                               pkg.CacheConfig(bs, num_blocks, kvcache_dtype="fp8" if args.kv == "fp8" else "auto"),
                               device=dev, num_shards=tp_world)
         synthetic.fill_kv_cache(eng.gpu_cache, seed=1, tp_rank=tp_rank, tp_world=tp_world, num_kv_heads=cfg.num_kv_heads)
         torch.cuda.synchronize()
         model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, tp_rank=tp_rank, tp_world=tp_world, nccl_comm=nccl,
-                              stream=stream)
+                              stream=stream, rope_neox=args.config != "q4k")
         return model, eng, weights
 
     model, eng, weights = build(rank, world, comm.handle.value if comm else None)
@@ -299,7 +323,8 @@ def run_b200(args):
         barrier()
         if rank == 0:
             if world == 1:
-                ref_model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, use_graph=False, stream=stream)
+                ref_model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, use_graph=False, stream=stream,
+                                          rope_neox=args.config != "q4k")
                 ref_eng = None                                      # same cache: the steps rewrite the same slots with the same values
             else:
                 ref_model, ref_eng, ref_w = build(0, 1, None)
@@ -372,7 +397,7 @@ def run_b200(args):
 
     # ---- (3) rooflines: paged-attention decode alone per layer; the weight stream of all projections alone ---------
     roof = attention_roofline(pkg, model, cfg, eng, B, cur, tables, world, stream, dev)
-    roof_gemm = gemm_roofline(model, cfg, B, world, stream)
+    roof_gemm = gemm_roofline(model, cfg, B, world, stream, args.config)
     peer_ar = inboxes is not None and inboxes.active
     if inboxes is not None:
         timed_out = inboxes.timed_out()
@@ -393,10 +418,10 @@ def run_b200(args):
     src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s"
     roof.update(peak=hbm_peak, peak_source=src, frac=roof["achieved"] / hbm_peak)
     roof_gemm.update(peak=hbm_peak, peak_source=src, frac=roof_gemm["achieved"] / hbm_peak)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+    line = {"metric": conf["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f16 activations x q4_k/q6_k weights (fp32 accumulate), bf16 attention", "data": "synthetic",
-            "config": {"workload": f"Llama-3-8B Q4_K (lm_head Q6_K) decode, batch {B}, ctx {ctx_first}->{ctx_last} of 4096->5120, "
+            "dtype": conf["dtype"], "data": "synthetic",
+            "config": {"workload": f"{conf['name']} decode, batch {B}, ctx {ctx_first}->{ctx_last} of 4096->5120, "
                                    f"block_size {bs}, {args.kv} paged KV, random non-contiguous block tables",
                        "parallelism": f"tp{world}" + ("" if world == 1 else (" (fused all-reduce + add + norm over NVLink peer memory)" if peer_ar else " (NCCL all-reduce)")), "global_batch": B, "layers": cfg.num_layers,
                        "l2_policy": "inputs larger than L2 (KV 17+ GB and weights 4.4 GB streamed per step; 126 MB L2)"},
@@ -411,7 +436,7 @@ def run_b200(args):
         line["parity"] = parity
     if cfg.num_layers != 32:
         line["invalid"] = "debug run with fewer layers"
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.config == "q4k":      # the CPU arm is the reference's GGUF/GGML path
         tps, t_step, info = cpu_decode_sample(B, args.ctx, args.cpu_seconds)
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, **info}
     print(json.dumps(line), flush=True)
@@ -450,16 +475,20 @@ def ncu_traffic(csv_name: str, kernel_substr: str):
     return None, None
 
 
-def gemm_roofline(model, cfg, B, world, stream):
+def gemm_roofline(model, cfg, B, world, stream, config="q4k"):
     """The weight stream alone: every quantised projection of every layer + the lm_head + the small ops between them, without
     RoPE / cache write / attention (b200_llama_linear_chain), timed eagerly with CUDA events on the launching stream.  4.36 GB
     of weights per pass at TP = 1: far beyond the 126 MB L2."""
     import torch
     H, F, V = cfg.hidden, cfg.ffn, cfg.vocab
     qd, kd = cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim
-    q4 = (H * (qd + 2 * kd) + qd * H + 3 * H * F) * cfg.num_layers * 144 // 256
-    q6 = V * H * 210 // 256
-    alg = (q4 + q6) // world
+    params = (H * (qd + 2 * kd) + qd * H + 3 * H * F) * cfg.num_layers
+    if config == "dense_bf16":
+        alg = (params + V * H) * 2
+    elif config == "gptq_fp8kv":
+        alg = params // 2 + params // 128 * 2 + V * H * 210 // 256        # int4 + one f16 scale per 128 weights; lm_head Q6_K
+    else:
+        alg = (params * 144 // 256 + V * H * 210 // 256) // world
     with torch.cuda.stream(stream):
         for _ in range(3):
             model.linear_chain(B)
@@ -474,7 +503,7 @@ def gemm_roofline(model, cfg, B, world, stream):
     ms = e0.elapsed_time(e1) / reps
     return {"kernel": "all quantised projections of one decode step (QKV, wo, gate|up, w2 per layer + lm_head) incl. norm / SiLU between them, eager launches",
             "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
-            "ms_per_launch": ms, "launch": "one pass over all layers (weights 4.36 GB / world)",
+            "ms_per_launch": ms, "launch": f"one pass over all layers (weights {alg / 1e9:.2f} GB on this rank)",
             "traffic": None}
 
 

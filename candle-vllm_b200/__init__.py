@@ -15,7 +15,7 @@ from .backend import (  # noqa: F401
 )
 from .cache_engine import CacheConfig, CacheEngine  # noqa: F401
 from .inputs import prepare_decode, prepare_prompt, used_blocks_for_len, PAD_SLOT_ID  # noqa: F401
-from .llama import LlamaConfig, GGUFLLaMa  # noqa: F401
+from .llama import LlamaConfig, GGUFLLaMa, MarlinWeight  # noqa: F401
 from .block_manager import BlockManager, PrefixCache, PrefixCacheConfig, Seq, SeqGroup, AllocStatus  # noqa: F401
 from .gptq import gptq_matmul, marlin_weight_repack, marlin_permute_scales  # noqa: F401
 from .linear import QLinear  # noqa: F401

@@ -46,16 +46,18 @@ constexpr int kSubTileBytes = kTile * 64 * 2;             // 32 tokens x 64 dims
 constexpr int kMaxSeqs = 1024;
 
 // Shared-memory plan.  16-bit KV: 6 independent warp pipelines x 2 stages of 16 KB (K lo, K hi, V lo, V hi sub-tiles) = 192 KB of KV
-// reads in flight per SM.  FP8 (e4m3) KV: a tile is half the bytes (one 4 KB box for K, one for V: 32 tokens x 128 B), so the ring
-// is 3 stages of 8 KB per warp, plus one 16 KB f16 staging tile per warp into which the warp expands a landed stage (cvt e4m3x2 ->
-// f16x2, exact) in the sub-tile layout the ldmatrix code below reads; 5 warps x (24 + 16) KB = 200 KB, 120 KB of reads in flight.
+// reads in flight per SM.  FP8 (e4m3) KV: a tile is half the bytes (one 4 KB box for K, one for V: 32 tokens x 128 B) and has to be
+// expanded to f16 (cvt e4m3x2 -> f16x2, exact) into the sub-tile layout the ldmatrix code reads -- per-warp latency, not bytes, sets
+// the pace (ncu: 26 % issue-active with 5 warps), so the plan maximises resident warps: 2 stages of 8 KB + ONE 8 KB f16 staging tile
+// per warp (K is expanded, S = Q K^T runs, then V is expanded into the same tile) = 24 KB -> 8 warps (256 threads keep the full
+// 255-register budget; 9 warps would be capped at 168 and spill), 128 KB of reads in flight.
 template <bool kFp8>
 struct Plan {
-    static constexpr int kWarps = kFp8 ? 5 : 6;
-    static constexpr int kStages = kFp8 ? 3 : 2;
+    static constexpr int kWarps = kFp8 ? 8 : 6;
+    static constexpr int kStages = 2;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kStageBytes = kFp8 ? 2 * kTile * kHeadDim : 4 * kSubTileBytes;      // 8 KB / 16 KB
-    static constexpr int kConvBytes = kFp8 ? 4 * kSubTileBytes : 0;                          // f16 staging tile per warp
+    static constexpr int kConvBytes = kFp8 ? 2 * kSubTileBytes : 0;                          // f16 staging tile per warp (K, then V)
     static constexpr int kWarpBytes = kStages * kStageBytes + kConvBytes;
     // stages first (1024-byte aligned for the 128B swizzle): [warp][stage...][conv]
     static constexpr int kBars = kWarps * kWarpBytes;                               // full[kWarps][kStages]
@@ -289,35 +291,34 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         for (int tl = 0; tl < ntiles; ++tl) {
             const int s = consumed % kStagesPerWarp;
             mbar_wait(my_bars + s * 8, (consumed / kStagesPerWarp) & 1);
-            uint32_t kt = my_stages + s * kStageBytes;
-            if constexpr (kFp8) {
-                // expand the landed stage (K then V: 32 tokens x 128 e4m3 each, 128-byte swizzled rows) into this warp's f16 tile:
-                // lane -> one 16-byte chunk (16 dims) per step = two 16-byte f16 chunks of sub-tile (dim / 64), same swizzle
-                const uint8_t* raw = smem + (kt - smem_base);
+            uint32_t kt = my_stages + s * kStageBytes, vt = kt + 2 * kSubTileBytes;
+            // kFp8: expand 32 tokens x 128 e4m3 (128-byte swizzled rows at `raw`) into this warp's f16 staging tile: a lane takes one
+            // 16-byte chunk (16 dims) per step and writes two 16-byte f16 chunks of sub-tile (dim / 64), same XOR swizzle
+            auto expand = [&](const uint8_t* raw) {
                 uint8_t* conv = smem + (my_conv - smem_base);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int id = (i & 7) * 32 + lane, row = id >> 3, rc = id & 7;
-                    const uint4 v = *reinterpret_cast<const uint4*>(raw + (i >> 3) * (kTile * kHeadDim) + row * 128 + ((rc ^ (row & 7)) << 4));
+                for (int i = 0; i < 8; ++i) {
+                    const int id = i * 32 + lane, row = id >> 3, rc = id & 7;
+                    const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((rc ^ (row & 7)) << 4));
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                     uint32_t o[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[j] & 0xffffu), __NV_E4M3);
-                        const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(w[j] >> 16), __NV_E4M3);
-                        o[2 * j] = (uint32_t)lo.x | ((uint32_t)lo.y << 16);
-                        o[2 * j + 1] = (uint32_t)hi.x | ((uint32_t)hi.y << 16);
+                        // two e4m3 -> one packed f16x2 register per cvt; the 16-bit halves of w[j] are register sub-words (no byte permutes)
+                        asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\ncvt.rn.f16x2.e4m3x2 %0, lo;\ncvt.rn.f16x2.e4m3x2 %1, hi;\n}\n"
+                            : "=r"(o[2 * j]), "=r"(o[2 * j + 1]) : "r"(w[j]));
                     }
-                    uint8_t* dst = conv + ((i >> 3) * 2 + (rc >> 2)) * kSubTileBytes + row * 128;
+                    uint8_t* dst = conv + (rc >> 2) * kSubTileBytes + row * 128;
                     const int c0 = (2 * rc) & 7;
                     *reinterpret_cast<uint4*>(dst + ((c0 ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                     *reinterpret_cast<uint4*>(dst + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
                 }
                 __syncwarp();
-                issue_one();                                 // the raw stage is free again: refill it now (tile consumed + kStages)
+            };
+            if constexpr (kFp8) {
+                expand(smem + (kt - smem_base));             // K
                 kt = my_conv;
             }
-            const uint32_t vt = kt + 2 * kSubTileBytes;
             const int valid = min(kTile, ctx - (c * chunk_tokens + tl * kTile));
 
             // ---- S = Q K^T : 4 n-tiles (8 tokens each) x 8 k-steps --------------------------------
@@ -364,6 +365,12 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             if (corr != 1.f) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
+            }
+            if constexpr (kFp8) {
+                __syncwarp();                                    // every lane is done reading K from the staging tile
+                expand(smem + (my_stages + s * kStageBytes - smem_base) + kTile * kHeadDim);      // V
+                vt = my_conv;
+                issue_one();                                     // the raw stage is free: refill it (tile consumed + kStages)
             }
             // V rows past the context may hold non-finite garbage: 0 * NaN would poison O
             if (valid < kTile) {

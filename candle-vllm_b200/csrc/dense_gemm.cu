@@ -70,6 +70,8 @@ struct DenseParams {
     int tiles_a, tiles_b;          // tiles of the 128-row operand / of the BN-row operand
     int swap;                      // 1: A = weights (rows = n), B = activations (rows = m); output transposed on the way out
     int out_dtype, bf16;
+    int ksplit;                    // swap mode, f32 output: the k range is cut into ksplit parts per tile (more CTAs than weight tiles); partial
+    int accumulate;                // sums meet in y through fp32 atomics.  accumulate: y += result (f32 output)
 };
 
 template <typename TOut>
@@ -121,11 +123,17 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     const uint32_t tmem = *tmem_slot;
     pdl_trigger();
 
-    const int n_tiles = p.tiles_a * p.tiles_b;
-    const int nkb = (p.k + kBK - 1) / kBK;
+    const int n_tiles = p.tiles_a * p.tiles_b * p.ksplit;
+    const int nkb_all = (p.k + kBK - 1) / kBK;
     // tile order: bands of 8 A-tiles; inside a band the B-tile index is the slow one, so the CTAs running together (consecutive tile
     // ids) work on the same B tile (weights, or activations when swapped) and neighbouring A tiles -> both stay in L2
+    // split-K (swap mode only): tile id = (weight tile, k part); part z owns k blocks [nkb_all * z / ksplit, nkb_all * (z + 1) / ksplit)
+    auto k_range = [&](int t, int& kb0, int& kb1) {
+        const int z = p.ksplit > 1 ? t % p.ksplit : 0;
+        kb0 = nkb_all * z / p.ksplit; kb1 = nkb_all * (z + 1) / p.ksplit;
+    };
     auto tile_coords = [&](int t, int& ta, int& tb) {
+        if (p.ksplit > 1) { ta = t / p.ksplit; tb = 0; return; }
         constexpr int kBand = 8;
         const int per_band = kBand * p.tiles_b;
         const int band = t / per_band, r = t - band * per_band;
@@ -142,9 +150,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
         int it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            int ta, tb;
+            int ta, tb, kb0, kb1;
             tile_coords(t, ta, tb);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
+            k_range(t, kb0, kb1);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % kS;
                 mbar_wait(empty(s), ((it / kS) & 1) ^ 1);
                 if (leader) {
@@ -171,7 +180,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             mbar_wait(tmem_empty(ab), ((tcount >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_t = tmem + ab * kBN;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
+            int kb0, kb1;
+            k_range(t, kb0, kb1);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 const int s = it % kS;
                 mbar_wait(full(s), (it / kS) & 1);
                 tc_fence_after();
@@ -180,7 +191,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                 if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < kBK / 16; ++ks)
-                        tc_mma_ss(d_t, ad0 + (uint64_t)(ks * 2), bd0 + (uint64_t)(ks * 2), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma_ss(d_t, ad0 + (uint64_t)(ks * 2), bd0 + (uint64_t)(ks * 2), idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
                     tc_commit(empty(s));
                 }
                 __syncwarp();
@@ -214,6 +225,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                     // y[ia][jb .. jb+32): this lane owns a row, 32 consecutive columns
                     if (ia < p.m) {
                         TOut* dst = static_cast<TOut*>(p.y) + (int64_t)ia * p.ldy + jb;
+                        if constexpr (sizeof(TOut) == 4) {
+                            if (p.accumulate) {         // y += : this CTA owns the tile exclusively (no split-K here), plain read-modify-write
+                                for (int i = 0; i < 32; ++i)
+                                    if (jb + i < p.n) dst[i] = dst[i] + __uint_as_float(acc[i]) + (bias ? to_f32(bias[jb + i]) : 0.f);
+                                continue;
+                            }
+                        }
                         if (jb + 32 <= p.n && (((uintptr_t)dst) & 15) == 0) {
                             store_row16<TOut>(dst, acc, bias ? bias + jb : nullptr, bias != nullptr);
                             store_row16<TOut>(dst + 16, acc + 16, bias ? bias + jb + 16 : nullptr, bias != nullptr);
@@ -225,10 +243,18 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                 } else {
                     // swapped: the lane owns output COLUMN ia (a weight row); y[jb + i][ia]: lanes -> consecutive addresses
                     if (ia < p.n) {
-                        const float bv = bias ? to_f32(bias[ia]) : 0.f;
+                        const bool first_part = p.ksplit <= 1 || (t % p.ksplit) == 0;
+                        const float bv = (bias && first_part) ? to_f32(bias[ia]) : 0.f;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (jb + i < p.m) static_cast<TOut*>(p.y)[(int64_t)(jb + i) * p.ldy + ia] = from_f32<TOut>(__uint_as_float(acc[i]) + bv);
+                        for (int i = 0; i < 32; ++i) {
+                            if (jb + i < p.m) {
+                                TOut* o = static_cast<TOut*>(p.y) + (int64_t)(jb + i) * p.ldy + ia;
+                                if constexpr (sizeof(TOut) == 4) {
+                                    if (p.ksplit > 1 || p.accumulate) { atomicAdd(o, __uint_as_float(acc[i]) + bv); continue; }
+                                }
+                                *o = from_f32<TOut>(__uint_as_float(acc[i]) + bv);
+                            }
+                        }
                     }
                 }
             }
@@ -279,7 +305,7 @@ template <int kBN, typename TOut>
 void launch_dense(const CUtensorMap& am, const CUtensorMap& bm, const DenseParams& p, cudaStream_t st) {
     auto kern = dense_gemm_kernel<kBN, TOut>;
     ensure_dynamic_smem(reinterpret_cast<const void*>(kern), DCfg<kBN>::kTotal);
-    const int tiles = p.tiles_a * p.tiles_b;
+    const int tiles = p.tiles_a * p.tiles_b * p.ksplit;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     launch_pdl(kern, dim3(grid), dim3(kGemmThreads), DCfg<kBN>::kTotal, st, am, bm, p);
     count_launch();
@@ -297,7 +323,7 @@ void launch_out(const CUtensorMap& am, const CUtensorMap& bm, const DenseParams&
 // y[m, n] (out_dtype f16 / bf16 / f32, row pitch ldy) = x[m, k] . w[n, k]^T (+ bias[n], of out_dtype); x and w of `dtype` (f16 / bf16),
 // row pitches ldx / ldw elements.  k % 8 == 0, 16-byte aligned bases and pitches (TMA).
 bool dense_gemm_16(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int64_t ldx, int64_t ldw, int64_t ldy,
-                   int dtype, int out_dtype, cudaStream_t st) {
+                   int dtype, int out_dtype, cudaStream_t st, int accumulate, int allow_split_k) {
     if (m <= 0 || n <= 0 || k <= 0) return true;
     if (dtype != B200_F16 && dtype != B200_BF16) { set_error(kErrUnsupported, "dense_gemm: operand dtype %d (f16 / bf16)", dtype); return false; }
     if (out_dtype != B200_F16 && out_dtype != B200_BF16 && out_dtype != B200_F32) { set_error(kErrUnsupported, "dense_gemm: out dtype %d", out_dtype); return false; }
@@ -308,10 +334,20 @@ bool dense_gemm_16(const void* x, const void* w, const void* bias, void* y, int 
     const bool bf16 = dtype == B200_BF16;
     DenseParams p{};
     p.y = y; p.bias = bias; p.m = m; p.n = n; p.k = k; p.ldy = ldy; p.out_dtype = out_dtype; p.bf16 = bf16 ? 1 : 0;
+    p.ksplit = 1; p.accumulate = accumulate ? 1 : 0;
+    if (accumulate && out_dtype != B200_F32) { set_error(kErrUnsupported, "dense_gemm: accumulate needs f32 output"); return false; }
     CUtensorMap am, bm;
     if (m <= 64) {                       // swap-AB: weights are the 128-row operand
         const int bn = m <= 32 ? 32 : 64;
         p.swap = 1; p.tiles_a = (n + kBM - 1) / kBM; p.tiles_b = 1;
+        // decode sizes are a pure weight stream: with fewer weight tiles than SMs, cut k so that every SM streams a part (f32 output
+        // pre-zeroed by the caller, or accumulate: the parts meet in fp32 atomics)
+        if (allow_split_k && out_dtype == B200_F32 && p.tiles_a < sm_count()) {
+            const int nkb = (k + kBK - 1) / kBK;
+            int ks = sm_count() / p.tiles_a;
+            if (ks > nkb / 4) ks = nkb / 4;
+            if (ks > 1) p.ksplit = ks;
+        }
         if (!make_map(&am, w, n, k, ldw, kBM, bf16) || !make_map(&bm, x, m, k, ldx, bn, bf16)) return false;
         if (bn == 32) launch_out<32>(am, bm, p, st); else launch_out<64>(am, bm, p, st);
     } else {
@@ -333,7 +369,7 @@ extern "C" {
 void linear_16bit(const void* x, const void* weight, const void* bias, void* out, int32_t m, int32_t n, int32_t k, int32_t dtype, int64_t stream) {
     if (m == 0 || n == 0) return;
     B200_REQUIRE(x && weight && out && m > 0 && n > 0 && k > 0, kErrBadArg, "linear_16bit: bad arguments");
-    dense_gemm_16(x, weight, bias, out, m, n, k, k, k, n, dtype, dtype, as_stream(stream));
+    dense_gemm_16(x, weight, bias, out, m, n, k, k, k, n, dtype, dtype, as_stream(stream), 0, 0);
 }
 
 }  // extern "C"

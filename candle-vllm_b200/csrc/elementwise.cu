@@ -518,6 +518,16 @@ void rope_and_cache_slabs(float* qkv, const SlabInfo& si, void* q_out, void* key
                        interleaved, dtype, cache_dtype, false, stream);
 }
 
+// act = silu(gate) * up in the activation format the next linear reads (fp16 K4, or natural f16 / bf16); gate / up re-zeroed
+void silu_mul_zero_src_fmt(float* gate, float* up, void* out, int64_t numel, int fmt, int64_t stream) {
+    if (fmt == B200_F16_K4) launch_pdl(silu_mul_kernel<__half, true, true>, dim3(ew_grid(numel)), dim3(256), 0, as_stream(stream), gate, up, (__half*)out, numel);
+    else if (fmt == B200_F16) launch_pdl(silu_mul_kernel<__half, false, true>, dim3(ew_grid(numel)), dim3(256), 0, as_stream(stream), gate, up, (__half*)out, numel);
+    else if (fmt == B200_BF16) launch_pdl(silu_mul_kernel<__nv_bfloat16, false, true>, dim3(ew_grid(numel)), dim3(256), 0, as_stream(stream), gate, up, (__nv_bfloat16*)out, numel);
+    else { set_error(kErrUnsupported, "silu_mul: activation format %d", fmt); return; }
+    count_launch();
+    check_launch("silu_mul");
+}
+
 void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, int64_t stream) {
     launch_pdl(silu_mul_kernel<__half, true, true>, dim3(ew_grid(numel)), dim3(256), 0, as_stream(stream), gate, up, (__half*)out_f16_k4, numel);
     count_launch();

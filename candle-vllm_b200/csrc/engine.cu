@@ -44,11 +44,12 @@ void argmax_reduce_pairs(const void* gathered, int32_t* out, int rows, int world
 
 struct b200_llama {
     b200_llama_config cfg;
-    std::vector<b200_llama_layer> layers;
+    std::vector<b200_llama_layer_ex> layers;
     const float* tok_embeddings = nullptr;
     const float* norm = nullptr;
-    const void* output_w = nullptr;
-    int output_type = 0;
+    b200_linear output{};                     // lm_head
+    int rope_neox = 0;
+    float* lin_scratch = nullptr; size_t lin_scratch_bytes = 0;     // fp32 partial-sum slabs of the int4 GEMMs
     std::vector<void*> kc, vc;
     int64_t num_blocks = 0;
     void* comm = nullptr;
@@ -131,6 +132,32 @@ __global__ void zero_f32_kernel(float* p, int64_t n) {
 }
 
 // One decode forward on `st` for B sequences.  Returns number of kernel launches issued.
+// ---- one linear of the decode engine: y[B, n] (f32, row pitch ldy) (+)= x16[B, k] . W[n, k]^T, whatever the weight kind ---------------
+// Activation format by kind (all linears of a model share it, checked in b200_llama_set_layer_ex): GGML / MARLIN4 read fp16 in K4
+// order, DENSE16 reads the weights' dtype in natural order.  accumulate = 0 with a GGML weight may still split tiles over K and
+// red.add: y must be zero then (the engine's consumers leave their inputs zeroed).
+int act_format(const b200_llama* m) {
+    const b200_linear& l = m->layers[0].wq;
+    return l.kind == B200_LIN_DENSE16 ? l.type : B200_F16_K4;
+}
+void linear(b200_llama* m, const b200_linear& l, const void* x16, float* y, int64_t ldy, int B, int n, int k, int accumulate, cudaStream_t st) {
+    switch (l.kind) {
+        case B200_LIN_GGML: qmatmul_dispatch(x16, l.w, y, ldy, B, n, k, l.type, accumulate, st); break;
+        case B200_LIN_MARLIN4: marlin_tc_f32(x16, l.w, l.scales, l.type == B200_BF16, l.zeros, y, ldy, B, n, k, l.group_size, accumulate, m->lin_scratch, st); break;
+        case B200_LIN_DENSE16: dense_gemm_16(x16, l.w, nullptr, y, B, n, k, k, k, ldy, l.type, B200_F32, st, accumulate, /*allow_split_k=*/1); break;
+        default: set_error(kErrUnsupported, "engine: linear kind %d", l.kind);
+    }
+}
+void lm_head(b200_llama* m, int B, cudaStream_t st) {
+    const int H = m->cfg.hidden;
+    const b200_linear& o = m->output;
+    const bool ggml_tc = o.kind == B200_LIN_GGML && qmatmul_tc_supported(B, m->vocab_l, H, o.type);
+    if ((ggml_tc && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) || o.kind == B200_LIN_DENSE16) {      // split tiles meet in y through atomics
+        launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
+    }
+    linear(m, o, m->xn, m->logits, m->vocab_l, B, m->vocab_l, H, 0, st);
+}
+
 // ---- forward on the persistent layer kernel (layer_mega.cu) --------------------------------------------------------------------
 // Per layer: {RoPE + cache write, attention, merge, ONE launch for wo -> +x, norm -> gate|up -> SiLU -> w2 -> +x, norm -> QKV of the
 // next layer}.  Split-K partial sums travel in slabs and are added in slab order by their consumer: bitwise reproducible.
@@ -140,9 +167,10 @@ bool mega_usable(const b200_llama* m, int B) {
     if (c.tp_world > 1 && (int)m->peers.size() != c.tp_world) return false;          // NCCL all-reduce: legacy launches
     if (!mega_supported(B, c.hidden, std::max(c.hidden, m->ffn_l))) return false;
     if ((m->heads_l * c.head_dim) % 256 || m->ffn_l % 256 || c.head_dim % 32) return false;
+    if (m->rope_neox) return false;
     for (const auto& w : m->layers)
-        for (int t : {w.tq, w.tk, w.tv, w.to, w.t1, w.t2, w.t3})
-            if (t != B200_GGML_Q4_K) return false;
+        for (const b200_linear* l : {&w.wq, &w.wk, &w.wv, &w.wo, &w.w1, &w.w2, &w.w3})
+            if (l->kind != B200_LIN_GGML || l->type != B200_GGML_Q4_K) return false;
     return true;
 }
 
@@ -172,10 +200,12 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         P.timeout_word = m->d_timeout;
         if (fused_ar) for (int i = 0; i < c.tp_world; ++i) P.peers.p[i] = static_cast<char*>(m->peers[i]);
         P.trace = launch == m->mega_trace_launch ? m->mega_trace : nullptr;
+        static const int trig = [] { const char* e = getenv("B200_MEGA_TRIGGER"); return e ? atoi(e) : 1; }();
+        P.early_trigger = trig;
     };
-    auto qkv_phase = [&](MegaParams& P, MegaPhase& ph, const b200_llama_layer& w, int map0) -> bool {
-        if (!mega_make_w_map(&P.maps[map0], w.wq, qd, H) || !mega_make_w_map(&P.maps[map0 + 1], w.wk, kd, H) ||
-            !mega_make_w_map(&P.maps[map0 + 2], w.wv, kd, H)) return false;
+    auto qkv_phase = [&](MegaParams& P, MegaPhase& ph, const b200_llama_layer_ex& w, int map0) -> bool {
+        if (!mega_make_w_map(&P.maps[map0], w.wq.w, qd, H) || !mega_make_w_map(&P.maps[map0 + 1], w.wk.w, kd, H) ||
+            !mega_make_w_map(&P.maps[map0 + 2], w.wv.w, kd, H)) return false;
         ph.w_map[0] = map0; ph.w_map[1] = map0 + 1; ph.w_map[2] = map0 + 2;
         ph.n[0] = qd; ph.n[1] = kd; ph.n[2] = kd;
         ph.tile_end[0] = tiles(qd); ph.tile_end[1] = tiles(qd) + tiles(kd); ph.tile_end[2] = tiles(qd) + 2 * tiles(kd);
@@ -200,7 +230,7 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         mega_launch(P, st);
     }
     for (int l = 0; l < L; ++l) {
-        const b200_llama_layer& w = m->layers[l];
+        const b200_llama_layer_ex& w = m->layers[l];
         if (!linear_only) {
             rope_and_cache_slabs(m->qkv_slabs, qkv_si, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
                                  m->heads_l, m->kv_l, hd, /*interleaved=*/1, B200_BF16, c.kv_dtype, s);
@@ -212,8 +242,8 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         base_params(P, l + 1);
         // maps: 0 attn16 [B, qd], 1 xn [B, H], 2 act16 [B, F], 3 wo, 4 w1, 5 w3, 6 w2, 7..9 q, k, v of the next layer
         if (!mega_make_x_map(&P.maps[0], m->attn16, B, qd) || !mega_make_x_map(&P.maps[1], m->xn, B, H) ||
-            !mega_make_x_map(&P.maps[2], m->act16, B, F) || !mega_make_w_map(&P.maps[3], w.wo, H, qd) ||
-            !mega_make_w_map(&P.maps[4], w.w1, F, H) || !mega_make_w_map(&P.maps[5], w.w3, F, H) || !mega_make_w_map(&P.maps[6], w.w2, H, F)) return 0;
+            !mega_make_x_map(&P.maps[2], m->act16, B, F) || !mega_make_w_map(&P.maps[3], w.wo.w, H, qd) ||
+            !mega_make_w_map(&P.maps[4], w.w1.w, F, H) || !mega_make_w_map(&P.maps[5], w.w3.w, F, H) || !mega_make_w_map(&P.maps[6], w.w2.w, H, F)) return 0;
         const int norm_op = fused_ar ? kEopTpNorm : kEopNorm;
         MegaPhase& a = P.phase[0];        // x (+)= wo(attn): partial sums -> ro_slabs
         a.x_map = 0; a.w_map[0] = a.w_map[1] = a.w_map[2] = 3; a.n[0] = a.n[1] = a.n[2] = H;
@@ -241,10 +271,7 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         P.n_phases = 4;
         mega_launch(P, st);
     }
-    if (qmatmul_tc_supported(B, m->vocab_l, H, m->output_type) && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) {
-        launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
-    }
-    qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
+    lm_head(m, B, st);
     const int live_cols = std::max(0, std::min(m->vocab_l, c.vocab - c.tp_rank * m->vocab_l));
     argmax_pairs(m->logits, m->tp_pairs, B, m->vocab_l, live_cols, kArgmaxChunks, c.tp_rank * m->vocab_l, st);
     if (c.tp_world == 1) {
@@ -269,67 +296,76 @@ int forward(b200_llama* m, int B, cudaStream_t st, bool linear_only = false) {
     embedding_f32(m->tok_embeddings, m->d_tokens, m->x, B, H, s);
     // tensor parallel with peer inboxes: the all-reduce of the row-parallel GEMMs, the residual add and the NEXT RMSNorm are
     // one kernel over NVLink peer memory (tp.cu); `partial` is left zeroed by that kernel for the next split-K GEMM
-    const bool fused_ar = c.tp_world > 1 && (int)m->peers.size() == c.tp_world;
+    const bool fused_ar = c.tp_world > 1 && (int)m->peers.size() == c.tp_world && act_format(m) == B200_F16_K4;
     auto residual_fused = [&](const float* next_norm) {
         tp_allreduce_add_norm(m->partial, m->x, next_norm, m->xn, m->peers.data(), c.tp_rank, c.tp_world, B, H, c.max_num_seqs, c.rms_eps, m->d_timeout, st);
     };
+    const int fmt = act_format(m);                      // what the linears read: fp16 K4 (GGML, int4) or the dense weights' dtype
+    const bool all_ggml = [&] {
+        for (const auto& w : m->layers)
+            for (const b200_linear* q : {&w.wq, &w.wk, &w.wv, &w.w1, &w.w3}) if (q->kind != B200_LIN_GGML) return false;
+        return true;
+    }();
     for (int l = 0; l < c.num_layers; ++l) {
-        const b200_llama_layer& w = m->layers[l];
-        if (!fused_ar || l == 0) rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
+        const b200_llama_layer_ex& w = m->layers[l];
+        if (!fused_ar || l == 0) rms_norm(m->x, w.attn_norm, m->xn, B, H, c.rms_eps, fmt, s);
         // QKV / gate / up accumulate (split-K) into buffers that their consumers leave zeroed
-        {   // fused QKV: three weight matrices, one launch
-            const void* ws[3] = {w.wq, w.wk, w.wv};
-            const int ts[3] = {w.tq, w.tk, w.tv}, ns[3] = {qd, kd, kd};
+        if (all_ggml) {   // fused QKV: three weight matrices, one launch
+            const void* ws[3] = {w.wq.w, w.wk.w, w.wv.w};
+            const int ts[3] = {w.wq.type, w.wk.type, w.wv.type}, ns[3] = {qd, kd, kd};
             float* ys[3] = {m->qkv, m->qkv + qd, m->qkv + qd + kd};
             // accumulate = 0: whole tiles are plain stores, split tiles red.add into the zeroed buffer
             qmatmul_dispatch_multi(m->xn, 3, ws, ts, ys, ns, m->qkv_row, B, H, 0, st);
+        } else {
+            linear(m, w.wq, m->xn, m->qkv, m->qkv_row, B, qd, H, 0, st);
+            linear(m, w.wk, m->xn, m->qkv + qd, m->qkv_row, B, kd, H, 0, st);
+            linear(m, w.wv, m->xn, m->qkv + qd + kd, m->qkv_row, B, kd, H, 0, st);
         }
         if (linear_only) { launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->qkv, (int64_t)B * m->qkv_row); count_launch(); } else {
         // (also re-zeroes qkv: the split-K GEMMs accumulate into it)
         rope_and_cache_impl(m->qkv, m->q16, m->kc[l], m->vc[l], m->cos_t, m->sin_t, m->d_positions, m->d_slots, B,
-                            m->heads_l, m->kv_l, hd, /*interleaved=*/1, B200_BF16, c.kv_dtype, /*zero_src=*/true, s);
+                            m->heads_l, m->kv_l, hd, /*interleaved=*/m->rope_neox ? 0 : 1, B200_BF16, c.kv_dtype, /*zero_src=*/true, s);
         paged_attention_decode(m->attn16, m->q16, m->kc[l], m->vc[l], m->d_tables, m->d_ctx, B, m->heads_l, m->kv_l, hd,
                                c.block_size, c.max_blocks_per_seq, m->num_blocks, 1.0f / sqrtf((float)hd), 0.f, 0,
-                               B200_BF16, c.kv_dtype, B200_KV_FLASH, B200_F16_K4, m->attn_ws, m->attn_ws_bytes, s);
+                               B200_BF16, c.kv_dtype, B200_KV_FLASH, fmt, m->attn_ws, m->attn_ws_bytes, s);
         }
         if (c.tp_world == 1) {
-            qmatmul_dispatch(m->attn16, w.wo, m->x, H, B, H, qd, w.to, 1, st);          // x += wo(attn)
+            linear(m, w.wo, m->attn16, m->x, H, B, H, qd, 1, st);                        // x += wo(attn)
         } else if (fused_ar) {
-            qmatmul_dispatch(m->attn16, w.wo, m->partial, H, B, H, qd, w.to, 1, st);
+            linear(m, w.wo, m->attn16, m->partial, H, B, H, qd, 1, st);
             residual_fused(w.ffn_norm);                                                    // x += sum_ranks(partial); xn = ffn_norm(x)
         } else {
             // row-parallel: partial sums -> all-reduce -> residual add (distributed.rs:696-710)
             launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->partial, (int64_t)B * H); count_launch();
-            qmatmul_dispatch(m->attn16, w.wo, m->partial, H, B, H, qd, w.to, 1, st);
+            linear(m, w.wo, m->attn16, m->partial, H, B, H, qd, 1, st);
             tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);   // tp.cu (NCCL)
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
-        if (!fused_ar) rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
-        {   // fused gate | up
-            const void* ws[2] = {w.w1, w.w3};
-            const int ts[2] = {w.t1, w.t3}, ns[2] = {m->ffn_l, m->ffn_l};
+        if (!fused_ar) rms_norm(m->x, w.ffn_norm, m->xn, B, H, c.rms_eps, fmt, s);
+        if (all_ggml) {   // fused gate | up
+            const void* ws[2] = {w.w1.w, w.w3.w};
+            const int ts[2] = {w.w1.type, w.w3.type}, ns[2] = {m->ffn_l, m->ffn_l};
             float* ys[2] = {m->gate, m->up};
             qmatmul_dispatch_multi(m->xn, 2, ws, ts, ys, ns, m->ffn_l, B, H, 0, st);
+        } else {
+            linear(m, w.w1, m->xn, m->gate, m->ffn_l, B, m->ffn_l, H, 0, st);
+            linear(m, w.w3, m->xn, m->up, m->ffn_l, B, m->ffn_l, H, 0, st);
         }
-        silu_mul_zero_src(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, s);      // act = silu(gate)*up; gate/up re-zeroed
+        silu_mul_zero_src_fmt(m->gate, m->up, m->act16, (int64_t)B * m->ffn_l, fmt, s);      // act = silu(gate)*up; gate/up re-zeroed
         if (c.tp_world == 1) {
-            qmatmul_dispatch(m->act16, w.w2, m->x, H, B, H, m->ffn_l, w.t2, 1, st);     // x += w2(act)
+            linear(m, w.w2, m->act16, m->x, H, B, H, m->ffn_l, 1, st);                   // x += w2(act)
         } else if (fused_ar) {
-            qmatmul_dispatch(m->act16, w.w2, m->partial, H, B, H, m->ffn_l, w.t2, 1, st);
+            linear(m, w.w2, m->act16, m->partial, H, B, H, m->ffn_l, 1, st);
             residual_fused(l + 1 < c.num_layers ? m->layers[l + 1].attn_norm : m->norm);
         } else {
             launch_pdl(zero_f32_kernel, dim3(64), dim3(256), 0, st, m->partial, (int64_t)B * H); count_launch();
-            qmatmul_dispatch(m->act16, w.w2, m->partial, H, B, H, m->ffn_l, w.t2, 1, st);
+            linear(m, w.w2, m->act16, m->partial, H, B, H, m->ffn_l, 1, st);
             tp_allreduce_f32(m->comm, m->partial, (int64_t)B * H, st);
             add_f32(m->x, m->partial, (int64_t)B * H, s);
         }
     }
-    if (!fused_ar)
-    rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, B200_F16_K4, s);
-    if (qmatmul_tc_supported(B, m->vocab_l, H, m->output_type) && qmatmul_tc_needs_zeroed_output(m->vocab_l, H)) {
-        launch_pdl(zero_f32_kernel, dim3(sm_count() * 2), dim3(256), 0, st, m->logits, (int64_t)B * m->vocab_l); count_launch();
-    }
-    qmatmul_dispatch(m->xn, m->output_w, m->logits, m->vocab_l, B, m->vocab_l, H, m->output_type, 0, st);
+    if (!fused_ar) rms_norm(m->x, m->norm, m->xn, B, H, c.rms_eps, fmt, s);
+    lm_head(m, B, st);
     // greedy sampling in two stages; vocab-parallel lm_head (distributed.rs:1632-1667): gather (max, global index) pairs
     // instead of the logits
     // vocab-parallel: this rank's columns are [tp_rank * vocab_l, ...); columns at or beyond `vocab` are padding (never sampled)
@@ -364,9 +400,9 @@ bool peer_timed_out(b200_llama* m, const char* who) {
 
 bool ready(b200_llama* m) {
     if (!m || !m->ok) { set_error(kErrBadArg, "engine: model not initialised"); return false; }
-    if (!m->tok_embeddings || !m->norm || !m->output_w) { set_error(kErrBadArg, "engine: globals not set"); return false; }
+    if (!m->tok_embeddings || !m->norm || !m->output.w) { set_error(kErrBadArg, "engine: globals not set"); return false; }
     if ((int)m->kc.size() != m->cfg.num_layers) { set_error(kErrBadArg, "engine: kv cache not set"); return false; }
-    for (auto& l : m->layers) if (!l.wq) { set_error(kErrBadArg, "engine: layer weights not set"); return false; }
+    for (auto& l : m->layers) if (!l.wq.w) { set_error(kErrBadArg, "engine: layer weights not set"); return false; }
     if (m->cfg.tp_world > 1 && !m->comm) { set_error(kErrBadArg, "engine: tp_world > 1 but no communicator"); return false; }
     return true;
 }
@@ -422,7 +458,7 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
     b200_llama* m = new b200_llama();
     m->cfg = c;
     m->layers.resize(c.num_layers);
-    for (auto& l : m->layers) l = b200_llama_layer{};
+    for (auto& l : m->layers) l = b200_llama_layer_ex{};
     m->heads_l = c.num_heads / c.tp_world;
     // kv_head_shard (/root/reference/src/openai/distributed.rs:725-765): split, or replicate when kvh < world
     m->kv_l = c.num_kv_heads >= c.tp_world ? c.num_kv_heads / c.tp_world : 1;
@@ -527,22 +563,82 @@ void b200_llama_destroy(b200_llama* m) {
     if (m->logits_gathered) cudaFree(m->logits_gathered);
     if (m->logits_full) cudaFree(m->logits_full);
     if (m->mega_trace) cudaFree(m->mega_trace);
+    if (m->lin_scratch) cudaFree(m->lin_scratch);
     for (void* p : {(void*)m->qkv_slabs, (void*)m->ro_slabs, (void*)m->gate_slabs, (void*)m->up_slabs, (void*)m->mega_counters}) if (p) cudaFree(p);
     delete m;
+}
+
+static b200_linear ggml_linear(const void* w, int type) { b200_linear l{}; l.kind = B200_LIN_GGML; l.type = type; l.w = w; return l; }
+
+static bool check_linear(const b200_linear& l, int n, int k, const char* name) {
+    if (!l.w) { set_error(kErrBadArg, "engine: %s: null weight", name); return false; }
+    switch (l.kind) {
+        case B200_LIN_GGML:
+            if (l.type != B200_GGML_Q4_K && l.type != B200_GGML_Q6_K && l.type != B200_GGML_Q8_0) { set_error(kErrUnsupported, "engine: %s: ggml type %d", name, l.type); return false; }
+            return true;
+        case B200_LIN_MARLIN4:
+            if (!l.scales || (l.type != B200_F16 && l.type != B200_BF16) || (l.group_size != -1 && l.group_size != 64 && l.group_size != 128) || k % 256 || n % 64) {
+                set_error(kErrUnsupported, "engine: %s: marlin int4 needs f16 / bf16 scales, group 64 / 128 / -1, k %% 256 == 0, n %% 64 == 0 (n=%d k=%d g=%d)", name, n, k, l.group_size);
+                return false;
+            }
+            return true;
+        case B200_LIN_DENSE16:
+            if ((l.type != B200_F16 && l.type != B200_BF16) || k % 8 || ((uintptr_t)l.w & 15)) { set_error(kErrUnsupported, "engine: %s: dense weights must be f16 / bf16, k %% 8 == 0, 16-byte aligned", name); return false; }
+            return true;
+        default: set_error(kErrUnsupported, "engine: %s: linear kind %d", name, l.kind); return false;
+    }
+}
+static int fmt_of(const b200_linear& l) { return l.kind == B200_LIN_DENSE16 ? l.type : B200_F16_K4; }
+
+void b200_llama_set_layer_ex(b200_llama* m, int32_t layer, const b200_llama_layer_ex* w) {
+    B200_REQUIRE(m && w && layer >= 0 && layer < m->cfg.num_layers, kErrBadArg, "b200_llama_set_layer_ex: bad arguments");
+    B200_REQUIRE(w->attn_norm && w->ffn_norm, kErrBadArg, "b200_llama_set_layer_ex: null norm in layer %d", layer);
+    const b200_llama_config& c = m->cfg;
+    const int H = c.hidden, qd = m->heads_l * c.head_dim, kd = m->kv_l * c.head_dim, F = m->ffn_l;
+    if (!check_linear(w->wq, qd, H, "wq") || !check_linear(w->wk, kd, H, "wk") || !check_linear(w->wv, kd, H, "wv") ||
+        !check_linear(w->wo, H, qd, "wo") || !check_linear(w->w1, F, H, "w1") || !check_linear(w->w2, H, F, "w2") || !check_linear(w->w3, F, H, "w3")) return;
+    const int fmt = fmt_of(w->wq);
+    for (const b200_linear* l : {&w->wk, &w->wv, &w->wo, &w->w1, &w->w2, &w->w3})
+        B200_REQUIRE(fmt_of(*l) == fmt, kErrUnsupported, "b200_llama_set_layer_ex: the linears of a model must share one activation format");
+    m->layers[layer] = *w;
+    // fp32 partial-sum slabs of the int4 GEMMs (library scratch is per stream and may grow: the engine owns a fixed one instead)
+    size_t need = 0;
+    auto slab = [&](const b200_linear& l, int n, int k) { if (l.kind == B200_LIN_MARLIN4) need = std::max(need, (size_t)wq16_slabs(n, k) * c.max_num_seqs * n * 4 + 256); };
+    slab(w->wq, qd, H); slab(w->wk, kd, H); slab(w->wv, kd, H); slab(w->wo, H, qd); slab(w->w1, F, H); slab(w->w2, H, F); slab(w->w3, F, H);
+    if (need > m->lin_scratch_bytes) {
+        cudaDeviceSynchronize();
+        if (m->lin_scratch) cudaFree(m->lin_scratch);
+        m->lin_scratch = nullptr; m->lin_scratch_bytes = 0;
+        void* q = nullptr;
+        B200_REQUIRE(cudaMalloc(&q, need) == cudaSuccess, kErrCuda, "b200_llama_set_layer_ex: scratch cudaMalloc(%zu) failed", need);
+        m->lin_scratch = static_cast<float*>(q); m->lin_scratch_bytes = need;
+    }
+    invalidate_graphs(m);
 }
 
 void b200_llama_set_layer(b200_llama* m, int32_t layer, const b200_llama_layer* w) {
     B200_REQUIRE(m && w && layer >= 0 && layer < m->cfg.num_layers, kErrBadArg, "b200_llama_set_layer: bad arguments");
     B200_REQUIRE(w->attn_norm && w->ffn_norm && w->wq && w->wk && w->wv && w->wo && w->w1 && w->w2 && w->w3, kErrBadArg,
                  "b200_llama_set_layer: null weight in layer %d", layer);
-    m->layers[layer] = *w;
+    b200_llama_layer_ex e{};
+    e.attn_norm = w->attn_norm; e.ffn_norm = w->ffn_norm;
+    e.wq = ggml_linear(w->wq, w->tq); e.wk = ggml_linear(w->wk, w->tk); e.wv = ggml_linear(w->wv, w->tv); e.wo = ggml_linear(w->wo, w->to);
+    e.w1 = ggml_linear(w->w1, w->t1); e.w2 = ggml_linear(w->w2, w->t2); e.w3 = ggml_linear(w->w3, w->t3);
+    b200_llama_set_layer_ex(m, layer, &e);
+}
+
+void b200_llama_set_globals_ex(b200_llama* m, const float* tok_embeddings, const float* norm, const b200_linear* output, int32_t rope_neox) {
+    B200_REQUIRE(m && tok_embeddings && norm && output, kErrBadArg, "b200_llama_set_globals_ex: null pointer");
+    if (!check_linear(*output, m->vocab_l, m->cfg.hidden, "output")) return;
+    B200_REQUIRE(output->kind != B200_LIN_MARLIN4, kErrUnsupported, "b200_llama_set_globals_ex: the lm_head is GGML or dense (the reference never quantises it to int4)");
+    m->tok_embeddings = tok_embeddings; m->norm = norm; m->output = *output; m->rope_neox = rope_neox ? 1 : 0;
     invalidate_graphs(m);
 }
 
 void b200_llama_set_globals(b200_llama* m, const float* tok_embeddings, const float* norm, const void* output_w, int32_t output_type) {
     B200_REQUIRE(m && tok_embeddings && norm && output_w, kErrBadArg, "b200_llama_set_globals: null pointer");
-    m->tok_embeddings = tok_embeddings; m->norm = norm; m->output_w = output_w; m->output_type = output_type;
-    invalidate_graphs(m);
+    const b200_linear o = ggml_linear(output_w, output_type);
+    b200_llama_set_globals_ex(m, tok_embeddings, norm, &o, 0);
 }
 
 void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const* value_caches, int64_t num_blocks) {

@@ -359,7 +359,7 @@ layer_mega_kernel(const __grid_constant__ MegaParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    pdl_trigger();
+    if (P.early_trigger) pdl_trigger();
 
     const uint32_t G = gridDim.x;
     // counters of this launch: [2 * ph] = GEMM phase ph-1 complete on every CTA, [2 * ph + 1] = activations of phase ph ready
@@ -650,13 +650,16 @@ void mega_launch(const MegaParams& P, cudaStream_t st) {
             return;
         }
     }
-    if (P.m <= 32) {
-        ensure_dynamic_smem(reinterpret_cast<const void*>(layer_mega_kernel<32>), MCfg<32>::kTotal);
-        launch_pdl(layer_mega_kernel<32>, dim3(G), dim3(kThreads), MCfg<32>::kTotal, st, P);
-    } else {
-        ensure_dynamic_smem(reinterpret_cast<const void*>(layer_mega_kernel<64>), MCfg<64>::kTotal);
-        launch_pdl(layer_mega_kernel<64>, dim3(G), dim3(kThreads), MCfg<64>::kTotal, st, P);
-    }
+    // tuning knobs (measured in profiles/): B200_MEGA_PDL=0 launches the kernel without programmatic serialization (it then starts
+    // only after its predecessor has drained); MegaParams.early_trigger lets the NEXT kernel's grid be scheduled early
+    static const int pdl_in = [] { const char* e = getenv("B200_MEGA_PDL"); return e ? atoi(e) : 1; }();
+    auto go = [&](auto kern, int smem) {
+        ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+        if (pdl_in) launch_pdl(kern, dim3(G), dim3(kThreads), smem, st, P);
+        else kern<<<dim3(G), dim3(kThreads), smem, st>>>(P);
+    };
+    if (P.m <= 32) go(layer_mega_kernel<32>, MCfg<32>::kTotal);
+    else go(layer_mega_kernel<64>, MCfg<64>::kTotal);
     count_launch();
     check_launch("layer_mega");
 }

@@ -21,6 +21,7 @@ void rope_and_cache_impl(float* qkv, void* q_out, void* key_cache, void* value_c
                          int32_t num_kv_heads, int32_t head_dim, int32_t interleaved, int32_t dtype, int32_t cache_dtype,
                          bool zero_src, int64_t stream);
 void silu_mul_zero_src(float* gate, float* up, void* out_f16_k4, int64_t numel, int64_t stream);
+void silu_mul_zero_src_fmt(float* gate, float* up, void* out, int64_t numel, int fmt, int64_t stream);
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,
                 int accumulate, cudaStream_t st);
 
@@ -44,6 +45,8 @@ int wq16_slabs(int n, int k);
 // int4 (GPTQ symmetric / AWQ with zero points; repacked by gptq_repack / awq_repack) x fp16 activations in K4 order
 void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const void* qzeros /* null: symmetric */, void* out, int out_dtype,
                int m, int n, int k, int group_size, float* slabs, cudaStream_t st);
+void marlin_tc_f32(const void* x_f16_k4, const void* w, const void* scales, int scale_bf16, const void* qzeros, float* y, int64_t ldy, int m, int n, int k,
+                   int group_size, int accumulate, float* slabs, cudaStream_t st);
 // e4m3 [n,k] with f32 scale per [by, bx] tile x fp16 activations in natural order
 bool fp8_tc_supported(int m, int n, int k, int by, int bx);
 void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void* bias, void* out, int out_dtype, int m, int n, int k,
@@ -52,8 +55,10 @@ void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void
 void* get_scratch(size_t bytes, cudaStream_t st);
 
 // dense 16-bit GEMM on tcgen05 (dense_gemm.cu): y[m,n] = x[m,k] . w[n,k]^T (+ bias); operands f16 / bf16 (`dtype`), out f16 / bf16 / f32
+// accumulate (f32 output only): y += result.  allow_split_k: decode-size calls with f32 output may cut k over several CTAs whose partial
+// sums meet in y through fp32 atomics (y must then hold the addend: zeros, or the accumulate target)
 bool dense_gemm_16(const void* x, const void* w, const void* bias, void* y, int m, int n, int k, int64_t ldx, int64_t ldw, int64_t ldy,
-                   int dtype, int out_dtype, cudaStream_t st);
+                   int dtype, int out_dtype, cudaStream_t st, int accumulate = 0, int allow_split_k = 0);
 // GGML blocks -> fp16 [n, k] (natural order), one rounding
 bool dequantize_f16(const void* w, void* out_f16, int64_t n, int64_t k, int ggml_type, cudaStream_t st);
 

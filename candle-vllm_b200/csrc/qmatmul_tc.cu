@@ -654,6 +654,23 @@ __global__ void finish_slabs_kernel(const float* __restrict__ slabs, int n_slabs
     }
 }
 
+// y[m][ldy] (f32) (+)= sum of the fp32 slabs: the finishing pass of the int4 GEMM inside the decode engine (f32 residual stream)
+__global__ void finish_slabs_f32_kernel(const float* __restrict__ slabs, int n_slabs, int64_t slab_stride, float* __restrict__ y, int64_t ldy,
+                                        int64_t total, int n, int accumulate) {
+    pdl_wait();
+    pdl_trigger();
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (int64_t)gridDim.x * blockDim.x * 4) {
+        float4 a = *reinterpret_cast<const float4*>(slabs + i);
+        for (int sl = 1; sl < n_slabs; ++sl) {
+            const float4 b = *reinterpret_cast<const float4*>(slabs + sl * slab_stride + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        float4* o = reinterpret_cast<float4*>(y + (i / n) * ldy + (i % n));
+        if (accumulate) { const float4 c = *o; a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w; }
+        *o = a;
+    }
+}
+
 }  // namespace
 
 bool qmatmul_tc_supported(int m, int n, int k, int ggml_type) {
@@ -746,7 +763,7 @@ int wq16_slabs(int n, int k) { return qmatmul_tc_slab_count((n + kTileN - 1) / k
 
 static void wq16_launch(int kind, const void* x_f16, const void* w, const void* scales, int scale_bf16, int group_or_bx, int by, int sk,
                         const float* norm, const uint32_t* zp, const void* bias, void* out, int out_dtype, int m, int n, int k, float* slabs, cudaStream_t st,
-                        const char* who) {
+                        const char* who, int64_t ldy_f32 = 0, int accumulate_f32 = 0) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) { set_error(kErrCuda, "%s: cuTensorMapEncodeTiled unavailable", who); return; }
     if (((uintptr_t)x_f16 | (uintptr_t)w) & 15) { set_error(kErrBadArg, "%s: x and weights must be 16-byte aligned", who); return; }
@@ -779,7 +796,9 @@ static void wq16_launch(int kind, const void* x_f16, const void* w, const void* 
     const int64_t total = (int64_t)m * n;
     int64_t g = (total / 4 + 255) / 256;
     if (g > (int64_t)sm_count() * 4) g = (int64_t)sm_count() * 4;
-    if (out_dtype == B200_BF16)
+    if (out_dtype == B200_F32)
+        launch_pdl(finish_slabs_f32_kernel, dim3((int)g), dim3(256), 0, st, (const float*)slabs, p.slabs, p.slab_stride, (float*)out, ldy_f32, total, n, accumulate_f32);
+    else if (out_dtype == B200_BF16)
         launch_pdl(finish_slabs_kernel<__nv_bfloat16>, dim3((int)g), dim3(256), 0, st, (const float*)slabs, p.slabs, p.slab_stride, (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, total, n, norm);
     else
         launch_pdl(finish_slabs_kernel<__half>, dim3((int)g), dim3(256), 0, st, (const float*)slabs, p.slabs, p.slab_stride, (const __half*)bias, (__half*)out, total, n, norm);
@@ -793,6 +812,13 @@ void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const vo
                int group_size, float* slabs, cudaStream_t st) {
     wq16_launch(kTypeM4, x_f16_k4, w, scales, out_dtype == B200_BF16, group_size, 1, 0, nullptr, static_cast<const uint32_t*>(qzeros), nullptr, out,
                 out_dtype, m, n, k, slabs, st, qzeros ? "marlin_awq_4bit" : "marlin_4bit");
+}
+
+// the same GEMM with f32 output (+ accumulate) for the decode engine: y[m][ldy] (+)= x . ((q - z) * s)^T; n % 4 == 0
+void marlin_tc_f32(const void* x_f16_k4, const void* w, const void* scales, int scale_bf16, const void* qzeros, float* y, int64_t ldy, int m, int n, int k,
+                   int group_size, int accumulate, float* slabs, cudaStream_t st) {
+    wq16_launch(kTypeM4, x_f16_k4, w, scales, scale_bf16, group_size, 1, 0, nullptr, static_cast<const uint32_t*>(qzeros), nullptr, y, B200_F32, m, n, k,
+                slabs, st, "marlin_4bit(f32)", ldy, accumulate);
 }
 
 // block-scaled e4m3 weights x fp16 (fp8_matmul); activations fp16 in natural order

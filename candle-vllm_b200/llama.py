@@ -55,13 +55,52 @@ class _CLayer(C.Structure):
                [(n, C.c_int32) for n in ("tq", "tk", "tv", "to", "t1", "t2", "t3")]
 
 
+class _CLinear(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("type", C.c_int32), ("w", C.c_void_p), ("scales", C.c_void_p), ("zeros", C.c_void_p),
+                ("group_size", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _CLayerEx(C.Structure):
+    _fields_ = [("attn_norm", C.c_void_p), ("ffn_norm", C.c_void_p)] + [(n, _CLinear) for n in ("wq", "wk", "wv", "wo", "w1", "w2", "w3")]
+
+
+@dataclass
+class MarlinWeight:
+    """GPTQ / AWQ int4 weight prepared like the reference prepares it for Marlin (linear.rs:300-413): ``qweight`` =
+    ``marlin_weight_repack`` output, ``scales`` = ``marlin_permute_scales`` output (f16 / bf16), ``zeros`` = the converter's AWQ zero
+    points or None (symmetric GPTQ)."""
+    qweight: torch.Tensor
+    scales: torch.Tensor
+    group_size: int
+    zeros: Optional[torch.Tensor] = None
+
+
+_DT = {torch.float16: DType.F16, torch.bfloat16: DType.BF16}
+
+
+def _clinear(w) -> _CLinear:
+    """QTensor (GGML) | MarlinWeight (int4) | dense f16 / bf16 tensor [n, k] -> b200_linear."""
+    if isinstance(w, QTensor):
+        return _CLinear(0, w.ggml_type, w.data.data_ptr(), None, None, 0, 0)
+    if isinstance(w, MarlinWeight):
+        if w.scales.dtype not in _DT:
+            raise BackendError("MarlinWeight: scales must be f16 / bf16")
+        return _CLinear(1, _DT[w.scales.dtype], w.qweight.data_ptr(), w.scales.data_ptr(),
+                        None if w.zeros is None else w.zeros.data_ptr(), int(w.group_size), 0)
+    if isinstance(w, torch.Tensor) and w.dtype in _DT and w.dim() == 2 and w.is_contiguous():
+        return _CLinear(2, _DT[w.dtype], w.data_ptr(), None, None, 0, 0)
+    raise BackendError(f"unsupported linear weight {type(w)}")
+
+
 class GGUFLLaMa:
-    """weights: dict(tok_embeddings f32 [V,H], norm f32 [H], output QTensor, layers=[dict(attn_norm, ffn_norm f32;
-    wq, wk, wv, wo, w1, w2, w3 QTensor)]) already sharded for (tp_rank, tp_world)."""
+    """weights: dict(tok_embeddings f32 [V,H], norm f32 [H], output, layers=[dict(attn_norm, ffn_norm f32; wq, wk, wv, wo, w1, w2, w3)])
+    already sharded for (tp_rank, tp_world).  Every linear is a QTensor (GGML blocks: the GGUF models, quantized_llama.rs), a
+    MarlinWeight (GPTQ / AWQ int4) or a dense f16 / bf16 tensor [n, k] (the safetensors models, llama.rs); ``rope_neox`` selects the
+    rotation of the safetensors models (llama.rs:222) instead of GGUF's interleaved one."""
 
     def __init__(self, cfg: LlamaConfig, weights: dict, kv_cache: List, kv_dtype: int = DType.BF16,
                  tp_rank: int = 0, tp_world: int = 1, use_graph: bool = True, stream: Optional[torch.cuda.Stream] = None,
-                 nccl_comm: Optional[int] = None):
+                 nccl_comm: Optional[int] = None, rope_neox: bool = False):
         require_device()
         self.cfg, self.weights, self.kv_cache = cfg, weights, kv_cache
         # Default = torch's current stream: every other op of this package (CacheEngine swap / copy, PagedAttention prefill,
@@ -78,15 +117,19 @@ class GGUFLLaMa:
         check("b200_llama_create")
         if not self._h:
             raise BackendError("b200_llama_create returned null")
+        names = ("wq", "wk", "wv", "wo", "w1", "w2", "w3")
         for i, lw in enumerate(weights["layers"]):
-            cl = _CLayer(lw["attn_norm"].data_ptr(), lw["ffn_norm"].data_ptr(),
-                         *[lw[k].data.data_ptr() for k in ("wq", "wk", "wv", "wo", "w1", "w2", "w3")],
-                         *[lw[k].ggml_type for k in ("wq", "wk", "wv", "wo", "w1", "w2", "w3")])
-            L.b200_llama_set_layer(self._h, C.c_int32(i), C.byref(cl))
+            if all(isinstance(lw[k], QTensor) for k in names):       # the reference's GGUF form
+                cl = _CLayer(lw["attn_norm"].data_ptr(), lw["ffn_norm"].data_ptr(), *[lw[k].data.data_ptr() for k in names],
+                             *[lw[k].ggml_type for k in names])
+                L.b200_llama_set_layer(self._h, C.c_int32(i), C.byref(cl))
+            else:
+                ce = _CLayerEx(lw["attn_norm"].data_ptr(), lw["ffn_norm"].data_ptr(), *[_clinear(lw[k]) for k in names])
+                L.b200_llama_set_layer_ex(self._h, C.c_int32(i), C.byref(ce))
             check("b200_llama_set_layer")
-        out: QTensor = weights["output"]
-        L.b200_llama_set_globals(self._h, C.c_void_p(weights["tok_embeddings"].data_ptr()), C.c_void_p(weights["norm"].data_ptr()),
-                                 C.c_void_p(out.data.data_ptr()), C.c_int32(out.ggml_type))
+        out = _clinear(weights["output"])
+        L.b200_llama_set_globals_ex(self._h, C.c_void_p(weights["tok_embeddings"].data_ptr()), C.c_void_p(weights["norm"].data_ptr()),
+                                    C.byref(out), C.c_int32(1 if rope_neox else 0))
         check("b200_llama_set_globals")
         kp = (C.c_void_p * cfg.num_layers)(*[k.data_ptr() for k, _ in kv_cache])
         vp = (C.c_void_p * cfg.num_layers)(*[v.data_ptr() for _, v in kv_cache])

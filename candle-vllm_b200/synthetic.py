@@ -113,6 +113,62 @@ def make_weights(cfg: LlamaConfig, device="cuda", seed: int = 0, tp_rank: int = 
     return w
 
 
+def make_weights_16bit(cfg: LlamaConfig, device="cuda", seed: int = 0, dtype=torch.bfloat16):
+    """Dense 16-bit Llama (BASELINE config 2; the safetensors path of the reference, llama.rs): every linear a [n, k] tensor of
+    ``dtype`` ~ N(0, 0.02), lm_head included.  Returns (engine weights, oracle weights); the oracle sees exactly the 16-bit values."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    H, hd = cfg.hidden, cfg.head_dim
+    qd, kd = cfg.num_heads * hd, cfg.num_kv_heads * hd
+    mk = lambda n, k: (torch.randn((n, k), device=device, generator=gen, dtype=torch.float32) * 0.02).to(dtype).contiguous()
+    w = dict(tok_embeddings=torch.randn((cfg.vocab, H), device=device, generator=gen, dtype=torch.float32),
+             norm=torch.rand(H, device=device, generator=gen) + 0.5, layers=[])
+    for _ in range(cfg.num_layers):
+        w["layers"].append(dict(attn_norm=torch.rand(H, device=device, generator=gen) + 0.5, ffn_norm=torch.rand(H, device=device, generator=gen) + 0.5,
+                                wq=mk(qd, H), wk=mk(kd, H), wv=mk(kd, H), wo=mk(H, qd), w1=mk(cfg.ffn, H), w2=mk(H, cfg.ffn), w3=mk(cfg.ffn, H)))
+    w["output"] = mk(cfg.vocab, H)
+    return w
+
+
+def make_weights_gptq(cfg: LlamaConfig, device="cuda", seed: int = 0, group_size: int = 128, dtype=torch.float16, output_type: int = GgmlType.Q6_K,
+                      with_oracle: bool = True):
+    """GPTQ symmetric int4 Llama prepared for Marlin like the reference does at load time (linear.rs:300-413: ``gptq_repack`` +
+    ``marlin_permute_scales``): BASELINE config 3.  int4 uniform, scales ~ U(0.005, 0.02) of ``dtype``; the lm_head stays a GGML tensor
+    (the reference never quantises it to int4).  Returns (engine weights, oracle weights)."""
+    import numpy as np
+    from .gptq import marlin_permute_scales, marlin_weight_repack
+    from .llama import MarlinWeight
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    H, hd = cfg.hidden, cfg.head_dim
+    qd, kd = cfg.num_heads * hd, cfg.num_kv_heads * hd
+
+    def mk(n, k):
+        q = torch.randint(0, 16, (k, n), device=device, generator=gen, dtype=torch.int32)          # [K, N] like the checkpoint
+        packed = torch.zeros((k // 8, n), dtype=torch.int32, device=device)
+        for i in range(8):
+            packed |= q[i::8] << (4 * i)                                                              # nibble i of word kp = q[8 kp + i]
+        ng = 1 if group_size == -1 else k // group_size
+        scales = (torch.rand((ng, n), device=device, generator=gen) * 0.015 + 0.005).to(dtype)
+        eng = MarlinWeight(marlin_weight_repack(packed, 4, False), marlin_permute_scales(scales, k, n, group_size).contiguous(), group_size)
+        orc = ("gptq", packed.cpu().numpy().view(np.uint32), scales.float().cpu().numpy(), group_size) if with_oracle else None
+        return eng, orc
+
+    w = dict(tok_embeddings=torch.randn((cfg.vocab, H), device=device, generator=gen, dtype=torch.float32),
+             norm=torch.rand(H, device=device, generator=gen) + 0.5, layers=[])
+    ow = dict(tok_embeddings=w["tok_embeddings"].cpu().numpy() if with_oracle else None, norm=w["norm"].cpu().numpy(), layers=[])
+    for _ in range(cfg.num_layers):
+        lw = dict(attn_norm=torch.rand(H, device=device, generator=gen) + 0.5, ffn_norm=torch.rand(H, device=device, generator=gen) + 0.5)
+        lo = dict(attn_norm=lw["attn_norm"].cpu().numpy(), ffn_norm=lw["ffn_norm"].cpu().numpy())
+        for name, (n, k) in dict(wq=(qd, H), wk=(kd, H), wv=(kd, H), wo=(H, qd), w1=(cfg.ffn, H), w2=(H, cfg.ffn), w3=(cfg.ffn, H)).items():
+            lw[name], lo[name] = mk(n, k)
+        w["layers"].append(lw); ow["layers"].append(lo)
+    out = random_qtensor(gen, output_type, cfg.vocab, H, device)
+    w["output"] = out
+    ow["output"] = (out.data.cpu().numpy(), out.ggml_type, cfg.vocab, H) if with_oracle else None
+    return w, ow
+
+
 def fill_kv_cache(kv_cache, seed: int = 1, tp_rank: int = 0, tp_world: int = 1, num_kv_heads: int = 0) -> None:
     """KV contents N(0,1) in the cache dtype (bf16, or e4m3 bits for u8 caches).  With tp_world > 1 (and the model's total
     ``num_kv_heads``) every rank draws the FULL layer [nb, bs, kvh, hd] from the same seeded stream and keeps its own kv heads

@@ -247,6 +247,26 @@ typedef struct {
     int32_t tq, tk, tv, to, t1, t2, t3;                     /* ggml types */
 } b200_llama_layer;
 
+/* A linear layer of the decode engine.  GGUF models use GGML tensors (b200_llama_layer above is the short form); the safetensors
+ * models of the reference use Linear / GPTQ-Marlin / block-FP8 layers (/root/reference/src/openai/models/llama.rs:47-64,
+ * linear.rs:124-172, :300-413): BASELINE configs 2 (dense BF16) and 3 (GPTQ/Marlin int4 + FP8 KV). */
+enum { B200_LIN_GGML = 0,      /* w = GGML blocks, type = ggml type */
+       B200_LIN_MARLIN4 = 1,   /* w = gptq_repack / awq_repack output, scales = marlin_permute_scales output (type = B200_F16 / B200_BF16 of the
+                                  scales), zeros = NULL (symmetric GPTQ) or the converter's AWQ zero points, group_size 64 / 128 / -1 */
+       B200_LIN_DENSE16 = 2 }; /* w = dense [n, k] of type B200_F16 / B200_BF16 */
+typedef struct {
+    int32_t kind, type;
+    const void* w;
+    const void* scales;
+    const void* zeros;
+    int32_t group_size, reserved;
+} b200_linear;
+
+typedef struct {
+    const float* attn_norm; const float* ffn_norm;          /* f32 [hidden] */
+    b200_linear wq, wk, wv, wo, w1, w2, w3;
+} b200_llama_layer_ex;
+
 typedef struct b200_llama b200_llama;
 
 b200_llama* b200_llama_create(const b200_llama_config* cfg);
@@ -255,6 +275,12 @@ void        b200_llama_destroy(b200_llama* m);
 void b200_llama_set_layer(b200_llama* m, int32_t layer, const b200_llama_layer* w);
 void b200_llama_set_globals(b200_llama* m, const float* tok_embeddings /*f32 [vocab,hidden]*/,
                             const float* norm, const void* output_w, int32_t output_type);
+/* general forms: any linear kind per weight; all linears of a model must share one activation format (GGML / MARLIN4: fp16 K4;
+ * DENSE16: the weights' dtype).  rope_neox != 0 selects the NeoX rotation (i, i + hd/2) of the safetensors models (llama.rs:222)
+ * instead of the interleaved one of GGUF (quantized_llama.rs:313-318).  The persistent layer kernel serves all-Q4_K layers only;
+ * other kinds run one launch per GEMM. */
+void b200_llama_set_layer_ex(b200_llama* m, int32_t layer, const b200_llama_layer_ex* w);
+void b200_llama_set_globals_ex(b200_llama* m, const float* tok_embeddings, const float* norm, const b200_linear* output, int32_t rope_neox);
 /* KV caches: flash layout, one K and one V device pointer per layer (cache_engine.rs:122-294) */
 void b200_llama_set_kv_cache(b200_llama* m, void* const* key_caches, void* const* value_caches,
                              int64_t num_blocks);

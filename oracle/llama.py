@@ -42,6 +42,15 @@ def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
 
 
 def qmm(x, w, mode):
+    """w = (ggml bytes, type, n, k) -- the GGUF models -- or ("dense", W [n, k]) (Linear, linear.rs:124-172) or
+    ("gptq", qweight u32 [K/8, N], scales [K/g, N], group) (GPTQ symmetric int4, oracle/gptq.py)."""
+    if isinstance(w[0], str):
+        if w[0] == "dense":
+            return (np.asarray(x, np.float64) @ np.asarray(w[1], np.float64).T).astype(np.float32)
+        if w[0] == "gptq":
+            from . import gptq as OG
+            return OG.gptq_matmul(np.asarray(x, np.float32), w[1], w[2], w[3]).astype(np.float32)
+        raise ValueError(w[0])
     wbytes, t, n, k = w
     if mode == "q8k":
         return G.qmatmul_q8k(x, wbytes, t, n, k)
@@ -65,8 +74,9 @@ def forward(cfg, weights, tokens, positions, k_caches, v_caches, meta, mode="deq
         q = qmm(h, lw["wq"], mode).reshape(T, nh, hd)
         k = qmm(h, lw["wk"], mode).reshape(T, nkv, hd)
         v = qmm(h, lw["wv"], mode).reshape(T, nkv, hd)
-        q = A.apply_rope(q, cos, sin, positions, interleaved=True)
-        k = A.apply_rope(k, cos, sin, positions, interleaved=True)
+        il = not cfg.get("rope_neox", False)            # GGUF llama: rope_i (quantized_llama.rs:313-318); safetensors llama: NeoX (llama.rs:222)
+        q = A.apply_rope(q, cos, sin, positions, interleaved=il)
+        k = A.apply_rope(k, cos, sin, positions, interleaved=il)
         q, k, v = bf16_round(q), bf16_round(k), bf16_round(v)
         C.reshape_and_cache_flash(k, v, k_caches[li], v_caches[li], meta["slot_mapping"], fp8=fp8_kv)
         if is_prefill:

@@ -141,6 +141,50 @@ def test_decode_with_fp8_kv_cache_matches_oracle(use_graph):
         lens = [L + 1 for L in lens]
 
 
+def _oracle_dense(w):
+    f = lambda t: ("dense", t.float().cpu().numpy())
+    return dict(tok_embeddings=w["tok_embeddings"].cpu().numpy(), norm=w["norm"].cpu().numpy(), output=f(w["output"]),
+                layers=[dict(attn_norm=l["attn_norm"].cpu().numpy(), ffn_norm=l["ffn_norm"].cpu().numpy(),
+                             **{k: f(l[k]) for k in ("wq", "wk", "wv", "wo", "w1", "w2", "w3")}) for l in w["layers"]])
+
+
+@pytest.mark.parametrize("kind", ["dense_bf16", "dense_f16", "gptq_f16", "gptq_bf16_fp8kv"])
+def test_decode_with_other_linear_kinds_matches_oracle(kind):
+    """The safetensors models of the reference through the same engine (b200_llama_set_layer_ex): dense 16-bit linears on the tcgen05
+    dense GEMM (BASELINE config 2) and GPTQ int4 prepared for Marlin (config 3, here also with the FP8 KV cache), NeoX RoPE.
+    Tolerance: 2e-3 of max|logit| (bf16 weights and activations carry 8-bit mantissas; the oracle sees the same 16-bit weight values)."""
+    cfg = _small_cfg(block_size=64, max_blocks_per_seq=8)
+    fp8 = kind.endswith("fp8kv")
+    if kind.startswith("dense"):
+        w = synthetic.make_weights_16bit(cfg, DEV, seed=0, dtype=torch.bfloat16 if "bf16" in kind else torch.float16)
+        ow = _oracle_dense(w)
+    else:
+        w, ow = synthetic.make_weights_gptq(cfg, DEV, seed=0, group_size=128, dtype=torch.bfloat16 if "bf16" in kind else torch.float16)
+    nb = 32
+    eng = pkg.CacheEngine(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim, pkg.CacheConfig(cfg.block_size, nb, kvcache_dtype="fp8" if fp8 else "auto"))
+    synthetic.fill_kv_cache(eng.gpu_cache, seed=1)
+    okc = [(k.cpu().numpy() if fp8 else k.float().cpu().numpy()).copy() for k, _ in eng.gpu_cache]
+    ovc = [(v.cpu().numpy() if fp8 else v.float().cpu().numpy()).copy() for _, v in eng.gpu_cache]
+    model = pkg.GGUFLLaMa(cfg, w, eng.gpu_cache, kv_dtype=pkg.DType.FP8_E4M3 if fp8 else pkg.DType.BF16, rope_neox=True)
+    assert not model.uses_layer_kernel(5)
+    ocfg = dict(_ocfg(cfg), rope_neox=True)
+    lens, tokens = [1, 64, 65, 200, 300], [5, 700, 33, 0, 123]
+    tables = synthetic.random_block_tables(5, 5, nb, seed=2)
+    for step in range(3):
+        prep = pkg.prepare_decode(lens, tokens, tables, cfg.block_size)
+        nxt, logits = model.decode(prep, want_logits=True)
+        ref = OL.forward(ocfg, ow, prep["tokens"].astype(np.int64), prep["positions"], okc, ovc,
+                         dict(slot_mapping=prep["slot_mapping"], block_tables=prep["block_tables"], context_lens=prep["context_lens"]), fp8_kv=fp8)
+        scale = np.abs(ref).max()
+        err = np.abs(logits - ref).max() / scale
+        assert err < 2e-3, (kind, step, err)
+        for b in range(5):
+            if nxt[b] != ref[b].argmax():
+                assert ref[b].max() - ref[b, nxt[b]] <= 2 * err * scale, (step, b)
+        tokens = [int(t) for t in ref.argmax(axis=1)]
+        lens = [L + 1 for L in lens]
+
+
 def test_resident_replay_equals_host_driven_steps():
     cfg = _small_cfg()
     w = synthetic.make_weights(cfg, DEV, seed=3)
