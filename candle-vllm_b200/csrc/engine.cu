@@ -200,7 +200,7 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         P.timeout_word = m->d_timeout;
         if (fused_ar) for (int i = 0; i < c.tp_world; ++i) P.peers.p[i] = static_cast<char*>(m->peers[i]);
         P.trace = launch == m->mega_trace_launch ? m->mega_trace : nullptr;
-        static const int trig = [] { const char* e = getenv("B200_MEGA_TRIGGER"); return e ? atoi(e) : 1; }();
+        static const int trig = [] { const char* e = getenv("B200_MEGA_TRIGGER"); return e ? atoi(e) : 0; }();     // early trigger measured 9 % slower
         P.early_trigger = trig;
     };
     auto qkv_phase = [&](MegaParams& P, MegaPhase& ph, const b200_llama_layer_ex& w, int map0) -> bool {
@@ -522,8 +522,10 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
         ok = dmalloc(m->logits_gathered, B * (size_t)m->vocab_pad) && dmalloc(m->logits_full, B * (size_t)c.vocab);
         tp_set_timeout_ms(m->tp_timeout_ms);
     }
-    // persistent layer kernel (B200_MEGA=0 keeps the one-launch-per-GEMM path): slab buffers sized for the worst tile split
-    static const int mega_on = [] { const char* e = getenv("B200_MEGA"); return e ? atoi(e) : 1; }();
+    // persistent layer kernel (csrc/layer_mega.cu), opt-in with B200_MEGA=1: bitwise-deterministic split-K reduction, but its in-kernel
+    // grid-wide syncs cost more than the PDL-overlapped kernel boundaries of the one-launch-per-GEMM path (measured: 5.5 vs 5.3 ms /
+    // step at one GPU, 4.9 vs 4.1 ms at TP = 2; profiles/r02_layer_kernel.md), so the default stays one launch per GEMM
+    const int mega_on = [] { const char* e = getenv("B200_MEGA"); return e ? atoi(e) : 0; }();      // read per model: tests toggle it
     if (ok && mega_on && c.hidden % 256 == 0 && c.hidden <= 8192 && (m->heads_l * c.head_dim) % 256 == 0 && m->ffn_l % 256 == 0) {
         auto tiles = [](int n) { return (n + 127) / 128; };
         const int G = mega_grid();

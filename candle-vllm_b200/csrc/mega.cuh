@@ -55,7 +55,7 @@ struct MegaParams {
     int tp_rank, tp_world, rows_max;
     unsigned long long tp_timeout_ns;
     uint32_t* timeout_word;
-    int early_trigger;                // 1: griddepcontrol.launch_dependents right after the prologue (B200_MEGA_TRIGGER, default 1)
+    int early_trigger;                // 1: griddepcontrol.launch_dependents right after the prologue (B200_MEGA_TRIGGER; default 0: measured 9 % slower)
     long long* trace;                 // profiling aid (B200_MEGA_TRACE): [CTA][phase][8] clock64 stamps, see layer_mega.cu
 };
 

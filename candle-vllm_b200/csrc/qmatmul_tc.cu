@@ -64,6 +64,12 @@ struct Cfg {
     static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
+}  // namespace
+}  // namespace b200
+#include "moe.cuh"
+namespace b200 {
+namespace {
+
 constexpr int kMaxSeg = 3;           // weight matrices sharing one activation (fused QKV, gate|up) in one launch
 struct GemmParams {
     float* y[kMaxSeg];             // output base of each segment (row stride ldy)
@@ -81,6 +87,13 @@ struct GemmParams {
     int scale_bf16, scale_by, scale_sk;
     const float* norm;             // fp8: {2^p, 2^-p} range shift of the tile scales (device)
     const uint32_t* zp;            // AWQ: packed zero points [K/g, N/8] in the marlin layout (null: symmetric, zero point 8)
+    // grouped (mixture-of-experts) mode: the tile list lives in device memory -- built from the routing of this step (moe.cu) --
+    // and every "tile" is one (expert, 128-row weight tile, chunk of <= kMB routed rows): weights at row w_row0 of the stacked
+    // [E * N, K] tensor, activations at row x_row0 of the expert-sorted fp16 copy, results scattered to row_map[x_row0 + i]
+    const MoeItem* items;          // null: dense mode
+    const int* num_items;          // device: number of items of this step
+    const uint32_t* row_map;       // sorted position -> output row
+    const float* row_scale;        // per OUTPUT row multiplier (top-k routing weight) or null
     long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
     int debug;                     // profiling aid (B200_GEMM_DEBUG): 1 = skip MMA issue, 2 = skip dequant, 4 = skip epilogue stores
 };
@@ -368,9 +381,12 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
     // ---- stream-K range of this CTA over the flattened (tile, super-block) space -----------------
     // (32-bit on purpose: 64-bit integer division costs ~500 cycles each on the SM and sat on the critical path of every
     // launch; the host guarantees total * gridDim.x < 2^31)
-    const uint32_t total = (uint32_t)p.n_tiles * (uint32_t)p.nsb, nsb = (uint32_t)p.nsb;
-    const uint32_t u0 = p.whole_tiles ? ((uint32_t)p.n_tiles * blockIdx.x / gridDim.x) * nsb : total * blockIdx.x / gridDim.x;
-    const uint32_t u1 = p.whole_tiles ? ((uint32_t)p.n_tiles * (blockIdx.x + 1) / gridDim.x) * nsb : total * (blockIdx.x + 1) / gridDim.x;
+    const bool moe = p.items != nullptr;
+    if (moe) pdl_wait();               // the tile list is produced by the previous kernel (routing of this step)
+    const uint32_t n_tiles_rt = moe ? (uint32_t)*reinterpret_cast<const volatile int*>(p.num_items) : (uint32_t)p.n_tiles;
+    const uint32_t total = n_tiles_rt * (uint32_t)p.nsb, nsb = (uint32_t)p.nsb;
+    const uint32_t u0 = p.whole_tiles ? (n_tiles_rt * blockIdx.x / gridDim.x) * nsb : total * blockIdx.x / gridDim.x;
+    const uint32_t u1 = p.whole_tiles ? (n_tiles_rt * (blockIdx.x + 1) / gridDim.x) * nsb : total * (blockIdx.x + 1) / gridDim.x;
     const uint32_t tile0 = u0 / nsb, sb0 = u0 - tile0 * nsb;          // first unit of this CTA
 
     if (warp == kDequantWarps) {
@@ -385,19 +401,19 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             const int s = it % kW;
             mbar_wait(w_empty(s), ((it / kW) & 1) ^ 1);
             if (p.trace && blockIdx.x == 0 && leader && it < 32) p.trace[it * 8 + 0] = clock64();
-            const int sg = seg_of_tile(p, tile);
+            const int sg = moe ? 0 : seg_of_tile(p, tile);
             const CUtensorMap* wm = sg == 0 ? &wmap0 : (sg == 1 ? &wmap1 : &wmap2);
-            const int ltile = tile - seg_first_tile(p, sg);
+            const int wrow = moe ? p.items[tile].w_row0 : (tile - seg_first_tile(p, sg)) * kTileN;      // first weight row of this tile
             if (leader) {
                 // W box start (bytes): Q4_K blocks are 144 B (16-aligned); Q6_K blocks (210 B) start at the block address
                 // rounded down to 16 -- TMA box starts must be 16-byte aligned
                 mbar_expect_tx(w_full(s), C::kWBytes);
                 if constexpr (kType == kTypeF8) {       // two 128-byte-swizzled boxes per unit
-                    tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), sb * 256, ltile * kTileN, pol_w);
-                    tma_load_2d(smem_base + C::kWOff + s * C::kWBytes + 16384, wm, w_full(s), sb * 256 + 128, ltile * kTileN, pol_w);
+                    tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), sb * 256, wrow, pol_w);
+                    tma_load_2d(smem_base + C::kWOff + s * C::kWBytes + 16384, wm, w_full(s), sb * 256 + 128, wrow, pol_w);
                 } else
                 tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : (kType == kTypeM4 ? sb * 128 : ((sb * 210) & ~15)),
-                            ltile * kTileN, pol_w);
+                            wrow, pol_w);
             }
             __syncwarp();
             if (++sb == (int)nsb) { sb = 0; ++tile; }
@@ -409,18 +425,19 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         uint64_t pol_x;
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_x));
         int it = 0;
-        int sb = (int)sb0;
+        int sb = (int)sb0, xtile = (int)tile0;
         for (uint32_t u = u0; u < u1; ++u, ++it) {
             const int s = it % kX;
             mbar_wait(x_empty(s), ((it / kX) & 1) ^ 1);
+            const int xrow = moe ? p.items[xtile].x_row0 : 0;          // grouped mode: this tile's rows of the expert-sorted activations
             if (leader) {
                 mbar_expect_tx(x_full(s), C::kXBytes);
                 const uint32_t dst = smem_base + C::kXOff + s * C::kXBytes;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, x_full(s), sb * kSB + q * 64, 0, pol_x);
+                for (int q = 0; q < 4; ++q) tma_load_2d(dst + q * kMB * kXSubBytes, &xmap, x_full(s), sb * kSB + q * 64, xrow, pol_x);
             }
             __syncwarp();
-            if (++sb == (int)nsb) sb = 0;
+            if (++sb == (int)nsb) { sb = 0; ++xtile; }
         }
     } else if (warp == kDequantWarps + 2) {
         // ======================================= MMA ISSUER ======================================
@@ -506,6 +523,36 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             tc_fence_after();
             if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && seg < 3) p.trace[32 * 8 + 3 + 2 * seg] = clock64();   // accumulator complete
             const bool whole = (seg_begin == tile_begin) && (seg_end == tile_end);
+            if (moe) {
+                // grouped mode: whole item per CTA; column i of the accumulator = routed row x_row0 + i of this expert's chunk, scattered
+                // to its output row (pair index) with the routing weight folded in
+                const MoeItem item = p.items[tile];
+                const int n_loc = item.n0 + row;
+                constexpr int kColsPerWarpM = kMB / 4;
+#pragma unroll
+                for (int c0 = 0; c0 < kColsPerWarpM; c0 += 8) {
+                    uint32_t acc[8], more[8];
+                    tc_ld8(tmem + kColD + lane_addr + qt * kColsPerWarpM + c0, acc);
+                    tc_ld8(tmem + kColD + kMB + lane_addr + qt * kColsPerWarpM + c0, more);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (n_loc < p.n[0]) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int mi = qt * kColsPerWarpM + c0 + i;
+                            if (mi < item.count) {
+                                const uint32_t orow = __ldg(p.row_map + item.x_row0 + mi);
+                                const float sc = p.row_scale ? __ldg(p.row_scale + orow) : 1.f;
+                                p.y[0][(int64_t)orow * p.ldy + n_loc] = (__uint_as_float(acc[i]) + __uint_as_float(more[i])) * sc;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty);
+                ++seg;
+                continue;
+            }
             const int sg = seg_of_tile(p, tile);
             const int n_idx = (tile - seg_first_tile(p, sg)) * kTileN + row;
             float* ybase = sg == 0 ? p.y[0] : (sg == 1 ? p.y[1] : p.y[2]);
@@ -832,6 +879,41 @@ void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void
     launch_pdl(fp8_scale_norm_kernel, dim3(1), dim3(256), 0, st, scale, (int64_t)((n + by - 1) / by) * sk, norm);
     count_launch();
     wq16_launch(kTypeF8, x_f16, w, scale, 0, bx, by, sk, norm, nullptr, bias, out, out_dtype, m, n, k, slabs, st, "fp8_matmul");
+}
+
+// ---- grouped (mixture-of-experts) form ------------------------------------------------------------------------------------------------
+bool qmatmul_tc_moe_supported(int n, int k, int ggml_type) {
+    if (n < 1 || k < 256 || k % 256) return false;
+    if (ggml_type == B200_GGML_Q4_K) return true;
+    if (ggml_type == B200_GGML_Q6_K) return ((int64_t)(k / 256) * 210) % 16 == 0;
+    return false;
+}
+
+void qmatmul_tc_moe(const void* xs_f16_k4, int xs_rows, const void* w, int num_experts, float* y, int64_t ldy, int n, int k, int ggml_type,
+                    const MoeItem* items, const int* num_items, int max_items, const uint32_t* row_map, const float* row_scale, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error(kErrCuda, "moe_gemm: cuTensorMapEncodeTiled unavailable"); return; }
+    if (((uintptr_t)xs_f16_k4 | (uintptr_t)w) & 15) { set_error(kErrBadArg, "moe_gemm: x and w must be 16-byte aligned"); return; }
+    const int nsb = k / 256;
+    CUtensorMap wm[kMaxSeg], xm;
+    for (int i = 0; i < kMaxSeg; ++i) if (!make_w_map(&wm[i], w, num_experts * n, nsb, ggml_type)) return;      // experts stacked along the rows
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)xs_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+        const cuuint32_t box[2] = {64, 32};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(xs_f16_k4), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "moe_gemm: activation tensor map failed (%d)", (int)r); return; }
+    }
+    if ((int64_t)max_items * nsb * sm_count() >= (int64_t)1 << 31) { set_error(kErrUnsupported, "moe_gemm: %d items x %d super-blocks exceed the 32-bit unit range", max_items, nsb); return; }
+    GemmParams p{};
+    for (int i = 0; i < kMaxSeg; ++i) { p.y[i] = y; p.n[i] = n; p.tile_end[i] = 0x7fffffff; }
+    p.ldy = ldy; p.m = 32; p.nsb = nsb; p.n_tiles = max_items; p.accumulate = 0; p.whole_tiles = 1;
+    p.items = items; p.num_items = num_items; p.row_map = row_map; p.row_scale = row_scale;
+    if (ggml_type == B200_GGML_Q4_K) launch<32, B200_GGML_Q4_K>(wm, xm, p, st); else launch<32, B200_GGML_Q6_K>(wm, xm, p, st);
+    check_launch("moe_gemm");
 }
 
 void qmatmul_tc(const void* x_f16, const void* w, float* y, int64_t ldy, int m, int n, int k, int ggml_type,

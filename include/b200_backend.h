@@ -203,6 +203,26 @@ void nvfp4_matmul(const void* x, const void* blocks, const void* scales, float g
 void mxfp4_matmul(const void* x, const void* blocks, const void* scales, const void* bias, void* out, int32_t m, int32_t n,
                   int32_t k, int32_t dtype, int64_t stream);
 
+/* ---- fused mixture-of-experts on GGUF expert tensors -- replaces attention_rs::{topk::topk_softmax, moe::moe_gemm_gguf} and the host-side
+ * sort (call sites /root/reference/src/openai/models/layers/moe.rs:35-45, :425-480, :1429-1482; quantized_qwen3_moe.rs:70-141).
+ *   topk_softmax: router_logits f32 [T, E] -> topk_weights f32 [T, k] (softmax probabilities of the k largest, NOT renormalised: the
+ *     caller applies norm_topk_prob / routed_scaling_factor like the reference), topk_ids u32 [T, k]; ties -> smaller expert id.
+ *   sort_expert_assignments: flattened topk_ids u32 [P = T * k] -> expert_ids u32 [P] ascending, sorted_token_ids u32 [P] = the pair index
+ *     (token * k + slot) at each sorted position (moe.rs:35-45; stable).
+ *   moe_gemm_gguf: out f32 [P, n]; row p = W[expert of pair p] (experts = stacked GGML blocks [E, n, k]) . x[row(p)] (* topk_weights[p] when
+ *     given); x f32 [size_m, k] with size_m == P (one row per pair: the down projection) or size_m * topk == P (one row per token: gate / up).
+ *     Activations are rounded to fp16 like QMatMul.  Q4_K / Q6_K with k % 256 == 0 (Q6_K: k % 2048 == 0) run grouped on the tcgen05
+ *     dequant-GEMM -- every expert that was hit is streamed once -- given a 256-byte aligned workspace of moe_gemm_workspace_bytes();
+ *     other shapes run a shape-generic kernel.  is_prefill is accepted for signature parity (the sort is the same here). */
+void topk_softmax(const float* router_logits, float* topk_weights, uint32_t* topk_ids, int32_t num_tokens, int32_t num_experts, int32_t topk,
+                  int64_t stream);
+void sort_expert_assignments(const uint32_t* topk_ids, uint32_t* expert_ids, uint32_t* sorted_token_ids, int32_t num_pairs, int32_t num_experts,
+                             int64_t stream);
+size_t moe_gemm_workspace_bytes(int32_t num_pairs, int32_t n, int32_t k, int32_t num_experts);
+void moe_gemm_gguf(const float* x, const void* experts, const float* topk_weights, const uint32_t* sorted_token_ids, const uint32_t* expert_ids,
+                   float* out, int32_t num_experts, int32_t topk, int32_t size_m, int32_t num_pairs, int32_t n, int32_t k, int32_t ggml_type,
+                   int32_t is_prefill, void* workspace, size_t workspace_bytes, int64_t stream);
+
 /* ---- K15 / K21: the elementwise ops between the big ones ------------------------------------
  * rms_norm: candle_nn::ops::rms_norm (layers/qrmsnorm.rs:28-31).  out_dtype F32 or F16. */
 void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int32_t n, float eps,
@@ -323,9 +343,10 @@ void b200_llama_decode_resident(b200_llama* m, int32_t num_seqs, int32_t advance
  * layer, the lm_head and the small ops between them (bench.py's roofline_gemm times the weight stream with it).  Leaves the
  * activations of the static buffers meaningless; never call it between decode steps whose results matter. */
 void b200_llama_linear_chain(b200_llama* m, int32_t num_seqs, int64_t stream);
-/* 1 when a step of `num_seqs` sequences runs on the persistent layer kernel (csrc/layer_mega.cu: one launch per layer for wo -> norm ->
- * gate|up -> SiLU -> w2 -> norm -> next QKV, split-K sums reduced in a fixed order => bitwise reproducible logits), 0 when it runs one
- * launch per GEMM (mixed weight types, NCCL all-reduce, B200_MEGA=0: split-K sums then meet in fp32 atomics, run-to-run spread ~1e-6). */
+/* 1 when a step of `num_seqs` sequences runs on the persistent layer kernel (csrc/layer_mega.cu, opt-in with B200_MEGA=1: one launch per layer
+ * for wo -> norm -> gate|up -> SiLU -> w2 -> norm -> next QKV, split-K sums reduced in a fixed order => bitwise reproducible logits, ~4 %
+ * slower), 0 when it runs one launch per GEMM (the default: split-K sums meet in fp32 atomics; the run-to-run spread of the logits is bounded
+ * and tested, tests/test_llama_gpu.py). */
 int32_t b200_llama_uses_layer_kernel(b200_llama* m, int32_t num_seqs);
 /* Profiling aid (env B200_MEGA_TRACE=<launch index> at model creation): clock64 stamps [CTA][phase 0..3][8] of that launch of the
  * persistent layer kernel, copied to `host`; returns the number of CTAs.  tools/mega_trace.py prints the timeline. */

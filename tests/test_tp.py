@@ -73,8 +73,8 @@ def test_tp2_sharding_matches_unsharded_on_gloo():
     assert err < 1e-5 and ok
 
 
-def _nccl_worker(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _nccl_worker(rank, world, port, out, mega=0):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), B200_MEGA=str(mega))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -130,8 +130,9 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mega", [0, 1], ids=["per_gemm", "layer_kernel"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_tp_decode_matches_tp1(world):
+def test_tp_decode_matches_tp1(world, mega):
     """NCCL all-reduce path and the fused peer-memory all-reduce (CUDA IPC inboxes) against the unsharded model: same greedy
     tokens.  world = 4 also exercises rows owned by ranks that hold no sequence (4 sequences, owners r % 4) and epoch parity."""
     if torch.cuda.device_count() < world:
@@ -139,7 +140,7 @@ def test_tp_decode_matches_tp1(world):
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, mega)) for r in range(world)]
     for p in procs: p.start()
     for p in procs: p.join(300)
     assert all(p.exitcode == 0 for p in procs)
