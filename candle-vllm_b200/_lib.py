@@ -20,10 +20,11 @@ def lib_path() -> str:
 # every symbol include/b200_backend.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = [
     "b200_abi_version", "b200_last_error", "b200_last_error_message", "b200_device_sm_count", "b200_device_cc",
-    "copy_blocks_bf16", "copy_blocks_f16", "copy_blocks_f32", "copy_blocks_u8", "swap_blocks", "reshape_and_cache",
+    "copy_blocks_bf16", "copy_blocks_f16", "copy_blocks_f32", "copy_blocks_u8", "swap_blocks", "flashinfer_csr_to_paged", "reshape_and_cache",
     "paged_attention_decode_workspace_bytes", "paged_attention_decode", "paged_attention_prefill",
     "qmatmul_workspace_bytes", "qmatmul_f32", "qmatmul_f16act", "qmatmul_slab_count", "qmatmul_f16act_slabs", "b200_llama_peer_inbox_bytes", "b200_llama_set_peer_inboxes", "b200_llama_peer_timeouts", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free",
     "dequantize_f32", "linear_16bit", "fp8_matmul", "nvfp4_matmul", "mxfp4_matmul",
+    "concat_and_cache_mla", "mla_paged_decode_workspace_bytes", "mla_paged_attention",
     "topk_softmax", "sort_expert_assignments", "moe_gemm_workspace_bytes", "moe_gemm_gguf",
     "rms_norm", "fused_rope_f32", "silu_mul", "add_f32", "cast", "embedding_f32", "argmax_f32", "rope_and_cache",
     "b200_llama_create", "b200_llama_destroy", "b200_llama_set_layer", "b200_llama_set_globals", "b200_llama_set_layer_ex", "b200_llama_set_globals_ex",
@@ -48,6 +49,7 @@ def lib() -> C.CDLL:
         L.paged_attention_decode_workspace_bytes.restype = C.c_size_t
         L.qmatmul_workspace_bytes.restype = C.c_size_t
         L.moe_gemm_workspace_bytes.restype = C.c_size_t
+        L.mla_paged_decode_workspace_bytes.restype = C.c_size_t
         L.b200_llama_create.restype = C.c_void_p
         L.b200_llama_peer_inbox_bytes.restype = C.c_size_t
         L.b200_ipc_alloc.restype = C.c_void_p

@@ -222,6 +222,17 @@ static void launch_rac(const void* key, const void* value, void* kc, void* vc, c
     }
 }
 
+// FlashInfer-style CSR page tables (indptr / indices / last_len, /root/reference/src/openai/pipelines/inputs.rs:477-506) -> the padded block
+// table + context lengths every attention entry point of this library reads.  Device side, no host sync: graph-replay safe.
+__global__ void csr_to_paged_kernel(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const uint32_t* __restrict__ last_len,
+                                    uint32_t* __restrict__ tables, uint32_t* __restrict__ ctx, int num_seqs, int width, int block_size) {
+    const int b = blockIdx.x;
+    if (b >= num_seqs) return;
+    const uint32_t p0 = indptr[b], pages = indptr[b + 1] - p0;
+    for (int j = threadIdx.x; j < width; j += blockDim.x) tables[(int64_t)b * width + j] = (uint32_t)j < pages ? indices[p0 + j] : 0u;
+    if (threadIdx.x == 0) ctx[b] = pages == 0 ? 0u : (pages - 1) * (uint32_t)block_size + last_len[b];      // kv_len (inputs.rs:523-531)
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -232,6 +243,15 @@ void copy_blocks_bf16(void* k, void* v, const void* m, int32_t nl, int32_t np, i
 void copy_blocks_f16(void* k, void* v, const void* m, int32_t nl, int32_t np, int32_t numel, int64_t s) { copy_blocks_impl(k, v, m, nl, np, numel, 2, s); }
 void copy_blocks_f32(void* k, void* v, const void* m, int32_t nl, int32_t np, int32_t numel, int64_t s) { copy_blocks_impl(k, v, m, nl, np, numel, 4, s); }
 void copy_blocks_u8(void* k, void* v, const void* m, int32_t nl, int32_t np, int32_t numel, int64_t s) { copy_blocks_impl(k, v, m, nl, np, numel, 1, s); }
+
+void flashinfer_csr_to_paged(const uint32_t* indptr, const uint32_t* indices, const uint32_t* last_len, uint32_t* block_tables, uint32_t* context_lens,
+                             int32_t num_seqs, int32_t max_blocks_per_seq, int32_t block_size, int64_t stream) {
+    if (num_seqs == 0) return;
+    B200_REQUIRE(indptr && indices && last_len && block_tables && context_lens && max_blocks_per_seq > 0 && block_size > 0, kErrBadArg, "flashinfer_csr_to_paged: bad arguments");
+    csr_to_paged_kernel<<<num_seqs, 128, 0, as_stream(stream)>>>(indptr, indices, last_len, block_tables, context_lens, num_seqs, max_blocks_per_seq, block_size);
+    count_launch();
+    check_launch("flashinfer_csr_to_paged");
+}
 
 void swap_blocks(const void* src, void* dst, const int64_t* mapping, int32_t num_pairs,
                  int64_t bytes_per_block, int64_t stream) {

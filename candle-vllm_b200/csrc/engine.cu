@@ -83,6 +83,7 @@ struct b200_llama {
 
     // persistent layer kernel (layer_mega.cu): per-tile partial-sum slabs of the GEMM phases and the grid-wide counters
     bool use_mega = false;
+    int mega_mode = 0;             // B200_MEGA: 0 one launch per GEMM with atomics (legacy), 1 fused layer kernel, 2 split deterministic
     long long tp_timeout_ms = 120000;
     int mega_G = 0, s_qkv = 1, s_ro = 1, s_gu = 1;                // slabs per buffer (max CTAs sharing one tile)
     float* qkv_slabs = nullptr; float* ro_slabs = nullptr; float* gate_slabs = nullptr; float* up_slabs = nullptr;
@@ -201,7 +202,7 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
         if (fused_ar) for (int i = 0; i < c.tp_world; ++i) P.peers.p[i] = static_cast<char*>(m->peers[i]);
         P.trace = launch == m->mega_trace_launch ? m->mega_trace : nullptr;
         static const int trig = [] { const char* e = getenv("B200_MEGA_TRIGGER"); return e ? atoi(e) : 0; }();     // early trigger measured 9 % slower
-        P.early_trigger = trig;
+        P.early_trigger = m->mega_mode == 2 ? 1 : trig;      // single-phase launches behave like the per-GEMM kernels: let the next grid start early
     };
     auto qkv_phase = [&](MegaParams& P, MegaPhase& ph, const b200_llama_layer_ex& w, int map0) -> bool {
         if (!mega_make_w_map(&P.maps[map0], w.wq.w, qd, H) || !mega_make_w_map(&P.maps[map0 + 1], w.wk.w, kd, H) ||
@@ -269,7 +270,24 @@ int forward_mega(b200_llama* m, int B, cudaStream_t st, bool linear_only) {
             e.n_tiles = 0; e.nsb = 0; e.tile_end[0] = e.tile_end[1] = e.tile_end[2] = 0x7fffffff;
         }
         P.n_phases = 4;
-        mega_launch(P, st);
+        if (m->mega_mode == 2) {
+            // "split" mode: the same phases and the same deterministic slab reduction, but one launch per GEMM phase and the elementwise op
+            // as its own small kernel in between, all chained by programmatic dependent launch
+            for (int i = 0; i < 4; ++i) {
+                if (P.phase[i].eop != kEopNone) {
+                    MegaParams E = P;
+                    E.phase[0] = P.phase[i - 1]; E.phase[1] = P.phase[i]; E.n_phases = 2;
+                    mega_eop_launch(E, P.phase[i].eop, st);
+                }
+                if (P.phase[i].n_tiles > 0) {
+                    MegaParams S = P;
+                    S.phase[0] = P.phase[i]; S.phase[0].eop = kEopNone; S.n_phases = 1; S.early_trigger = 1;
+                    mega_launch(S, st);
+                }
+            }
+        } else {
+            mega_launch(P, st);
+        }
     }
     lm_head(m, B, st);
     const int live_cols = std::max(0, std::min(m->vocab_l, c.vocab - c.tp_rank * m->vocab_l));
@@ -539,6 +557,7 @@ b200_llama* b200_llama_create(const b200_llama_config* cfg) {
              dmalloc(m->gate_slabs, (size_t)m->s_gu * B * m->ffn_l) && dmalloc(m->up_slabs, (size_t)m->s_gu * B * m->ffn_l) &&
              dmalloc(m->mega_counters, m->mega_counter_bytes / sizeof(uint32_t));
         m->use_mega = ok && m->s_qkv <= kMegaMaxSlabs && m->s_ro <= kMegaMaxSlabs && m->s_gu <= 4;
+        m->mega_mode = mega_on;
         if (const char* tr = getenv("B200_MEGA_TRACE")) {
             m->mega_trace_launch = atoi(tr);
             ok = ok && dmalloc(m->mega_trace, (size_t)G * kMegaMaxPhases * 8);

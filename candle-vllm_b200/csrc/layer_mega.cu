@@ -119,11 +119,11 @@ __device__ __forceinline__ float block_sum_512(float v, float* red, int tid) {
 
 // ---- elementwise ops between the GEMM phases (run by the 512 dequant-warp threads of every CTA) -------------------------------
 // x[row] += sum of the previous phase's slabs; act_out[row] = RMSNorm(x[row]) * w  (f16, K4 order).  One row per CTA.
-__device__ __forceinline__ void eop_norm(const MegaParams& P, const MegaPhase& prev, const MegaPhase& cur, float* red, int tid) {
+__device__ __forceinline__ void eop_norm(const MegaParams& P, const MegaPhase& prev, const MegaPhase& cur, float* red, int tid, uint32_t gemm_grid) {
     const int row = blockIdx.x;
     if (row >= P.m) return;
     const int n = P.hidden, nv = n >> 2;
-    const uint32_t nsb = (uint32_t)prev.nsb, total = (uint32_t)prev.n_tiles * nsb, G = total < gridDim.x ? total : gridDim.x;
+    const uint32_t nsb = (uint32_t)prev.nsb, total = (uint32_t)prev.n_tiles * nsb, G = total < gemm_grid ? total : gemm_grid;
     float* xr = P.x + (int64_t)row * n;
     float4 v[4];
     float ss = 0.f;
@@ -155,9 +155,9 @@ __device__ __forceinline__ void eop_norm(const MegaParams& P, const MegaPhase& p
 }
 
 // act_out = silu(gate) * up (f16, K4 order); gate / up = slab sums of segments 0 / 1 of the previous phase.  Grid-stride.
-__device__ __forceinline__ void eop_silu(const MegaParams& P, const MegaPhase& prev, const MegaPhase& cur, int tid) {
+__device__ __forceinline__ void eop_silu(const MegaParams& P, const MegaPhase& prev, const MegaPhase& cur, int tid, uint32_t gemm_grid) {
     const int F = prev.n[0], fv = F >> 2;
-    const uint32_t nsb = (uint32_t)prev.nsb, total = (uint32_t)prev.n_tiles * nsb, G = total < gridDim.x ? total : gridDim.x;
+    const uint32_t nsb = (uint32_t)prev.nsb, total = (uint32_t)prev.n_tiles * nsb, G = total < gemm_grid ? total : gemm_grid;
     const int t_up = prev.tile_end[0];
     const int items = P.m * fv;
     __half* out = static_cast<__half*>(cur.act_out);
@@ -196,11 +196,11 @@ __device__ __forceinline__ void ll_wait(const void* addr, uint32_t e, uint4& w, 
         }
     }
 }
-__device__ __forceinline__ void eop_tp_norm(const MegaParams& P, const MegaPhase& prev, const MegaPhase& cur, float* red, int tid) {
+__device__ __forceinline__ void eop_tp_norm(const MegaParams& P, const MegaPhase& prev, const MegaPhase& cur, float* red, int tid, uint32_t gemm_grid) {
     const int row = blockIdx.x;
     if (row >= P.m) return;
     const int n = P.hidden, nv = n >> 2, world = P.tp_world, rank = P.tp_rank, rows_max = P.rows_max;
-    const uint32_t nsb = (uint32_t)prev.nsb, total = (uint32_t)prev.n_tiles * nsb, G = total < gridDim.x ? total : gridDim.x;
+    const uint32_t nsb = (uint32_t)prev.nsb, total = (uint32_t)prev.n_tiles * nsb, G = total < gemm_grid ? total : gemm_grid;
     const TpInboxLayout lay(world, rows_max, n);
     char* const mine = P.peers.p[rank];
     uint32_t* epoch = reinterpret_cast<uint32_t*>(mine + lay.epoch_off);
@@ -292,9 +292,9 @@ __device__ __forceinline__ void run_eop(const MegaParams& P, int ph, float* red)
     pdl_wait();                                                                // x / the slabs may still be in use by the previous kernel
     if (tid == 0) { trace_stamp(P, ph, 1); wait_counter(P.counters + 2 * ph, gridDim.x, P.error_word); trace_stamp(P, ph, 2); }   // phase ph-1 complete everywhere
     named_bar_sync(1, kDeqThreads);
-    if (g.eop == kEopNorm) eop_norm(P, prev, g, red, tid);
-    else if (g.eop == kEopSilu) eop_silu(P, prev, g, tid);
-    else eop_tp_norm(P, prev, g, red, tid);
+    if (g.eop == kEopNorm) eop_norm(P, prev, g, red, tid, gridDim.x);
+    else if (g.eop == kEopSilu) eop_silu(P, prev, g, tid, gridDim.x);
+    else eop_tp_norm(P, prev, g, red, tid, gridDim.x);
     named_bar_sync(1, kDeqThreads);                                            // every thread's stores are issued
     // bar.sync orders the other threads' stores before thread 0 at CTA scope; its gpu-scope release is cumulative over them
     if (tid == 0) { red_release_gpu_add(P.counters + 2 * ph + 1, 1u); trace_stamp(P, ph, 3); }
@@ -577,6 +577,21 @@ layer_mega_kernel(const __grid_constant__ MegaParams P) {
     }
 }
 
+// The same elementwise ops as stand-alone kernels ("split" mode: one launch per GEMM phase with programmatic dependent launch between
+// them -- kernel boundaries turned out cheaper than in-kernel grid syncs -- but still the deterministic slab reduction).  `src` / `dst`
+// are the phase that produced the slabs and the phase that will read the activations; gemm_grid = the grid of the producing launch.
+__global__ void __launch_bounds__(kDeqThreads)
+mega_eop_kernel(const __grid_constant__ MegaParams P, int eop, uint32_t gemm_grid) {
+    __shared__ float red[32];
+    pdl_wait();
+    pdl_trigger();
+    const MegaPhase& prev = P.phase[0];
+    const MegaPhase& cur = P.phase[1];
+    if (eop == kEopNorm) eop_norm(P, prev, cur, red, threadIdx.x, gemm_grid);
+    else if (eop == kEopSilu) eop_silu(P, prev, cur, threadIdx.x, gemm_grid);
+    else eop_tp_norm(P, prev, cur, red, threadIdx.x, gemm_grid);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -640,6 +655,16 @@ bool mega_make_x_map(CUtensorMap* map, const void* x_f16, int m, int k) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error(kErrCuda, "layer_mega: activation tensor map failed (%d)", (int)r); return false; }
     return true;
+}
+
+// stand-alone elementwise op between two single-phase launches: P.phase[0] = the phase whose slabs are folded, P.phase[1] = the consumer
+// (eop, norm_w, act_out); no tensor maps needed
+void mega_eop_launch(const MegaParams& P, int eop, cudaStream_t st) {
+    const int G = mega_grid();
+    const int grid = eop == kEopSilu ? G : P.m;
+    launch_pdl(mega_eop_kernel, dim3(grid), dim3(kDeqThreads), 0, st, P, eop, (uint32_t)G);
+    count_launch();
+    check_launch("layer_mega(eop)");
 }
 
 void mega_launch(const MegaParams& P, cudaStream_t st) {

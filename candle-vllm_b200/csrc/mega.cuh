@@ -65,6 +65,7 @@ bool mega_supported(int m, int hidden, int k_max);
 bool mega_make_w_map(CUtensorMap* map, const void* w, int n, int k);
 bool mega_make_x_map(CUtensorMap* map, const void* x_f16, int m, int k);
 void mega_launch(const MegaParams& P, cudaStream_t st);
+void mega_eop_launch(const MegaParams& P, int eop, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ---- deterministic split-K bookkeeping (the same arithmetic on the producer and the consumer side) --------------------------

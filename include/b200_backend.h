@@ -71,6 +71,13 @@ void copy_blocks_u8  (void* key_cache_ptrs, void* value_cache_ptrs, const void* 
 void swap_blocks(const void* src, void* dst, const int64_t* mapping, int32_t num_pairs,
                  int64_t bytes_per_block, int64_t stream);
 
+/* ---- FlashInfer-style page tables (the reference's default build): indptr u32 [B + 1], indices u32 [nnz] (physical block ids, sequence by
+ * sequence), last_len u32 [B] (tokens in each sequence's last page), as built at /root/reference/src/openai/pipelines/inputs.rs:477-506 ->
+ * block_tables u32 [B, max_blocks_per_seq] (0-padded) and context_lens u32 [B] = (pages - 1) * block_size + last_len (inputs.rs:523-531), on
+ * the device and stream-ordered, so a host that only has CSR metadata (graph.rs:471-803 static buffers) can drive every entry point below. */
+void flashinfer_csr_to_paged(const uint32_t* indptr, const uint32_t* indices, const uint32_t* last_len, uint32_t* block_tables, uint32_t* context_lens,
+                             int32_t num_seqs, int32_t max_blocks_per_seq, int32_t block_size, int64_t stream);
+
 /* ---- K3: reshape_and_cache -- the cache write inside PagedAttention::forward ----------------
  * Call sites: /root/reference/src/openai/models/layers/attention.rs:707-718, :983-994; slot math
  * /root/reference/src/openai/pipelines/inputs.rs:180-194, :410-423.
@@ -202,6 +209,24 @@ void nvfp4_matmul(const void* x, const void* blocks, const void* scales, float g
                   void* out, int32_t m, int32_t n, int32_t k, int32_t dtype, int64_t stream);
 void mxfp4_matmul(const void* x, const void* blocks, const void* scales, const void* bias, void* out, int32_t m, int32_t n,
                   int32_t k, int32_t dtype, int64_t stream);
+
+/* ---- multi-head latent attention (DeepSeek-V2 / V3) -- replaces attention_rs::mla::{concat_and_cache_mla, mla_paged_decode, mla_paged_prefill}
+ * (call sites /root/reference/src/openai/models/layers/mla_attention.rs:479-552; cache shapes /root/reference/src/scheduler/cache_engine.rs:172-185).
+ *   concat_and_cache_mla: ckv [T, kv_lora_rank], k_pe [T, qk_rope_head_dim] -> ckv_cache [nb, bs, 1, kv_lora_rank], kpe_cache [nb, bs, 1, rope] at
+ *     slot_mapping[t] (negative = pad, skipped); 16-bit `dtype`, bit copy.
+ *   mla_paged_attention: "absorbed" MLA: q_absorbed [rows, H, kv_lora_rank] (W_uk already folded in), q_pe [rows, H, rope];
+ *     score = (q_abs . ckv + q_pe . kpe) * sm_scale over the keys of the sequence, out [rows, H, kv_lora_rank] = softmax . ckv (the caller applies
+ *     W_uv).  cu_seqlens_q == NULL: decode (one row per sequence, context_lens INCLUDING the new token); otherwise causal chunked prefill where
+ *     sequence i owns rows cu_seqlens_q[i] .. cu_seqlens_q[i+1] = the last positions of its context_lens[i] keys.  Decode with latent 512 / rope 64 /
+ *     block 64 runs the tensor-core split-KV kernel (workspace of mla_paged_decode_workspace_bytes, num_blocks = blocks in the cache); everything
+ *     else a shape-generic kernel. */
+void concat_and_cache_mla(const void* ckv, const void* k_pe, void* ckv_cache, void* kpe_cache, const int64_t* slot_mapping, int32_t num_tokens,
+                          int32_t kv_lora_rank, int32_t qk_rope_head_dim, int32_t dtype, int64_t stream);
+size_t mla_paged_decode_workspace_bytes(int32_t num_seqs, int32_t num_heads, int32_t max_blocks_per_seq, int32_t block_size);
+void mla_paged_attention(void* out, const void* q_absorbed, const void* q_pe, const void* ckv_cache, const void* kpe_cache, const uint32_t* block_tables,
+                         const uint32_t* context_lens, const uint32_t* cu_seqlens_q, int32_t num_seqs, int32_t num_rows, int32_t num_heads,
+                         int32_t kv_lora_rank, int32_t qk_rope_head_dim, int32_t block_size, int32_t max_blocks_per_seq, int64_t num_blocks, float sm_scale,
+                         int32_t dtype, void* workspace, size_t workspace_bytes, int64_t stream);
 
 /* ---- fused mixture-of-experts on GGUF expert tensors -- replaces attention_rs::{topk::topk_softmax, moe::moe_gemm_gguf} and the host-side
  * sort (call sites /root/reference/src/openai/models/layers/moe.rs:35-45, :425-480, :1429-1482; quantized_qwen3_moe.rs:70-141).

@@ -26,7 +26,8 @@ def topk_softmax(logits: np.ndarray, k: int):
 def expert_weight(stacked: np.ndarray, ggml_type: int, e: int, n: int, k: int) -> np.ndarray:
     bb, be = G.BLOCK_BYTES[ggml_type], G.BLOCK_ELEMS[ggml_type]
     per = n * (k // be) * bb
-    return G.dequantize_weight(stacked[e * per:(e + 1) * per], ggml_type, n, k)
+    flat = np.asarray(stacked, np.uint8).reshape(-1)
+    return G.dequantize_weight(flat[e * per:(e + 1) * per], ggml_type, n, k)
 
 
 def moe_gemm(x, stacked, ggml_type, E, n, k, topk_ids_flat, topk, weights_flat=None):

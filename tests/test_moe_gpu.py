@@ -45,7 +45,7 @@ def test_sort_expert_assignments_is_a_stable_ascending_sort():
 ])
 def test_moe_gemm_gguf_matches_oracle(ggml_type, E, N, K, T, k):
     rng = np.random.default_rng(E + N + T)
-    stacked = np.concatenate([G.random_weight(rng, ggml_type, N, K) for _ in range(E)])
+    stacked = np.concatenate([G.random_weight(rng, ggml_type, N, K).reshape(-1) for _ in range(E)])
     ids = np.stack([rng.permutation(E)[:k] for _ in range(T)]).astype(np.int32)
     tw = rng.uniform(0.05, 0.5, (T, k)).astype(np.float32)
     x = rng.standard_normal((T, K)).astype(np.float32)
@@ -67,9 +67,9 @@ def test_fused_moe_block_matches_oracle():
     rng = np.random.default_rng(5)
     E, H, I, k, T = 32, 2048, 768, 8, 16
     gate = (rng.standard_normal((E, H)) * 0.05).astype(np.float32)
-    ge = np.concatenate([G.random_weight(rng, 12, I, H) for _ in range(E)])
-    ue = np.concatenate([G.random_weight(rng, 12, I, H) for _ in range(E)])
-    de = np.concatenate([G.random_weight(rng, 12, H, I) for _ in range(E)])
+    ge = np.concatenate([G.random_weight(rng, 12, I, H).reshape(-1) for _ in range(E)])
+    ue = np.concatenate([G.random_weight(rng, 12, I, H).reshape(-1) for _ in range(E)])
+    de = np.concatenate([G.random_weight(rng, 12, H, I).reshape(-1) for _ in range(E)])
     x = rng.standard_normal((T, H)).astype(np.float32)
     t = lambda a: torch.from_numpy(a).to(DEV)
     blk = pkg.FusedMoe(t(gate), t(ge), t(ue), t(de), (12, 12, 12), E, H, I, k)
