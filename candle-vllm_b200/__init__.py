@@ -10,11 +10,11 @@ There is no CPU fallback: without the CUDA library / an sm_100 GPU every op rais
 """
 from ._lib import BackendError, lib, lib_path, device_ok  # noqa: F401
 from .backend import (  # noqa: F401
-    DType, GgmlType, KvLayout, copy_blocks, swap_blocks, reshape_and_cache, InputMetadata,
+    DType, GgmlType, KvLayout, copy_blocks, swap_blocks, reshape_and_cache, InputMetadata, FlashInferMetadata,
     PagedAttention, QTensor, QMatMul, Linear, LnFp8, LnNvfp4, LnMxfp4, rms_norm, fused_rope, silu_mul, argmax, dequantize,
 )
 from .cache_engine import CacheConfig, CacheEngine  # noqa: F401
-from .inputs import prepare_decode, prepare_prompt, used_blocks_for_len, PAD_SLOT_ID  # noqa: F401
+from .inputs import prepare_decode, prepare_prompt, used_blocks_for_len, flashinfer_csr, PAD_SLOT_ID  # noqa: F401
 from .llama import LlamaConfig, GGUFLLaMa, MarlinWeight  # noqa: F401
 from .block_manager import BlockManager, PrefixCache, PrefixCacheConfig, Seq, SeqGroup, AllocStatus  # noqa: F401
 from .gptq import gptq_matmul, marlin_weight_repack, marlin_permute_scales  # noqa: F401

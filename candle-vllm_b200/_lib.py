@@ -32,7 +32,7 @@ SYMBOLS = [
     "b200_llama_logits", "b200_llama_next_tokens", "b200_llama_kernel_launches",
     "b200_llama_read_next_tokens", "b200_llama_read_logits",
     "b200_total_kernel_launches", "b200_allreduce_f32",
-    "gptq_repack", "awq_repack", "marlin_4bit_f16", "marlin_4bit_bf16", "marlin_awq_4bit_f16", "marlin_awq_4bit_bf16",
+    "gptq_repack", "marlin_checkpoint_repack", "awq_repack", "marlin_4bit_f16", "marlin_4bit_bf16", "marlin_awq_4bit_f16", "marlin_awq_4bit_bf16",
     "gemm_half_q_half_alt", "b200_set_scratch",
 ]
 

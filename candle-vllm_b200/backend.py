@@ -179,6 +179,33 @@ class InputMetadata:
     is_mtp_verify: bool = False
 
 
+@dataclass
+class FlashInferMetadata:
+    """The CSR page-table encoding of the reference's flashinfer build (``FlashInferMetadata``, inputs.rs:477-549): ``indptr`` u32 [B + 1],
+    ``indices`` u32 [nnz] physical block ids sequence by sequence, ``last_len`` u32 [B] tokens in each sequence's last page."""
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    last_len: torch.Tensor
+    max_blocks_per_seq: int = 0
+
+    def to_paged(self, block_size: int):
+        """-> (block_tables i32 [B, W] 0-padded, context_lens i32 [B]) on the device, through ``flashinfer_csr_to_paged`` (no host sync;
+        W = max_blocks_per_seq, which the host knows from its own tables -- graph replay uses the static width)."""
+        require_device()
+        B = self.last_len.numel()
+        W = int(self.max_blocks_per_seq)
+        if W <= 0:
+            raise BackendError("FlashInferMetadata.max_blocks_per_seq must be set (static table width)")
+        dev = self.indptr.device
+        bt = torch.empty((B, W), dtype=torch.int32, device=dev)
+        cl = torch.empty((B,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            lib().flashinfer_csr_to_paged(_ptr(self.indptr), _ptr(self.indices), _ptr(self.last_len), _ptr(bt), _ptr(cl), C.c_int32(B), C.c_int32(W),
+                                          C.c_int32(block_size), _stream(dev))
+        check("flashinfer_csr_to_paged")
+        return bt, cl
+
+
 class PagedAttention:
     """``PagedAttention::new(num_heads, head_dim, scale, num_kv_heads, sliding_window, device, alibi,
     fp8_kvcache)`` / ``.forward(q, k, v, mask, k_cache, v_cache, &meta, softcap)`` (attention-rs;
@@ -234,8 +261,13 @@ class PagedAttention:
         odt = out_dtype or query.dtype
         out = torch.empty((T, H, hd), dtype=odt, device=query.device)
         bt = meta.block_tables
+        if bt is None and meta.flashinfer_metadata is not None and not meta.is_prefill:
+            # the reference's default (flashinfer) build hands CSR page tables instead (inputs.rs:477-506): expand them on the device
+            fm = meta.flashinfer_metadata
+            bt, cl_csr = fm.to_paged(bs)
+            meta = InputMetadata(False, meta.slot_mapping, bt, cl_csr)
         if bt is None:
-            raise BackendError("InputMetadata.block_tables is required")
+            raise BackendError("InputMetadata.block_tables (or flashinfer_metadata for decode) is required")
         if bt.dtype not in (torch.int32, torch.uint32) or not bt.is_contiguous():
             raise BackendError("block_tables must be contiguous u32/i32")
         cache_dt = DType.FP8_E4M3 if fp8 else _dt(key_cache)

@@ -13,6 +13,7 @@
 // 8 bit) takes the shape-generic gemm_half_q_half_alt kernel, as in the reference (gptq.rs:182-197).
 #include <map>
 #include <mutex>
+#include <set>
 #include <utility>
 
 #include "qmatmul.cuh"
@@ -55,6 +56,51 @@ __global__ void awq_repack_kernel(const uint32_t* __restrict__ in, uint32_t* __r
         }
         out[(int64_t)col * kw + wk] = o;
     }
+}
+
+// Marlin checkpoint format (`B` u32 [K/16, 2N], checkpoint_format == "marlin", /root/reference/src/openai/models/linear.rs:219-251) -> GPTQ packing
+// u32 [K/8, N], from which gptq_repack makes this library's layout.  The tile order is the Marlin project's published one (IST-DASLab/marlin,
+// `_get_perms` / `Layer.pack`; restated in oracle/gptq.py): w[k][n] sits in row k / 16, tile-flat position (n / 16) * 256 + (k % 16) * 16 + n % 16,
+// permuted inside every 1024 values by `perm` (inv_perm below, built once on the host) and packed 8 nibbles per word with stride 8.
+__constant__ uint16_t c_marlin_inv_perm[1024];
+__global__ void marlin_to_gptq_kernel(const uint32_t* __restrict__ B, uint32_t* __restrict__ out, int k, int n) {
+    const int64_t total = (int64_t)(k / 8) * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int col = (int)(i % n), kp = (int)(i / n);
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kk = kp * 8 + j;
+            const int64_t t = (int64_t)(col >> 4) * 256 + (kk & 15) * 16 + (col & 15);         // position in the row of 16 x 16 tiles
+            const int64_t c = (t & ~(int64_t)1023) + c_marlin_inv_perm[t & 1023];               // after the permutation
+            const uint32_t word = B[(int64_t)(kk >> 4) * (2 * n) + (c >> 3)];
+            o |= ((word >> (4 * (c & 7))) & 0xFu) << (4 * j);
+        }
+        out[i] = o;
+    }
+}
+static bool upload_marlin_inv_perm() {
+    static std::mutex mu;
+    static std::set<int> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.count(dev)) return true;
+    int perm[1024], n = 0;
+    for (int i = 0; i < 32; ++i) {
+        int perm1[8], c = 0;
+        const int col = i / 4;
+        for (int block = 0; block < 2; ++block)
+            for (int row : {2 * (i % 4), 2 * (i % 4) + 1, 2 * (i % 4 + 4), 2 * (i % 4 + 4) + 1}) perm1[c++] = 16 * row + col + 8 * block;
+        for (int j = 0; j < 4; ++j) for (int q = 0; q < 8; ++q) perm[n++] = perm1[q] + 256 * j;
+    }
+    static const int interleave[8] = {0, 2, 4, 6, 1, 3, 5, 7};
+    uint16_t inv[1024];
+    for (int g = 0; g < 128; ++g)
+        for (int q = 0; q < 8; ++q) inv[perm[g * 8 + interleave[q]]] = (uint16_t)(g * 8 + q);      // res[x] = w[perm'[x]], perm' = interleaved perm
+    if (cudaMemcpyToSymbol(c_marlin_inv_perm, inv, sizeof(inv)) != cudaSuccess) return false;
+    done.insert(dev);
+    return true;
 }
 
 // Conventional GPTQ (act-order and / or asymmetric, 4 or 8 bit): the shape-generic path behind gemm_half_q_half_alt
@@ -175,6 +221,19 @@ void b200_set_scratch(void* ptr, size_t bytes) {
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     if (ptr && bytes) g_user_scratch[dev] = Scratch{ptr, bytes, false};
     else g_user_scratch.erase(dev);
+}
+
+void marlin_checkpoint_repack(const void* marlin_b, void* out, void* scratch_gptq, int32_t k, int32_t n, int64_t stream) {
+    B200_REQUIRE(marlin_b && out && scratch_gptq && k > 0 && n > 0, kErrBadArg, "marlin_checkpoint_repack: bad arguments");
+    B200_REQUIRE(k % 64 == 0 && n % 64 == 0, kErrUnsupported, "marlin_checkpoint_repack: k and n must be multiples of 64 (k=%d n=%d)", k, n);
+    B200_REQUIRE(upload_marlin_inv_perm(), kErrCuda, "marlin_checkpoint_repack: permutation upload failed");
+    const int64_t total = (int64_t)(k / 8) * n;
+    int64_t g = (total + 255) / 256;
+    if (g > (int64_t)sm_count() * 16) g = (int64_t)sm_count() * 16;
+    marlin_to_gptq_kernel<<<(int)g, 256, 0, as_stream(stream)>>>((const uint32_t*)marlin_b, (uint32_t*)scratch_gptq, k, n);
+    count_launch();
+    if (!check_launch("marlin_checkpoint_repack")) return;
+    gptq_repack(scratch_gptq, out, k / 8, n, stream);
 }
 
 void gptq_repack(const void* in, void* out, int32_t k_packed, int32_t n, int64_t stream) {

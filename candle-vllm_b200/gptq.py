@@ -52,6 +52,20 @@ def marlin_weight_repack(qweight: torch.Tensor, bits: int = 4, is_awq: bool = Fa
     return out
 
 
+def marlin_checkpoint_repack(b: torch.Tensor, size_k: int, size_n: int) -> torch.Tensor:
+    """Weights of a checkpoint that is ALREADY in Marlin format (``B`` u32 [K/16, 2N], linear.rs:219-251) -> the layout ``gptq_matmul`` reads
+    (what ``marlin_weight_repack`` would have produced from the GPTQ tensors), same shape."""
+    require_device()
+    if b.dtype not in (torch.int32, torch.uint32) or tuple(b.shape) != (size_k // 16, size_n * 2):
+        raise BackendError(f"marlin B tensor must be u32 [{size_k // 16}, {size_n * 2}], got {tuple(b.shape)} {b.dtype}")
+    out = torch.empty_like(b)
+    scratch = torch.empty((size_k // 8, size_n), dtype=torch.int32, device=b.device)
+    with torch.cuda.device(b.device):
+        lib().marlin_checkpoint_repack(_ptr(b.contiguous()), _ptr(out), _ptr(scratch), C.c_int32(size_k), C.c_int32(size_n), _stream(b.device))
+    check("marlin_checkpoint_repack")
+    return out
+
+
 def gptq_matmul(x: torch.Tensor, qweight: torch.Tensor, scales: torch.Tensor, qzeros: Optional[torch.Tensor],
                 g_idx: Optional[torch.Tensor], workspace: Optional[torch.Tensor], bits: int, group_size: int,
                 is_awq: bool = False) -> torch.Tensor:

@@ -97,6 +97,23 @@ def prepare_prompt(prompts: Sequence[Sequence[int]], block_tables: Sequence[Sequ
                 block_tables=_pad_tables(tabs), max_context_len=max_k)
 
 
+def flashinfer_csr(lens: Sequence[int], block_tables: Sequence[Sequence[int]], block_size: int) -> dict:
+    """The CSR page tables the reference builds for its flashinfer backend (inputs.rs:477-531): ``indptr`` [B + 1], ``indices`` (the used
+    blocks of every sequence, back to back), ``last_len`` = (len - 1) % block_size + 1 (0 for an empty sequence) and the derived
+    ``kv_len`` = (pages - 1) * block_size + last_len."""
+    indptr, indices, last_len, kv_len = [0], [], [], []
+    for n, table in zip(lens, block_tables):
+        used = used_blocks_for_len(int(n), block_size, len(table))
+        indices.extend(int(b) for b in table[:used])
+        indptr.append(len(indices))
+        last = 0 if n == 0 else (int(n) - 1) % block_size + 1
+        last_len.append(last)
+        pages = indptr[-1] - indptr[-2]
+        kv_len.append(0 if pages == 0 else (pages - 1) * block_size + last)
+    return dict(indptr=np.asarray(indptr, np.uint32), indices=np.asarray(indices, np.uint32), last_len=np.asarray(last_len, np.uint32),
+                kv_len=np.asarray(kv_len, np.uint32))
+
+
 def to_device(prep: dict, device="cuda"):
     """numpy metadata -> (tokens i64, positions i64, InputMetadata) on the device."""
     import torch

@@ -172,6 +172,11 @@ void dequantize_f32(const void* w, float* out, int64_t n, int64_t k, int32_t ggm
  *   [k/pack, n] packed along k, qzeros u32 [G, n/pack] packed along n and stored minus one, scales f16 [G, n], g_idx i32 [k]
  *   (required), out f16 [m,n]; shape-generic SIMT kernel. */
 void gptq_repack(const void* in, void* out, int32_t k_packed, int32_t n, int64_t stream);
+/* Pre-repacked "marlin" checkpoints (checkpoint_format == "marlin": tensors `B` u32 [K/16, 2N] and `s`, linear.rs:219-251) carry the Marlin project's
+ * tile order, which the reference hands to marlin_4bit_* unchanged.  This library's GEMM reads its own row-major int4 layout, so such a checkpoint
+ * needs ONE extra load-time call: marlin_checkpoint_repack(B) -> the layout marlin_4bit_* reads (same word count; scratch_gptq = k/8 * n words of
+ * scratch; `s` is used as is: it already is in marlin_permute_scales order).  k % 64 == 0, n % 64 == 0. */
+void marlin_checkpoint_repack(const void* marlin_b, void* out, void* scratch_gptq, int32_t k, int32_t n, int64_t stream);
 void awq_repack(const void* in, void* out, int32_t k, int32_t n_packed, int32_t bits, int64_t stream);
 void marlin_4bit_f16(const void* x, const int32_t* qweight, const void* scales, const void* qzeros, const void* g_idx,
                      void* out, int32_t m, int32_t k, int32_t n, const void* workspace, int32_t group_size, int64_t stream);

@@ -134,3 +134,45 @@ def dequant_gptq_alt(qweight: np.ndarray, qzeros: np.ndarray, scales: np.ndarray
     z = unpack_cols(qzeros).astype(np.float64)[np.asarray(g_idx, np.int64)] + 1.0
     s = np.asarray(scales, np.float64)[np.asarray(g_idx, np.int64)]
     return ((q - z) * s).T
+
+
+# ---- Marlin checkpoint format (checkpoint_format == "marlin": tensors `B` u32 [K/16, 2N] and `s`, /root/reference/src/openai/models/linear.rs:219-251) ----
+# The tile order is defined by the Marlin project (IST-DASLab/marlin, marlin/__init__.py: `_get_perms` and `Layer.pack`; third-party, not in
+# /root/reference -- only its scale permutation is, linear.rs:341-352, and it is the same `_get_perms` function).  Restated from the published
+# algorithm: w [K, N] -> 16 x 16 tiles -> rows of N * 16 values -> a fixed permutation inside every 1024 values -> 8 nibbles per word, strided.
+def marlin_weight_perm() -> np.ndarray:
+    perm = []
+    for i in range(32):
+        perm1 = []
+        col = i // 4
+        for block in (0, 1):
+            for row in (2 * (i % 4), 2 * (i % 4) + 1, 2 * (i % 4 + 4), 2 * (i % 4 + 4) + 1):
+                perm1.append(16 * row + col + 8 * block)
+        for j in range(4):
+            perm.extend(p + 256 * j for p in perm1)
+    perm = np.asarray(perm, np.int64)
+    interleave = np.asarray([0, 2, 4, 6, 1, 3, 5, 7])
+    return perm.reshape(-1, 8)[:, interleave].ravel()
+
+
+def pack_marlin(q: np.ndarray) -> np.ndarray:
+    """q u8 [K, N] in 0..15 -> B u32 [K/16, 2N] (Marlin `Layer.pack`)."""
+    K, N = q.shape
+    perm = marlin_weight_perm()
+    w = q.reshape(K // 16, 16, N // 16, 16).transpose(0, 2, 1, 3).reshape(K // 16, N * 16)
+    res = w.reshape(-1, perm.size)[:, perm].reshape(w.shape).astype(np.uint32)
+    out = np.zeros((res.shape[0], res.shape[1] // 8), np.uint32)
+    for i in range(8):
+        out |= res[:, i::8] << np.uint32(4 * i)
+    return out
+
+
+def unpack_marlin(B: np.ndarray, K: int, N: int) -> np.ndarray:
+    """inverse of pack_marlin -> q u8 [K, N]."""
+    perm = marlin_weight_perm()
+    res = np.empty((K // 16, N * 16), np.uint8)
+    for i in range(8):
+        res[:, i::8] = (B >> np.uint32(4 * i)) & 0xF
+    w = np.empty_like(res).reshape(-1, perm.size)
+    w[:, perm] = res.reshape(-1, perm.size)
+    return w.reshape(K // 16, N // 16, 16, 16).transpose(0, 2, 1, 3).reshape(K, N)

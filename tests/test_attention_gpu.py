@@ -199,6 +199,29 @@ def test_prefill_on_tensor_cores_matches_oracle(dtype, H, kvh, qlens, cached, wi
     _check(out, ref)
 
 
+def test_decode_from_flashinfer_csr_metadata_equals_block_tables():
+    """The reference's default build describes the pages as CSR (indptr / indices / last_len, inputs.rs:477-506): expanded on the device by
+    flashinfer_csr_to_paged, decode must give the same bits as with padded block tables."""
+    rng = np.random.default_rng(21)
+    B, H, kvh, hd, bs = 5, 8, 2, 128, 64
+    ctx = [1, 64, 65, 300, 128]
+    nb = sum(-(-c // bs) for c in ctx) + 3
+    q, kc, vc, kn, vn, bt = _mk(rng, B, H, kvh, hd, bs, nb, ctx)
+    attn = pkg.PagedAttention(H, hd, hd ** -0.5, kvh)
+    zero = torch.zeros(0, dtype=torch.int64, device=DEV)
+    ref = attn.forward(q, None, None, None, kc, vc, pkg.InputMetadata(False, zero, torch.from_numpy(bt).to(DEV), torch.tensor(ctx, dtype=torch.int32, device=DEV)))
+    csr = pkg.flashinfer_csr(ctx, [list(r) for r in bt], bs)
+    t = lambda a: torch.from_numpy(a.astype(np.int32)).to(DEV)
+    fm = pkg.FlashInferMetadata(t(csr["indptr"]), t(csr["indices"]), t(csr["last_len"]), max_blocks_per_seq=bt.shape[1])
+    tables, lens = fm.to_paged(bs)
+    assert lens.cpu().numpy().tolist() == ctx
+    for b in range(B):
+        n = -(-ctx[b] // bs)
+        assert tables[b, :n].cpu().numpy().tolist() == bt[b, :n].tolist() and (tables[b, n:] == 0).all()
+    out = attn.forward(q, None, None, None, kc, vc, pkg.InputMetadata(False, zero, flashinfer_metadata=fm))
+    assert torch.equal(out, ref)
+
+
 def test_attention_argument_errors():
     attn = pkg.PagedAttention(8, 128, 0.1, 2)
     q = torch.zeros(2, 8, 128, dtype=torch.float32, device=DEV)

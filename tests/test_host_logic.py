@@ -109,3 +109,14 @@ def test_prepare_decode_rectangular_tables_match_ragged_path():
                 assert a[k].dtype == b[k].dtype, k
     with pytest.raises(inputs.BackendError, match="Block table is too small"):
         inputs.prepare_decode(np.full(B, bs * width + 1), np.zeros(B, np.int64), tabs, bs)
+
+
+def test_flashinfer_csr_matches_the_reference_construction():
+    """inputs.rs:477-531: indptr / indices / last_len and the derived kv_len, incl. a sequence that exactly fills its last page and an
+    empty one."""
+    import candle_vllm_b200 as pkg
+    csr = pkg.flashinfer_csr([1, 64, 65, 130, 0], [[3], [5], [7, 1], [9, 0, 2], [4]], 64)
+    assert csr["indptr"].tolist() == [0, 1, 2, 4, 7, 7]
+    assert csr["indices"].tolist() == [3, 5, 7, 1, 9, 0, 2]
+    assert csr["last_len"].tolist() == [1, 64, 1, 2, 0]
+    assert csr["kv_len"].tolist() == [1, 64, 65, 130, 0]

@@ -82,6 +82,35 @@ def test_marlin_matmul_with_checkpoint_g_idx_and_qzeros_like_the_reference_call_
     assert np.linalg.norm(y1.float().cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-3
 
 
+def test_marlin_pack_roundtrip_on_the_oracle():
+    rng = np.random.default_rng(2)
+    q = rng.integers(0, 16, (128, 192), dtype=np.uint8)
+    B = OG.pack_marlin(q)
+    assert B.shape == (128 // 16, 2 * 192) and np.array_equal(OG.unpack_marlin(B, 128, 192), q)
+    assert sorted(OG.marlin_weight_perm().tolist()) == list(range(1024))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,n,g", [(256, 128, 128), (1024, 384, 64), (512, 64, -1)])
+def test_marlin_format_checkpoint_is_accepted_after_one_repack(k, n, g):
+    """checkpoint_format == "marlin" (linear.rs:219-251): `B` in the Marlin project's tile order + `s` already permuted.  One load-time
+    marlin_checkpoint_repack turns B into exactly what marlin_weight_repack makes from the GPTQ tensors; the GEMM then matches the oracle."""
+    from candle_vllm_b200 import gptq
+    rng = np.random.default_rng(k + n)
+    q = rng.integers(0, 16, (k, n), dtype=np.uint8)
+    b = torch.from_numpy(OG.pack_marlin(q).view(np.int32)).cuda()
+    w_from_marlin = gptq.marlin_checkpoint_repack(b, k, n)
+    w_from_gptq = pkg.marlin_weight_repack(torch.from_numpy(OG.pack_gptq(q).view(np.int32)).cuda(), 4, False)
+    assert torch.equal(w_from_marlin, w_from_gptq)
+    ng = 1 if g == -1 else k // g
+    scales = rng.uniform(0.005, 0.02, (ng, n)).astype(np.float32)
+    st = torch.from_numpy(scales).cuda().half()
+    x = torch.from_numpy(rng.standard_normal((7, k)).astype(np.float32)).cuda().half()
+    y = pkg.gptq_matmul(x, w_from_marlin, pkg.marlin_permute_scales(st, k, n, g), None, None, torch.zeros(n, dtype=torch.int32, device="cuda"), 4, g)
+    ref = OG.gptq_matmul(x.float().cpu().numpy(), OG.pack_gptq(q), st.float().cpu().numpy(), g)
+    assert np.linalg.norm(y.float().cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-3
+
+
 def test_awq_zero_point_layout_matches_reference_converter():
     """oracle restatement of examples/convert_awq_marlin.py:75-113 against vectors produced by EXECUTING that script
     (tests/golden/make_golden.py: awq_zero_points), plus pack / unpack round trips."""
