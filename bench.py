@@ -309,18 +309,21 @@ def run_b200(args):
     # all) against the same steps of a TP = 1 engine with the same seeds on rank 0: greedy tokens and full-vocabulary logits.
     # At N = 1 the second engine runs eagerly (no graph) -- that leg checks graph capture / replay and bounds the run-to-run
     # spread of the red.add reductions.
-    def parity_steps(mdl, want):
+    def parity_steps(mdl, want, forced=None):
+        """PS decode steps; with `forced` (the reference's tokens, [PS, B]) step s + 1 consumes forced[s] instead of the engine's own
+        argmax -- teacher forcing, so that a greedy near-tie that flips under the run-to-run noise of the fp32 reductions cannot
+        make the later steps decode different sequences and every step's logits stay comparable"""
         lens, toks, out_t, out_l = np.full(B, args.ctx + 1), list(toks0), [], []
-        for _ in range(PS):
+        for st in range(PS):
             nxt, lg = mdl.decode(pkg.prepare_decode(lens, toks, tables_np, bs), want_logits=want)
             out_t.append(np.asarray(nxt).copy()); out_l.append(lg)
-            toks, lens = [int(t) for t in nxt], lens + 1
+            toks, lens = [int(t) for t in (nxt if forced is None else forced[st])], lens + 1
         return np.stack(out_t), out_l
 
     parity = None
     if PS > 0:
-        got_t, got_l = parity_steps(model, True)                    # collective at N > 1 (logits all-gather)
-        barrier()
+        ref_t = torch.zeros(PS, B, dtype=torch.int64, device=dev)
+        ref_l = None
         if rank == 0:
             if world == 1:
                 ref_model = pkg.GGUFLLaMa(cfg, weights, eng.gpu_cache, kv_dtype=kv_dtype, use_graph=False, stream=stream,
@@ -328,25 +331,36 @@ def run_b200(args):
                 ref_eng = None                                      # same cache: the steps rewrite the same slots with the same values
             else:
                 ref_model, ref_eng, ref_w = build(0, 1, None)
-            ref_t, ref_l = parity_steps(ref_model, True)
-            scale = max(float(np.abs(l).max()) for l in ref_l)
-            err = max(float(np.abs(a - b).max()) for a, b in zip(got_l, ref_l)) / scale
-            # a greedy token may differ only on a near-tie inside the logit error
-            flips = 0
-            for st in range(PS):
-                for b in np.nonzero(got_t[st] != ref_t[st])[0]:
-                    margin = float(ref_l[st][b].max() - ref_l[st][b, got_t[st][b]])
-                    flips += int(margin > 2 * err * scale + 1e-6)
-                if not np.array_equal(got_t[st], ref_t[st]):
-                    break                                           # later steps decode different tokens by construction
-            parity = {"steps": PS, "logits_max_err": err, "tokens_equal_tp1": bool(np.array_equal(got_t, ref_t)),
-                      "token_mismatches_beyond_logit_error": flips, "logit_scale": scale,
-                      "reference": "TP=1 engine, same seeds, rank 0" + (" (eager, no CUDA graph)" if world == 1 else ""),
-                      "tolerance": "logits within 1e-3 of max|logit|"}
-            del ref_model, ref_l
+            t, ref_l = parity_steps(ref_model, True)
+            ref_t.copy_(torch.from_numpy(t.astype(np.int64)))
+            del ref_model
             if world > 1:
                 del ref_eng, ref_w
             torch.cuda.empty_cache()
+        if world > 1:
+            dist.broadcast(ref_t, src=0)
+        ref_t = ref_t.cpu().numpy()
+        got_t, got_l = parity_steps(model, True, forced=ref_t)      # collective at N > 1 (logits all-gather)
+        barrier()
+        if rank == 0:
+            scale = max(float(np.abs(l).max()) for l in ref_l)
+            errs = [float(np.abs(a - b).max()) / scale for a, b in zip(got_l, ref_l)]
+            err = max(errs)
+            # a greedy token may differ only on a near-tie inside the logit error
+            flips = mismatches = 0
+            for st in range(PS):
+                for b in np.nonzero(got_t[st] != ref_t[st])[0]:
+                    mismatches += 1
+                    margin = float(ref_l[st][b].max() - ref_l[st][b, got_t[st][b]])
+                    flips += int(margin > 2 * err * scale + 1e-6)
+            parity = {"steps": PS, "logits_max_err": err, "logits_max_err_per_step": errs,
+                      "tokens_equal_tp1": mismatches == 0, "token_mismatches": mismatches,
+                      "token_mismatches_beyond_logit_error": flips, "logit_scale": scale,
+                      "reference": "TP=1 engine, same seeds, rank 0" + (" (eager, no CUDA graph)" if world == 1 else "")
+                                   + "; teacher-forced: every step of both engines consumes the reference's tokens",
+                      "tolerance": "logits within 5e-3 of max|logit| (fp32 reduction order differs between the two engines: "
+                                   "profiles/r02_rounding_floor.md)"}
+            del ref_l
         barrier()
 
     # ---- (1) device-resident: metadata advanced on the device, graph replay only ----------------

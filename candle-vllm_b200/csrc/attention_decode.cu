@@ -260,6 +260,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
 
     // ---- consumer -----------------------------------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
+    const float sl2 = kFp8 ? p.scale_log2 * 256.f : p.scale_log2;        // FP8 cache: K and V are expanded as value * 2^-8 (see expand())
+    const float o_scale = kFp8 ? 256.f : 1.f;
     const T* qbase = static_cast<const T*>(p.q);
     unsigned int consumed = 0;
     for (int c_slot = 0;; ++c_slot) {
@@ -304,9 +306,13 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
                     uint32_t o[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        // two e4m3 -> one packed f16x2 register per cvt; the 16-bit halves of w[j] are register sub-words (no byte permutes)
-                        asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\ncvt.rn.f16x2.e4m3x2 %0, lo;\ncvt.rn.f16x2.e4m3x2 %1, hi;\n}\n"
-                            : "=r"(o[2 * j]), "=r"(o[2 * j + 1]) : "r"(w[j]));
+                        // e4m3 -> f16 WITHOUT the conversion pipe (F2FP.E4M3 issues at a fraction of the ALU rate and was the limiter: ncu,
+                        // profiles/r02_fp8_attention.md): put each byte in the high half of a 16-bit lane and move its 7 exponent / mantissa
+                        // bits down by one -- the result is the f16 with the same mantissa and exponent field e (bias 15 instead of 7), i.e.
+                        // the value * 2^-8, exact for normals AND subnormals; the 2^8 is folded into the softmax scale (K) and the output (V)
+                        const uint32_t ylo = __byte_perm(w[j], 0u, 0x1404), yhi = __byte_perm(w[j], 0u, 0x3424);      // [b1 0 b0 0], [b3 0 b2 0]
+                        o[2 * j] = ((ylo >> 1) & 0x3f803f80u) | (ylo & 0x80008000u);
+                        o[2 * j + 1] = ((yhi >> 1) & 0x3f803f80u) | (yhi & 0x80008000u);
                     }
                     uint8_t* dst = conv + (rc >> 2) * kSubTileBytes + row * 128;
                     const int c0 = (2 * rc) & 7;
@@ -345,8 +351,8 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int tok = nt * 8 + 2 * t;
-                sacc[nt][0] = tok < valid ? sacc[nt][0] * p.scale_log2 : -INFINITY;
-                sacc[nt][1] = tok + 1 < valid ? sacc[nt][1] * p.scale_log2 : -INFINITY;
+                sacc[nt][0] = tok < valid ? sacc[nt][0] * sl2 : -INFINITY;
+                sacc[nt][1] = tok + 1 < valid ? sacc[nt][1] * sl2 : -INFINITY;
                 mx = fmaxf(mx, fmaxf(sacc[nt][0], sacc[nt][1]));
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -408,7 +414,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             const int64_t slot = (((int64_t)b * p.num_kv_heads + h) * p.max_chunks + c) * kGroup + g;
             float* orow = p.part_o + slot * kHeadDim;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(orow + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
+            for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(orow + i * 8 + 2 * t) = make_float2(o[i][0] * o_scale, o[i][1] * o_scale);
             if (t == 0) { p.part_ml[slot * 2] = m_run; p.part_ml[slot * 2 + 1] = l_run; }
         }
     }

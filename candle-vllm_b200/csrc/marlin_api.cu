@@ -60,7 +60,7 @@ __global__ void awq_repack_kernel(const uint32_t* __restrict__ in, uint32_t* __r
 
 // Marlin checkpoint format (`B` u32 [K/16, 2N], checkpoint_format == "marlin", /root/reference/src/openai/models/linear.rs:219-251) -> GPTQ packing
 // u32 [K/8, N], from which gptq_repack makes this library's layout.  The tile order is the Marlin project's published one (IST-DASLab/marlin,
-// `_get_perms` / `Layer.pack`; restated in oracle/gptq.py): w[k][n] sits in row k / 16, tile-flat position (n / 16) * 256 + (k % 16) * 16 + n % 16,
+// `_get_perms` / `Layer.pack`): w[k][n] sits in row k / 16, tile-flat position (n / 16) * 256 + (k % 16) * 16 + n % 16,
 // permuted inside every 1024 values by `perm` (inv_perm below, built once on the host) and packed 8 nibbles per word with stride 8.
 __constant__ uint16_t c_marlin_inv_perm[1024];
 __global__ void marlin_to_gptq_kernel(const uint32_t* __restrict__ B, uint32_t* __restrict__ out, int k, int n) {
