@@ -46,20 +46,19 @@ constexpr int kSubTileBytes = kTile * 64 * 2;             // 32 tokens x 64 dims
 constexpr int kMaxSeqs = 1024;
 
 // Shared-memory plan.  16-bit KV: 6 independent warp pipelines x 2 stages of 16 KB (K lo, K hi, V lo, V hi sub-tiles) = 192 KB of KV
-// reads in flight per SM.  FP8 (e4m3) KV: a tile is half the bytes (one 4 KB box for K, one for V: 32 tokens x 128 B) and has to be
-// expanded to f16 (cvt e4m3x2 -> f16x2, exact) into the sub-tile layout the ldmatrix code reads -- per-warp latency, not bytes, sets
-// the pace (ncu: 26 % issue-active with 5 warps), so the plan maximises resident warps: 2 stages of 8 KB + ONE 8 KB f16 staging tile
-// per warp (K is expanded, S = Q K^T runs, then V is expanded into the same tile) = 24 KB -> 8 warps (256 threads keep the full
-// 255-register budget; 9 warps would be capped at 168 and spill), 128 KB of reads in flight.
+// reads in flight per SM.  FP8 (e4m3) KV: a tile is half the bytes (one 4 KB box for K, one for V: 32 tokens x 128 B), so 8 warps x 3
+// stages of 8 KB keep the same 192 KB in flight.  The e4m3 bytes are expanded to f16 IN REGISTERS on their way into the MMA fragments
+// (K: LDS.128 of a token row; V: the transposing 8-bit ldmatrix of sm_100a) -- there is no f16 staging tile.  [A first version
+// expanded each tile into a per-warp f16 staging tile (LDS + cvt + STS, then the 16-bit ldmatrix code): 0.45-0.59 of the HBM peak,
+// bound by the shared-memory round trip and the 24 KB per warp it cost; profiles/r02_fp8_attention.md.]
 template <bool kFp8>
 struct Plan {
     static constexpr int kWarps = kFp8 ? 8 : 6;
-    static constexpr int kStages = 2;
+    static constexpr int kStages = kFp8 ? 3 : 2;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kStageBytes = kFp8 ? 2 * kTile * kHeadDim : 4 * kSubTileBytes;      // 8 KB / 16 KB
-    static constexpr int kConvBytes = kFp8 ? 2 * kSubTileBytes : 0;                          // f16 staging tile per warp (K, then V)
-    static constexpr int kWarpBytes = kStages * kStageBytes + kConvBytes;
-    // stages first (1024-byte aligned for the 128B swizzle): [warp][stage...][conv]
+    static constexpr int kWarpBytes = kStages * kStageBytes;
+    // stages first (1024-byte aligned for the 128B swizzle): [warp][stage...]
     static constexpr int kBars = kWarps * kWarpBytes;                               // full[kWarps][kStages]
     static constexpr int kHdr = kBars + kWarps * kStages * 8;                       // int[kWarps][8][8] item headers (the producer cursor runs <= kStages + 2 items ahead)
     static constexpr int kPrefix = kHdr + kWarps * 8 * 8 * 4;                       // int[kMaxSeqs + 1]
@@ -152,11 +151,20 @@ struct DecodeParams {
 // Header words in shared memory: {valid, b, h, c, ctx, ntiles}.
 //
 // Every warp is an independent pipeline: it claims items from a global queue, gathers the chunk's block
-// ids from the block table, issues its own TMA loads two tiles ahead into a private 2-stage ring
+// ids from the block table, issues its own TMA loads two (FP8: three) tiles ahead into a private ring
 // (completion on an mbarrier) and consumes them with ldmatrix + mma.sync.  No CTA-wide barrier in the
 // steady state, and a warp only ever waits on a barrier phase it armed itself (no phase aliasing).
 // T = model dtype (q, and the cache when kFp8 is false).  kFp8: the cache holds e4m3 bytes (scale 1.0, the reference passes none);
 // K / V are expanded to f16 (exact), q is converted bf16 -> f16 and the MMAs run in f16.
+
+// four e4m3 bytes -> two packed f16x2 (bytes 0,1 | bytes 2,3); the 16-bit halves of w are register sub-words, no byte permutes
+__device__ __forceinline__ void cvt_e4m3x4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.rn.f16x2.e4m3x2 %0, l;\ncvt.rn.f16x2.e4m3x2 %1, h;\n}\n" : "=r"(lo), "=r"(hi) : "r"(w));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans_b8(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
 template <typename T, int kGroup, bool kFp8>
 __global__ void __launch_bounds__(Plan<kFp8>::kThreads, 1)
 paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
@@ -170,7 +178,6 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     int* prefix = reinterpret_cast<int*>(smem + PL::kPrefix);
     int* hdr = reinterpret_cast<int*>(smem + PL::kHdr) + warp * 64;          // [8][8]
     const uint32_t my_stages = smem_base + warp * PL::kWarpBytes;
-    const uint32_t my_conv = my_stages + kStagesPerWarp * kStageBytes;       // kFp8: this warp's f16 staging tile
     const uint32_t my_bars = smem_base + PL::kBars + warp * kStagesPerWarp * 8;
 
     if (lane == 0) {
@@ -260,8 +267,6 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
 
     // ---- consumer -----------------------------------------------------------------------------------
     const int g = lane >> 2, t = lane & 3;
-    const float sl2 = kFp8 ? p.scale_log2 * 256.f : p.scale_log2;        // FP8 cache: K and V are expanded as value * 2^-8 (see expand())
-    const float o_scale = kFp8 ? 256.f : 1.f;
     const T* qbase = static_cast<const T*>(p.q);
     unsigned int consumed = 0;
     for (int c_slot = 0;; ++c_slot) {
@@ -270,18 +275,22 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         if (hd[0] == 0) break;
         const int b = hd[1], h = hd[2], c = hd[3], ctx = hd[4], ntiles = hd[5];
 
-        // Q fragments: rows = the group's query heads (g < kGroup), zero padding otherwise
+        // Q fragments: rows = the group's query heads (g < kGroup), zero padding otherwise.  16-bit cache: k-step ks covers dims
+        // 16 ks .. 16 ks + 15 in the fragment's natural order.  FP8 cache: the K operand comes straight from 16-byte chunks of the
+        // e4m3 rows (see below), so k-step ks pairs slots (2t, 2t+1 | 2t+8, 2t+9) with dims D .. D+3, D = 16 (t + 4 (ks / 4)) + 4 (ks % 4)
+        // -- any permutation of the contraction index is fine as long as both operands use it
         uint32_t qa[8][2];
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             if (g < kGroup) {
-                const T* qr = qbase + ((int64_t)b * p.num_heads + h * kGroup + g) * kHeadDim + ks * 16 + 2 * t;
+                const int d0 = kFp8 ? 16 * (t + 4 * (ks >> 2)) + 4 * (ks & 3) : ks * 16 + 2 * t, d1 = kFp8 ? d0 + 2 : d0 + 8;
+                const T* qr = qbase + ((int64_t)b * p.num_heads + h * kGroup + g) * kHeadDim;
                 if constexpr (std::is_same<T, TM>::value) {
-                    qa[ks][0] = *reinterpret_cast<const uint32_t*>(qr);
-                    qa[ks][1] = *reinterpret_cast<const uint32_t*>(qr + 8);
+                    qa[ks][0] = *reinterpret_cast<const uint32_t*>(qr + d0);
+                    qa[ks][1] = *reinterpret_cast<const uint32_t*>(qr + d1);
                 } else {                        // model dtype bf16, f16 MMAs (FP8 cache): q -> f16 (saturating; exact for |q| in fp16's normal range)
-                    qa[ks][0] = pack2<TM>(to_f32(qr[0]), to_f32(qr[1]));
-                    qa[ks][1] = pack2<TM>(to_f32(qr[8]), to_f32(qr[9]));
+                    qa[ks][0] = pack2<TM>(to_f32(qr[d0]), to_f32(qr[d0 + 1]));
+                    qa[ks][1] = pack2<TM>(to_f32(qr[d1]), to_f32(qr[d1 + 1]));
                 }
             } else { qa[ks][0] = qa[ks][1] = 0u; }
         }
@@ -293,66 +302,58 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         for (int tl = 0; tl < ntiles; ++tl) {
             const int s = consumed % kStagesPerWarp;
             mbar_wait(my_bars + s * 8, (consumed / kStagesPerWarp) & 1);
-            uint32_t kt = my_stages + s * kStageBytes, vt = kt + 2 * kSubTileBytes;
-            // kFp8: expand 32 tokens x 128 e4m3 (128-byte swizzled rows at `raw`) into this warp's f16 staging tile: a lane takes one
-            // 16-byte chunk (16 dims) per step and writes two 16-byte f16 chunks of sub-tile (dim / 64), same XOR swizzle
-            auto expand = [&](const uint8_t* raw) {
-                uint8_t* conv = smem + (my_conv - smem_base);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int id = i * 32 + lane, row = id >> 3, rc = id & 7;
-                    const uint4 v = *reinterpret_cast<const uint4*>(raw + row * 128 + ((rc ^ (row & 7)) << 4));
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                    uint32_t o[8];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // e4m3 -> f16 WITHOUT the conversion pipe (F2FP.E4M3 issues at a fraction of the ALU rate and was the limiter: ncu,
-                        // profiles/r02_fp8_attention.md): put each byte in the high half of a 16-bit lane and move its 7 exponent / mantissa
-                        // bits down by one -- the result is the f16 with the same mantissa and exponent field e (bias 15 instead of 7), i.e.
-                        // the value * 2^-8, exact for normals AND subnormals; the 2^8 is folded into the softmax scale (K) and the output (V)
-                        const uint32_t ylo = __byte_perm(w[j], 0u, 0x1404), yhi = __byte_perm(w[j], 0u, 0x3424);      // [b1 0 b0 0], [b3 0 b2 0]
-                        o[2 * j] = ((ylo >> 1) & 0x3f803f80u) | (ylo & 0x80008000u);
-                        o[2 * j + 1] = ((yhi >> 1) & 0x3f803f80u) | (yhi & 0x80008000u);
-                    }
-                    uint8_t* dst = conv + (rc >> 2) * kSubTileBytes + row * 128;
-                    const int c0 = (2 * rc) & 7;
-                    *reinterpret_cast<uint4*>(dst + ((c0 ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4*>(dst + (((c0 + 1) ^ (row & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
-                }
-                __syncwarp();
-            };
-            if constexpr (kFp8) {
-                expand(smem + (kt - smem_base));             // K
-                kt = my_conv;
-            }
+            const uint32_t kt = my_stages + s * kStageBytes, vt = kt + (kFp8 ? kTile * kHeadDim : 2 * kSubTileBytes);
             const int valid = min(kTile, ctx - (c * chunk_tokens + tl * kTile));
 
             // ---- S = Q K^T : 4 n-tiles (8 tokens each) x 8 k-steps --------------------------------
             float sacc[4][4];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+            if constexpr (kFp8) {
+                // FP8 cache: no staging tile.  Lane (g, t) reads the two 16-byte chunks t and t + 4 of ONE e4m3 token row per n-tile
+                // (32 dims), expands them in registers (cvt.rn.f16x2.e4m3x2: two weights per instruction, exact) and feeds the words
+                // to the MMA as its B fragment.  Column n = g of n-tile nt is token 8 nt + (g >> 1) + 4 (g & 1): the two rows a
+                // quarter-warp touches then differ in bit 2 of the swizzle key and the LDS.128 are conflict free; thread t ends up with
+                // the scores of tokens 8 nt + t and 8 nt + t + 4 -- the order the transposing 8-bit ldmatrix of V hands out below.
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int row = nt * 8 + (lane & 7);
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int row = nt * 8 + (g >> 1) + 4 * (g & 1);
+                    const uint8_t* kr = smem + (kt - smem_base) + row * 128;
+                    const uint4 c0 = *reinterpret_cast<const uint4*>(kr + ((t ^ (row & 7)) << 4));
+                    const uint4 c1 = *reinterpret_cast<const uint4*>(kr + (((t + 4) ^ (row & 7)) << 4));
+                    const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-                for (int kp = 0; kp < 4; ++kp) {            // 32 dims (2 k-steps) per ldmatrix.x4
-                    const int chunk = kp * 4 + (lane >> 3);  // 16-byte chunk index 0..15 along the 128 dims
-                    const uint32_t addr = kt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-                    uint32_t kb[4];
-                    ldmatrix_x4(kb, addr);
-                    const uint32_t a0[4] = {qa[2 * kp][0], 0u, qa[2 * kp][1], 0u};
-                    const uint32_t a1[4] = {qa[2 * kp + 1][0], 0u, qa[2 * kp + 1][1], 0u};
-                    mma_16816<TM>(sacc[nt], a0, kb[0], kb[1]);
-                    mma_16816<TM>(sacc[nt], a1, kb[2], kb[3]);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        uint32_t b0, b1;
+                        cvt_e4m3x4(w[ks], b0, b1);
+                        const uint32_t a0[4] = {qa[ks][0], 0u, qa[ks][1], 0u};
+                        mma_16816<TM>(sacc[nt], a0, b0, b1);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int row = nt * 8 + (lane & 7);
+#pragma unroll
+                    for (int kp = 0; kp < 4; ++kp) {            // 32 dims (2 k-steps) per ldmatrix.x4
+                        const int chunk = kp * 4 + (lane >> 3);  // 16-byte chunk index 0..15 along the 128 dims
+                        const uint32_t addr = kt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+                        uint32_t kb[4];
+                        ldmatrix_x4(kb, addr);
+                        const uint32_t a0[4] = {qa[2 * kp][0], 0u, qa[2 * kp][1], 0u};
+                        const uint32_t a1[4] = {qa[2 * kp + 1][0], 0u, qa[2 * kp + 1][1], 0u};
+                        mma_16816<TM>(sacc[nt], a0, kb[0], kb[1]);
+                        mma_16816<TM>(sacc[nt], a1, kb[2], kb[3]);
+                    }
                 }
             }
             // ---- mask + online softmax (rows g; rows g+8 are padding) -----------------------------
             float mx = -INFINITY;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-                const int tok = nt * 8 + 2 * t;
-                sacc[nt][0] = tok < valid ? sacc[nt][0] * sl2 : -INFINITY;
-                sacc[nt][1] = tok + 1 < valid ? sacc[nt][1] * sl2 : -INFINITY;
+                const int tok0 = kFp8 ? nt * 8 + t : nt * 8 + 2 * t, tok1 = kFp8 ? tok0 + 4 : tok0 + 1;      // tokens of this thread's two columns
+                sacc[nt][0] = tok0 < valid ? sacc[nt][0] * p.scale_log2 : -INFINITY;
+                sacc[nt][1] = tok1 < valid ? sacc[nt][1] * p.scale_log2 : -INFINITY;
                 mx = fmaxf(mx, fmaxf(sacc[nt][0], sacc[nt][1]));
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -372,38 +373,62 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; }
             }
-            if constexpr (kFp8) {
-                __syncwarp();                                    // every lane is done reading K from the staging tile
-                expand(smem + (my_stages + s * kStageBytes - smem_base) + kTile * kHeadDim);      // V
-                vt = my_conv;
-                issue_one();                                     // the raw stage is free: refill it (tile consumed + kStages)
-            }
             // V rows past the context may hold non-finite garbage: 0 * NaN would poison O
             if (valid < kTile) {
-                for (int r = valid + (lane >> 4); r < kTile; r += 2) {
-                    const int ch = lane & 15;
-                    *reinterpret_cast<int4*>(smem + (vt - smem_base) + (ch >> 3) * kSubTileBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
-                        make_int4(0, 0, 0, 0);
+                if constexpr (kFp8) {
+                    for (int r = valid + (lane >> 3); r < kTile; r += 4)
+                        *reinterpret_cast<int4*>(smem + (vt - smem_base) + r * 128 + ((lane & 7) << 4)) = make_int4(0, 0, 0, 0);
+                } else {
+                    for (int r = valid + (lane >> 4); r < kTile; r += 2) {
+                        const int ch = lane & 15;
+                        *reinterpret_cast<int4*>(smem + (vt - smem_base) + (ch >> 3) * kSubTileBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) =
+                            make_int4(0, 0, 0, 0);
+                    }
                 }
                 __syncwarp();
             }
             // ---- O += P V : 2 k-steps (16 tokens) x 16 n-tiles (8 dims) ---------------------------
+            if constexpr (kFp8) {
+                // ldmatrix.m16n16.trans.b8 (sm_100a; fragment layout probed, tools/probes/ldmatrix_b8_probe.cu): with row addresses
+                // r = 0..15 from lanes 0..15 (x2: a second matrix from lanes 16..31), lane (g, t) receives bytes (rows 4t..4t+3, column g)
+                // and (rows 4t..4t+3, column g + 8).  Rows are tokens, columns dims of a 16-byte chunk; matrix row r is pointed at
+                // token (r >> 2) + 4 (r & 3) of the k-step, so the low half-word of a register holds tokens (t, t + 4) = the k slots
+                // (2t, 2t+1) that P's a0 carries, the high half-word tokens (t + 8, t + 12) = slots (2t+8, 2t+9) = a2.
 #pragma unroll
-            for (int ktk = 0; ktk < 2; ++ktk) {
-                const uint32_t a[4] = {pa[2 * ktk], 0u, pa[2 * ktk + 1], 0u};
-                const int row = ktk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                for (int ktk = 0; ktk < 2; ++ktk) {
+                    const uint32_t a[4] = {pa[2 * ktk], 0u, pa[2 * ktk + 1], 0u};
+                    const int r = lane & 15, row = ktk * 16 + (r >> 2) + 4 * (r & 3);
 #pragma unroll
-                for (int np = 0; np < 8; ++np) {            // two 8-dim n-tiles per ldmatrix.x4.trans
-                    const int chunk = np * 2 + (lane >> 4);
-                    const uint32_t addr = vt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-                    uint32_t vb[4];
-                    ldmatrix_x4_trans(vb, addr);
-                    mma_16816<TM>(o[2 * np], a, vb[0], vb[1]);
-                    mma_16816<TM>(o[2 * np + 1], a, vb[2], vb[3]);
+                    for (int cp = 0; cp < 4; ++cp) {            // two 16-dim chunks (four 8-dim n-tiles) per x2
+                        const int chunk = 2 * cp + (lane >> 4);
+                        uint32_t vb[4];
+                        ldmatrix_x2_trans_b8(vb, vt + row * 128 + ((chunk ^ (row & 7)) << 4));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t b0, b1;
+                            cvt_e4m3x4(vb[j], b0, b1);
+                            mma_16816<TM>(o[4 * cp + j], a, b0, b1);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ktk = 0; ktk < 2; ++ktk) {
+                    const uint32_t a[4] = {pa[2 * ktk], 0u, pa[2 * ktk + 1], 0u};
+                    const int row = ktk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                    for (int np = 0; np < 8; ++np) {            // two 8-dim n-tiles per ldmatrix.x4.trans
+                        const int chunk = np * 2 + (lane >> 4);
+                        const uint32_t addr = vt + (chunk >> 3) * kSubTileBytes + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+                        uint32_t vb[4];
+                        ldmatrix_x4_trans(vb, addr);
+                        mma_16816<TM>(o[2 * np], a, vb[0], vb[1]);
+                        mma_16816<TM>(o[2 * np + 1], a, vb[2], vb[3]);
+                    }
                 }
             }
             __syncwarp();
-            if constexpr (!kFp8) issue_one();                // refill the stage we just drained (tile consumed + 2)
+            issue_one();                                     // refill the stage we just drained (tile consumed + kStages)
             ++consumed;
         }
 
@@ -414,7 +439,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
             const int64_t slot = (((int64_t)b * p.num_kv_heads + h) * p.max_chunks + c) * kGroup + g;
             float* orow = p.part_o + slot * kHeadDim;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(orow + i * 8 + 2 * t) = make_float2(o[i][0] * o_scale, o[i][1] * o_scale);
+            for (int i = 0; i < 16; ++i) *reinterpret_cast<float2*>(orow + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
             if (t == 0) { p.part_ml[slot * 2] = m_run; p.part_ml[slot * 2 + 1] = l_run; }
         }
     }

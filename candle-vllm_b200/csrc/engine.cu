@@ -49,7 +49,6 @@ struct b200_llama {
     const float* norm = nullptr;
     b200_linear output{};                     // lm_head
     int rope_neox = 0;
-    float* lin_scratch = nullptr; size_t lin_scratch_bytes = 0;     // fp32 partial-sum slabs of the int4 GEMMs
     std::vector<void*> kc, vc;
     int64_t num_blocks = 0;
     void* comm = nullptr;
@@ -144,10 +143,26 @@ int act_format(const b200_llama* m) {
 void linear(b200_llama* m, const b200_linear& l, const void* x16, float* y, int64_t ldy, int B, int n, int k, int accumulate, cudaStream_t st) {
     switch (l.kind) {
         case B200_LIN_GGML: qmatmul_dispatch(x16, l.w, y, ldy, B, n, k, l.type, accumulate, st); break;
-        case B200_LIN_MARLIN4: marlin_tc_f32(x16, l.w, l.scales, l.type == B200_BF16, l.zeros, y, ldy, B, n, k, l.group_size, accumulate, m->lin_scratch, st); break;
+        case B200_LIN_MARLIN4: {
+            const void* zs[1] = {l.zeros};
+            marlin_tc_f32_multi(x16, 1, &l.w, &l.scales, l.type == B200_BF16, l.zeros ? zs : nullptr, &y, &n, ldy, B, k, l.group_size, accumulate, st);
+            break;
+        }
         case B200_LIN_DENSE16: dense_gemm_16(x16, l.w, nullptr, y, B, n, k, k, k, ldy, l.type, B200_F32, st, accumulate, /*allow_split_k=*/1); break;
         default: set_error(kErrUnsupported, "engine: linear kind %d", l.kind);
     }
+}
+// several int4 linears over the same activations (QKV, gate|up) as one launch when they share group size, scale dtype and zero-point form
+bool marlin_fusable(std::initializer_list<const b200_linear*> ls) {
+    const b200_linear* f = *ls.begin();
+    for (const b200_linear* l : ls)
+        if (l->kind != B200_LIN_MARLIN4 || l->group_size != f->group_size || l->type != f->type || (l->zeros != nullptr) != (f->zeros != nullptr)) return false;
+    return true;
+}
+void marlin_multi(b200_llama* m, int nseg, const b200_linear* const* ls, const void* x16, float* const* ys, const int* ns, int64_t ldy, int B, int k, cudaStream_t st) {
+    const void* ws[3]; const void* sc[3]; const void* zp[3];
+    for (int i = 0; i < nseg; ++i) { ws[i] = ls[i]->w; sc[i] = ls[i]->scales; zp[i] = ls[i]->zeros; }
+    marlin_tc_f32_multi(x16, nseg, ws, sc, ls[0]->type == B200_BF16, ls[0]->zeros ? zp : nullptr, ys, ns, ldy, B, k, ls[0]->group_size, 0, st);
 }
 void lm_head(b200_llama* m, int B, cudaStream_t st) {
     const int H = m->cfg.hidden;
@@ -334,6 +349,11 @@ int forward(b200_llama* m, int B, cudaStream_t st, bool linear_only = false) {
             float* ys[3] = {m->qkv, m->qkv + qd, m->qkv + qd + kd};
             // accumulate = 0: whole tiles are plain stores, split tiles red.add into the zeroed buffer
             qmatmul_dispatch_multi(m->xn, 3, ws, ts, ys, ns, m->qkv_row, B, H, 0, st);
+        } else if (marlin_fusable({&w.wq, &w.wk, &w.wv})) {
+            const b200_linear* ls[3] = {&w.wq, &w.wk, &w.wv};
+            const int ns[3] = {qd, kd, kd};
+            float* ys[3] = {m->qkv, m->qkv + qd, m->qkv + qd + kd};
+            marlin_multi(m, 3, ls, m->xn, ys, ns, m->qkv_row, B, H, st);
         } else {
             linear(m, w.wq, m->xn, m->qkv, m->qkv_row, B, qd, H, 0, st);
             linear(m, w.wk, m->xn, m->qkv + qd, m->qkv_row, B, kd, H, 0, st);
@@ -365,6 +385,11 @@ int forward(b200_llama* m, int B, cudaStream_t st, bool linear_only = false) {
             const int ts[2] = {w.w1.type, w.w3.type}, ns[2] = {m->ffn_l, m->ffn_l};
             float* ys[2] = {m->gate, m->up};
             qmatmul_dispatch_multi(m->xn, 2, ws, ts, ys, ns, m->ffn_l, B, H, 0, st);
+        } else if (marlin_fusable({&w.w1, &w.w3})) {
+            const b200_linear* ls[2] = {&w.w1, &w.w3};
+            const int ns[2] = {m->ffn_l, m->ffn_l};
+            float* ys[2] = {m->gate, m->up};
+            marlin_multi(m, 2, ls, m->xn, ys, ns, m->ffn_l, B, H, st);
         } else {
             linear(m, w.w1, m->xn, m->gate, m->ffn_l, B, m->ffn_l, H, 0, st);
             linear(m, w.w3, m->xn, m->up, m->ffn_l, B, m->ffn_l, H, 0, st);
@@ -584,7 +609,6 @@ void b200_llama_destroy(b200_llama* m) {
     if (m->logits_gathered) cudaFree(m->logits_gathered);
     if (m->logits_full) cudaFree(m->logits_full);
     if (m->mega_trace) cudaFree(m->mega_trace);
-    if (m->lin_scratch) cudaFree(m->lin_scratch);
     for (void* p : {(void*)m->qkv_slabs, (void*)m->ro_slabs, (void*)m->gate_slabs, (void*)m->up_slabs, (void*)m->mega_counters}) if (p) cudaFree(p);
     delete m;
 }
@@ -622,18 +646,6 @@ void b200_llama_set_layer_ex(b200_llama* m, int32_t layer, const b200_llama_laye
     for (const b200_linear* l : {&w->wk, &w->wv, &w->wo, &w->w1, &w->w2, &w->w3})
         B200_REQUIRE(fmt_of(*l) == fmt, kErrUnsupported, "b200_llama_set_layer_ex: the linears of a model must share one activation format");
     m->layers[layer] = *w;
-    // fp32 partial-sum slabs of the int4 GEMMs (library scratch is per stream and may grow: the engine owns a fixed one instead)
-    size_t need = 0;
-    auto slab = [&](const b200_linear& l, int n, int k) { if (l.kind == B200_LIN_MARLIN4) need = std::max(need, (size_t)wq16_slabs(n, k) * c.max_num_seqs * n * 4 + 256); };
-    slab(w->wq, qd, H); slab(w->wk, kd, H); slab(w->wv, kd, H); slab(w->wo, H, qd); slab(w->w1, F, H); slab(w->w2, H, F); slab(w->w3, F, H);
-    if (need > m->lin_scratch_bytes) {
-        cudaDeviceSynchronize();
-        if (m->lin_scratch) cudaFree(m->lin_scratch);
-        m->lin_scratch = nullptr; m->lin_scratch_bytes = 0;
-        void* q = nullptr;
-        B200_REQUIRE(cudaMalloc(&q, need) == cudaSuccess, kErrCuda, "b200_llama_set_layer_ex: scratch cudaMalloc(%zu) failed", need);
-        m->lin_scratch = static_cast<float*>(q); m->lin_scratch_bytes = need;
-    }
     invalidate_graphs(m);
 }
 

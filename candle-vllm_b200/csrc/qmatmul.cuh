@@ -45,8 +45,10 @@ int wq16_slabs(int n, int k);
 // int4 (GPTQ symmetric / AWQ with zero points; repacked by gptq_repack / awq_repack) x fp16 activations in K4 order
 void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const void* qzeros /* null: symmetric */, void* out, int out_dtype,
                int m, int n, int k, int group_size, float* slabs, cudaStream_t st);
-void marlin_tc_f32(const void* x_f16_k4, const void* w, const void* scales, int scale_bf16, const void* qzeros, float* y, int64_t ldy, int m, int n, int k,
-                   int group_size, int accumulate, float* slabs, cudaStream_t st);
+// decode-engine form: up to 3 int4 matrices sharing the activations in one launch, f32 output, split tiles red.add into y
+// (accumulate = 0: y zeroed by the caller)
+void marlin_tc_f32_multi(const void* x_f16_k4, int nseg, const void* const* w, const void* const* scales, int scale_bf16, const void* const* qzeros,
+                         float* const* y, const int* n, int64_t ldy, int m, int k, int group_size, int accumulate, cudaStream_t st);
 // e4m3 [n,k] with f32 scale per [by, bx] tile x fp16 activations in natural order
 bool fp8_tc_supported(int m, int n, int k, int by, int bx);
 void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void* bias, void* out, int out_dtype, int m, int n, int k,

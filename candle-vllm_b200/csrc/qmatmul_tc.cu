@@ -83,6 +83,8 @@ struct GemmParams {
     int slabs;                     // > 0: split tiles write their partial sums to DISTINCT slabs (plain stores, no atomics, no
     int64_t slab_stride;           //      pre-zeroed output): slab s of segment sg starts at y[sg] + s * slab_stride; the consumer sums
     const void* scales;            // marlin: [K/g, N] in marlin-permuted order (f16 / bf16: scale_bf16); fp8: f32 [N/by, K/bx]
+    const void* scales_seg[kMaxSeg];   // marlin, several weight matrices in one launch (engine: QKV, gate|up): scales / zero points of each
+    const uint32_t* zp_seg[kMaxSeg];   //   segment (slot 0 = scales / zp)
     int group_size, k;             // marlin group size / fp8 bx
     int scale_bf16, scale_by, scale_sk;
     const float* norm;             // fp8: {2^p, 2^-p} range shift of the tile scales (device)
@@ -504,8 +506,12 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const int off = kType == kTypeF8 ? row : (kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15));   // Q6_K: block offset in its window
                 const uint32_t afp = aph ^ 1;
                 const bool skip = (p.debug & 2) != 0;
-                const M4Ctx mc{p.scales, p.n[0], p.group_size, (int)(u - tile_begin) * kSB, tile * kTileN + row < p.n[0] ? tile * kTileN + row : 0,
-                               p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm, p.zp};
+                // marlin: the scales / zero points of the weight matrix this tile belongs to (constant indices only, see seg_first_tile)
+                const int msg = kType == kTypeM4 ? seg_of_tile(p, tile) : 0;
+                const int mrow = (tile - seg_first_tile(p, msg)) * kTileN + row, mn = msg == 0 ? p.n[0] : (msg == 1 ? p.n[1] : p.n[2]);
+                const M4Ctx mc{msg == 0 ? p.scales_seg[0] : (msg == 1 ? p.scales_seg[1] : p.scales_seg[2]), mn, p.group_size, (int)(u - tile_begin) * kSB,
+                               mrow < mn ? mrow : 0, p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm,
+                               msg == 0 ? p.zp_seg[0] : (msg == 1 ? p.zp_seg[1] : p.zp_seg[2])};
                 switch (qt) {
                     case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                     case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
@@ -836,6 +842,7 @@ static void wq16_launch(int kind, const void* x_f16, const void* w, const void* 
     p.slabs = qmatmul_tc_slab_count(tiles, nsb);
     p.slab_stride = (int64_t)m * n;
     p.scales = scales; p.group_size = group_or_bx; p.k = k; p.scale_bf16 = scale_bf16; p.scale_by = by; p.scale_sk = sk; p.norm = norm; p.zp = zp;
+    for (int i = 0; i < kMaxSeg; ++i) { p.scales_seg[i] = scales; p.zp_seg[i] = zp; }
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     if (kind == kTypeM4) { if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st); }
     else { if (mb == 32) launch<32, kTypeF8>(wm, xm, p, st); else launch<64, kTypeF8>(wm, xm, p, st); }
@@ -861,11 +868,44 @@ void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const vo
                 out_dtype, m, n, k, slabs, st, qzeros ? "marlin_awq_4bit" : "marlin_4bit");
 }
 
-// the same GEMM with f32 output (+ accumulate) for the decode engine: y[m][ldy] (+)= x . ((q - z) * s)^T; n % 4 == 0
-void marlin_tc_f32(const void* x_f16_k4, const void* w, const void* scales, int scale_bf16, const void* qzeros, float* y, int64_t ldy, int m, int n, int k,
-                   int group_size, int accumulate, float* slabs, cudaStream_t st) {
-    wq16_launch(kTypeM4, x_f16_k4, w, scales, scale_bf16, group_size, 1, 0, nullptr, static_cast<const uint32_t*>(qzeros), nullptr, y, B200_F32, m, n, k,
-                slabs, st, "marlin_4bit(f32)", ldy, accumulate);
+// the same GEMM for the decode engine: up to three int4 weight matrices that read the same activations (QKV, gate|up) in ONE launch,
+// f32 output y[i][m][ldy] (+)= x . ((q - z) * s)^T.  Like the GGML engine path, tiles split over K meet in y through red.global.add:
+// with accumulate = 0 the caller provides zeroed outputs (the engine's consumers leave their inputs zeroed).  n[i] % 4 == 0.
+void marlin_tc_f32_multi(const void* x_f16_k4, int nseg, const void* const* w, const void* const* scales, int scale_bf16, const void* const* qzeros,
+                         float* const* y, const int* n, int64_t ldy, int m, int k, int group_size, int accumulate, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error(kErrCuda, "marlin_4bit(f32): cuTensorMapEncodeTiled unavailable"); return; }
+    if (nseg < 1 || nseg > kMaxSeg) { set_error(kErrBadArg, "marlin_4bit(f32): %d segments (max %d)", nseg, kMaxSeg); return; }
+    if ((uintptr_t)x_f16_k4 & 15) { set_error(kErrBadArg, "marlin_4bit(f32): x must be 16-byte aligned"); return; }
+    const int nsb = k / 256;
+    const int mb = m <= 32 ? 32 : 64;
+    CUtensorMap wm[kMaxSeg], xm;
+    GemmParams p{};
+    int tiles = 0;
+    for (int i = 0; i < kMaxSeg; ++i) {
+        const int j = i < nseg ? i : nseg - 1;               // unused slots alias the last segment
+        if ((uintptr_t)w[j] & 15) { set_error(kErrBadArg, "marlin_4bit(f32): w must be 16-byte aligned"); return; }
+        if (!make_w_map(&wm[i], w[j], n[j], nsb, kTypeM4)) return;
+        if (i < nseg) tiles += (n[i] + kTileN - 1) / kTileN;
+        p.y[i] = y[j]; p.n[i] = n[j]; p.tile_end[i] = i < nseg ? tiles : 0x7fffffff;
+        p.scales_seg[i] = scales[j]; p.zp_seg[i] = static_cast<const uint32_t*>(qzeros ? qzeros[j] : nullptr);
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
+        const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+        const cuuint32_t box[2] = {64, (cuuint32_t)mb};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x_f16_k4), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "marlin_4bit(f32): activation tensor map failed (%d)", (int)r); return; }
+    }
+    p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
+    p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
+    p.scales = p.scales_seg[0]; p.zp = p.zp_seg[0]; p.group_size = group_size; p.k = k; p.scale_bf16 = scale_bf16; p.scale_by = 1;
+    { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st);
+    check_launch("marlin_4bit(f32)");
 }
 
 // block-scaled e4m3 weights x fp16 (fp8_matmul); activations fp16 in natural order
