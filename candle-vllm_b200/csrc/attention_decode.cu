@@ -51,10 +51,16 @@ constexpr int kMaxSeqs = 1024;
 // (K: LDS.128 of a token row; V: the transposing 8-bit ldmatrix of sm_100a) -- there is no f16 staging tile.  [A first version
 // expanded each tile into a per-warp f16 staging tile (LDS + cvt + STS, then the 16-bit ldmatrix code): 0.45-0.59 of the HBM peak,
 // bound by the shared-memory round trip and the 24 KB per warp it cost; profiles/r02_fp8_attention.md.]
+#ifndef B200_FP8_WARPS          // tuning aids (tools/gpu_run_r02m.sh builds variants)
+#define B200_FP8_WARPS 8
+#endif
+#ifndef B200_FP8_STAGES
+#define B200_FP8_STAGES 3
+#endif
 template <bool kFp8>
 struct Plan {
-    static constexpr int kWarps = kFp8 ? 8 : 6;
-    static constexpr int kStages = kFp8 ? 3 : 2;
+    static constexpr int kWarps = kFp8 ? B200_FP8_WARPS : 6;
+    static constexpr int kStages = kFp8 ? B200_FP8_STAGES : 2;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kStageBytes = kFp8 ? 2 * kTile * kHeadDim : 4 * kSubTileBytes;      // 8 KB / 16 KB
     static constexpr int kWarpBytes = kStages * kStageBytes;
@@ -62,7 +68,8 @@ struct Plan {
     static constexpr int kBars = kWarps * kWarpBytes;                               // full[kWarps][kStages]
     static constexpr int kHdr = kBars + kWarps * kStages * 8;                       // int[kWarps][8][8] item headers (the producer cursor runs <= kStages + 2 items ahead)
     static constexpr int kPrefix = kHdr + kWarps * 8 * 8 * 4;                       // int[kMaxSeqs + 1]
-    static constexpr int kTotal = kPrefix + (kMaxSeqs + 1) * 4;
+    static constexpr int kCtx = kPrefix + (kMaxSeqs + 1) * 4;                       // int[kMaxSeqs]: context lengths (read once from global)
+    static constexpr int kTotal = kCtx + kMaxSeqs * 4;
     static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
@@ -144,6 +151,7 @@ struct DecodeParams {
     float* part_ml;                   // [B*kvh*max_chunks][group][2]  (m in log2 domain, l)
     unsigned int* counter;            // dynamic work queue head (zero on entry; the merge kernel re-zeroes it)
     int num_seqs, num_heads, num_kv_heads, max_blocks, chunk_pages, max_chunks;
+    int static_walk;               // 1 (FP8 cache): walk the item queue statically when the batch is uniform (B200_ATTN_STATIC=0 turns it off)
     float scale_log2;                 // scale * log2(e)
 };
 
@@ -176,6 +184,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
     int* prefix = reinterpret_cast<int*>(smem + PL::kPrefix);
+    int* ctxs = reinterpret_cast<int*>(smem + PL::kCtx);
     int* hdr = reinterpret_cast<int*>(smem + PL::kHdr) + warp * 64;          // [8][8]
     const uint32_t my_stages = smem_base + warp * PL::kWarpBytes;
     const uint32_t my_bars = smem_base + PL::kBars + warp * kStagesPerWarp * 8;
@@ -191,6 +200,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     const int chunk_tokens = p.chunk_pages * kPage;
     for (int b = threadIdx.x; b < p.num_seqs; b += kThreads) {
         const int ctx = (int)p.context_lens[b];
+        ctxs[b] = ctx;
         prefix[b + 1] = (ctx + chunk_tokens - 1) / chunk_tokens;
     }
     __syncthreads();
@@ -201,12 +211,28 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     __syncthreads();
     const int total_items = prefix[p.num_seqs] * p.num_kv_heads;
 
-    // claim the next item of the global queue into header slot `slot`; returns the lane-distributed block ids
+    // Claiming the next item of the global queue is split in two so that neither the atomic's round trip (~1 us) nor the block-table
+    // load sits in the consumer's instruction stream: claim_begin() issues the atomicAdd, claim_finish() -- one tile later, or at
+    // the latest when the item is needed -- turns the ticket into a header slot and issues the block-table load, whose result
+    // (the lane-distributed block ids) is first touched when the item's first tile is issued.
     int n_claimed = 0;
-    auto claim = [&](bool& valid, int& h, int& ntiles) -> uint32_t {
-        unsigned int id = 0;
-        if (lane == 0) id = atomicAdd(p.counter, 1u);
-        id = __shfl_sync(0xffffffffu, id, 0);
+    unsigned int pend_id = 0;
+    bool pending = false;
+    // When every sequence has the same number of chunks (the usual decode batch) the queue is walked STATICALLY: ticket k of this
+    // CTA covers items (blockIdx + k * grid) * kWarps + warp, i.e. the warps of a CTA stream neighbouring kv heads of the same
+    // (sequence, chunk) side by side -- their 128 / 256-byte rows of one token are contiguous in the cache, and requested together
+    // they open one DRAM page once.  Ragged batches keep the dynamic queue (one atomic ticket per warp), which balances them.
+    const bool static_walk = p.static_walk != 0 && prefix[p.num_seqs] == p.num_seqs * prefix[1];
+    unsigned int n_begun = 0;
+    auto claim_begin = [&]() {
+        if (static_walk) pend_id = (blockIdx.x + n_begun * gridDim.x) * PL::kWarps + warp;
+        else if (lane == 0) pend_id = atomicAdd(p.counter, 1u);
+        ++n_begun;
+        pending = true;
+    };
+    auto claim_finish = [&](bool& valid, int& h, int& ntiles) -> uint32_t {
+        const unsigned int id = __shfl_sync(0xffffffffu, pend_id, 0);
+        pending = false;
         int* hd = hdr + (n_claimed & 7) * 8;
         ++n_claimed;
         valid = id < (unsigned int)total_items;
@@ -220,7 +246,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         int lo = 0, hi = p.num_seqs;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= pair) lo = mid; else hi = mid; }
         const int c = pair - prefix[lo];
-        const int ctx = (int)p.context_lens[lo];
+        const int ctx = ctxs[lo];
         const int ntok = min(chunk_tokens, ctx - c * chunk_tokens);
         ntiles = (ntok + kTile - 1) / kTile;
         const int npages = (ntok + kPage - 1) / kPage;
@@ -234,10 +260,14 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     // ---- producer cursor: runs kStagesPerWarp tiles ahead of the consumer ---------------------------
     bool pc_valid, pn_valid;
     int pc_h, pc_ntiles, pn_h, pn_ntiles, p_tile = 0;
-    uint32_t pc_blk = claim(pc_valid, pc_h, pc_ntiles);
-    uint32_t pn_blk = claim(pn_valid, pn_h, pn_ntiles);
+    claim_begin();
+    uint32_t pc_blk = claim_finish(pc_valid, pc_h, pc_ntiles);
+    uint32_t pn_blk = 0u;
+    pn_valid = false; pn_h = 0; pn_ntiles = 0;
+    claim_begin();
     unsigned int issued = 0;
     auto issue_one = [&]() {
+        if (pending) pn_blk = claim_finish(pn_valid, pn_h, pn_ntiles);
         if (!pc_valid) return;
         const int blk = (int)__shfl_sync(0xffffffffu, pc_blk, p_tile >> 1);
         if (lane == 0) {
@@ -259,7 +289,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         ++issued;
         if (++p_tile == pc_ntiles) {
             pc_valid = pn_valid; pc_h = pn_h; pc_ntiles = pn_ntiles; pc_blk = pn_blk; p_tile = 0;
-            pn_blk = claim(pn_valid, pn_h, pn_ntiles);
+            if (pc_valid) claim_begin(); else pn_valid = false;           // an empty queue stays empty: no ticket past the end needed
         }
     };
 #pragma unroll
@@ -596,6 +626,7 @@ void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
     p.q = a.q; p.block_tables = a.block_tables; p.context_lens = a.context_lens;
     p.num_seqs = a.num_seqs; p.num_heads = a.num_heads; p.num_kv_heads = a.num_kv_heads; p.max_blocks = a.max_blocks;
     p.chunk_pages = pick_chunk_pages(a.num_seqs, a.num_kv_heads, a.max_blocks);
+    { static const int sw = [] { const char* e = getenv("B200_ATTN_STATIC"); return e ? atoi(e) : 1; }(); p.static_walk = a.fp8 ? sw : 0; }     // measured: +7 % with FP8 KV (128-byte rows), -2 % with 16-bit KV
     p.max_chunks = (a.max_blocks + p.chunk_pages - 1) / p.chunk_pages;
     p.scale_log2 = a.scale * 1.4426950408889634f;
     const size_t n_part = (size_t)a.num_seqs * a.num_kv_heads * p.max_chunks * group;
