@@ -13,7 +13,7 @@
 //   warp 1  MMA issuer: one elected lane, tcgen05.mma.kind::f16 with both operands from shared memory (SS), UMMA 128 x BN x 16,
 //           accumulators in TMEM, DOUBLE-BUFFERED (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1;
 //   warps 2-5  epilogue: tcgen05.ld (each warp its TMEM lane quadrant), convert, 16-byte stores.
-//   BN = 256 for m >= 128 (x is the 128-row operand); "swap-AB" with BN = 32 / 64 for m <= 64 (the weight tile is the 128-row operand,
+//   BN = 256 (128 / 64 while 256-wide tiles would leave SMs idle) for m > 64 (x is the 128-row operand); "swap-AB" with BN = 32 / 64 for m <= 64 (the weight tile is the 128-row operand,
 //   the few activation rows are the UMMA N dimension), so decode-size calls stream the weights once with full-width MMAs.
 // Tiles are walked n-major within a band of m-tiles so that CTAs running together share the W tile (L2).
 #include <cuda.h>
@@ -160,11 +160,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                     mbar_expect_tx(full(s), C::kStageBytes);
                     const uint32_t dst = smem_base + s * C::kStageBytes;
                     tma_load_2d(dst, &amap, full(s), kb * kBK, ta * kBM, pol);
-                    if constexpr (kBN == 256) {           // a box holds at most 256 rows; keep both halves 1024-aligned
-                        tma_load_2d(dst + C::kABytes, &bmap, full(s), kb * kBK, tb * kBN, pol);
-                    } else {
-                        tma_load_2d(dst + C::kABytes, &bmap, full(s), kb * kBK, tb * kBN, pol);
-                    }
+                    tma_load_2d(dst + C::kABytes, &bmap, full(s), kb * kBK, tb * kBN, pol);
                 }
                 __syncwarp();
             }
@@ -351,9 +347,14 @@ bool dense_gemm_16(const void* x, const void* w, const void* bias, void* y, int 
         if (!make_map(&am, w, n, k, ldw, kBM, bf16) || !make_map(&bm, x, m, k, ldx, bn, bf16)) return false;
         if (bn == 32) launch_out<32>(am, bm, p, st); else launch_out<64>(am, bm, p, st);
     } else {
-        p.swap = 0; p.tiles_a = (m + kBM - 1) / kBM; p.tiles_b = (n + 255) / 256;
-        if (!make_map(&am, x, m, k, ldx, kBM, bf16) || !make_map(&bm, w, n, k, ldw, 256, bf16)) return false;
-        launch_out<256>(am, bm, p, st);
+        // 128 x 256 tiles when they fill the machine; mid-size m (a few hundred rows) gets narrower tiles so that every SM has one
+        int bn = 256;
+        auto tiles = [&](int b) { return (int64_t)((m + kBM - 1) / kBM) * ((n + b - 1) / b); };
+        if (tiles(256) < sm_count()) bn = 128;
+        if (bn == 128 && tiles(128) < sm_count()) bn = 64;
+        p.swap = 0; p.tiles_a = (m + kBM - 1) / kBM; p.tiles_b = (n + bn - 1) / bn;
+        if (!make_map(&am, x, m, k, ldx, kBM, bf16) || !make_map(&bm, w, n, k, ldw, bn, bf16)) return false;
+        if (bn == 256) launch_out<256>(am, bm, p, st); else if (bn == 128) launch_out<128>(am, bm, p, st); else launch_out<64>(am, bm, p, st);
     }
     return check_launch("dense_gemm");
 }

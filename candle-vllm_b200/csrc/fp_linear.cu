@@ -169,6 +169,48 @@ void launch(const Dec& dec, const void* x, const void* bias, void* out, int m, i
     check_launch(who);
 }
 
+// x (f16 / bf16) -> fp16 in "K8" order for the FP4 GEMM on the tcgen05 pipeline: within every aligned group of 8 along k the
+// positions 0..7 hold k = 0,4,1,5,2,6,3,7 (qmatmul_tc.cu, F4Quarter)
+template <typename T>
+__global__ void cast_f16_k8_kernel(const T* __restrict__ x, __half* __restrict__ out, int64_t groups) {
+    pdl_wait();
+    pdl_trigger();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + i * 8);
+        const T* v = reinterpret_cast<const T*>(&raw);
+        __half o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { o[2 * q] = __float2half_rn(to_f32(v[q])); o[2 * q + 1] = __float2half_rn(to_f32(v[4 + q])); }
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
+// decode sizes of the FP4 linears on the tcgen05 pipeline (qmatmul_tc.cu), 64 rows per pass.  Scratch = fp16 K8 copy of x + fp32
+// partial-sum slabs + the post-scale pair.  false: shape / alignment not supported there (the caller falls back to the SIMT kernel)
+bool fp4_tc_route(bool mx, const void* x, const void* blocks, const void* scales, float global_scale, const void* bias, void* out, int m, int n, int k,
+                  int dtype, cudaStream_t st) {
+    static const bool force_generic = [] { const char* e = getenv("B200_FP4_GENERIC"); return e && atoi(e) != 0; }();
+    if (force_generic || !fp4_tc_supported(m > 64 ? 64 : m, n, k) || (((uintptr_t)out) & 7) || (((uintptr_t)scales) & 3)) return false;
+    const int mc = m < 64 ? m : 64;
+    const size_t x_bytes = ((size_t)mc * k * 2 + 255) & ~(size_t)255;
+    const size_t slab_bytes = (size_t)wq16_slabs(n, k) * mc * n * 4;
+    char* xs = static_cast<char*>(get_scratch(x_bytes + slab_bytes + 256, st));
+    if (!xs) { b200_last_error(); return false; }
+    for (int m0 = 0; m0 < m; m0 += 64) {
+        const int mm = m - m0 < 64 ? m - m0 : 64;
+        const int64_t groups = (int64_t)mm * k / 8;
+        int64_t g = (groups + 255) / 256;
+        if (g > (int64_t)sm_count() * 8) g = (int64_t)sm_count() * 8;
+        const char* xr = static_cast<const char*>(x) + (size_t)m0 * k * 2;
+        if (dtype == B200_BF16) launch_pdl(cast_f16_k8_kernel<__nv_bfloat16>, dim3((int)g), dim3(256), 0, st, (const __nv_bfloat16*)xr, (__half*)xs, groups);
+        else launch_pdl(cast_f16_k8_kernel<__half>, dim3((int)g), dim3(256), 0, st, (const __half*)xr, (__half*)xs, groups);
+        count_launch();
+        fp4_tc_run(mx, xs, blocks, scales, global_scale, bias, static_cast<char*>(out) + (size_t)m0 * n * 2, dtype, mm, n, k,
+                   reinterpret_cast<float*>(xs + x_bytes), reinterpret_cast<float*>(xs + x_bytes + slab_bytes), st);
+    }
+    return true;
+}
+
 bool common_check(const char* who, const void* x, const void* w, const void* s, const void* out, int m, int n, int k, int dtype, int kmul) {
     if (!x || !w || !s || !out) { set_error(kErrBadArg, "%s: null pointer", who); return false; }
     if (m <= 0 || n <= 0 || k <= 0 || k % kmul) { set_error(kErrBadArg, "%s: bad sizes m=%d n=%d k=%d (k %% %d)", who, m, n, k, kmul); return false; }
@@ -222,6 +264,7 @@ void nvfp4_matmul(const void* x, const void* blocks, const void* scales, float g
     if (m == 0 || n == 0) return;
     if (!common_check("nvfp4_matmul", x, blocks, scales, out, m, n, k, dtype, 32)) return;
     const Nvfp4Dec dec{static_cast<const uint8_t*>(blocks), static_cast<const uint8_t*>(scales), global_scale, k};
+    if (m < kDenseRows && fp4_tc_route(false, x, blocks, scales, global_scale, bias, out, m, n, k, dtype, as_stream(stream))) return;
     launch(dec, x, bias, out, m, n, k, dtype, as_stream(stream), "nvfp4_matmul");
 }
 
@@ -230,6 +273,7 @@ void mxfp4_matmul(const void* x, const void* blocks, const void* scales, const v
     if (m == 0 || n == 0) return;
     if (!common_check("mxfp4_matmul", x, blocks, scales, out, m, n, k, dtype, 32)) return;
     const Mxfp4Dec dec{static_cast<const uint8_t*>(blocks), static_cast<const uint8_t*>(scales), k};
+    if (m < kDenseRows && fp4_tc_route(true, x, blocks, scales, 1.f, bias, out, m, n, k, dtype, as_stream(stream))) return;
     launch(dec, x, bias, out, m, n, k, dtype, as_stream(stream), "mxfp4_matmul");
 }
 

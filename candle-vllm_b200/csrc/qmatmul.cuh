@@ -53,6 +53,10 @@ void marlin_tc_f32_multi(const void* x_f16_k4, int nseg, const void* const* w, c
 bool fp8_tc_supported(int m, int n, int k, int by, int bx);
 void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void* bias, void* out, int out_dtype, int m, int n, int k,
                 int by, int bx, float* slabs, float* norm /* 2 floats, device */, cudaStream_t st);
+// e2m1 [n, k/2] with e4m3 scale per 16 (+ global scale) or e8m0 scale per 32 x fp16 activations in K8 order
+bool fp4_tc_supported(int m, int n, int k);
+void fp4_tc_run(bool mx, const void* x_f16_k8, const void* blocks, const void* scales, float global_scale, const void* bias, void* out, int out_dtype,
+                int m, int n, int k, float* slabs, float* norm /* 2 floats, device */, cudaStream_t st);
 // library-owned scratch (marlin_api.cu): grown outside stream capture or set once with b200_set_scratch()
 void* get_scratch(size_t bytes, cudaStream_t st);
 

@@ -46,7 +46,7 @@ struct Cfg {
     // dependency; k-step ks goes to D[ks % kAcc] and the epilogue adds them up.  Two suffice (the dequant side sets the
     // pace) and keep the epilogue's TMEM reads (64 B/clk) short: kAcc * kMB <= 128 TMEM columns.
     static constexpr int kAcc = 2;
-    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : (kType == kTypeM4 ? 128 : (kType == kTypeF8 ? 256 : 240));
+    static constexpr int kBlk = kType == B200_GGML_Q4_K ? 144 : (is_4bit_rows(kType) ? 128 : (kType == kTypeF8 ? 256 : 240));
     static constexpr int kWBytes = kTileN * kBlk;                  // raw weights of one unit (18 KB / 30 KB)
     static constexpr int kXBytes = 4 * kMB * kXSubBytes;           // 4 sub-tiles of [kMB][64] fp16 (16 KB / 32 KB)
     // Two rings.  Raw weight bytes are dead as soon as the dequant warps have pulled them into registers, so the
@@ -208,6 +208,59 @@ struct F8Quarter {
     }
 };
 
+// FP4 (e2m1) weights, two per byte in natural order (low nibble = even k), one scale per 16 (NVFP4: e4m3 byte) or 32 (MXFP4: e8m0
+// byte) weights along k; a unit is 128 rows x 128 bytes like int4.  A 32-bit word holds k = 8i .. 8i+7; the nibble's three magnitude
+// bits dropped at f16 bits 9-11 ARE the f16 with the same value * 2^-14 (exponent field e, mantissa bit m; e = 0 lands on an f16
+// subnormal m * 2^-15 = 0.5 m * 2^-14), the sign bit goes to bit 15: two shifts and two logic ops per pair, then one HMUL2 with the
+// block scale.  Pair q of word i is (k = 8i + q, k = 8i + 4 + q) -- the activations come in the matching "K8" order (fp_linear.cu).
+// The block scale is kept as f16 * 2^6 (NVFP4: e4m3 bits << 7 = scale * 2^-8, times 2^14, exact incl. subnormal scales; MXFP4:
+// exponent field e - 106, scales below 2^-20 flush to zero, above 2^9 saturate -- far outside any checkpoint), so the product is the
+// weight * 2^-8, exact (<= 6 significant bits); the finishing pass multiplies by 2^8 (and NVFP4's global scale).
+template <int kC, bool kMx>
+struct F4Quarter {
+    static constexpr int kRaw = 8;
+    static __device__ __forceinline__ void load(const uint8_t* blk, int, uint32_t (&raw)[kRaw]) {
+        const uint4 qa = *reinterpret_cast<const uint4*>(blk + kC * 32);
+        const uint4 qb = *reinterpret_cast<const uint4*>(blk + kC * 32 + 16);
+        raw[0] = qa.x; raw[1] = qa.y; raw[2] = qa.z; raw[3] = qa.w; raw[4] = qb.x; raw[5] = qb.y; raw[6] = qb.z; raw[7] = qb.w;
+    }
+    static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
+        const uint8_t* srow = static_cast<const uint8_t*>(c.scales) + (int64_t)c.n_idx * c.sk;      // sk = scale bytes per row
+        uint32_t S[4];                                   // block scale * 2^6 as f16x2, per 16 (NVFP4) / 32 (MXFP4) weights of the quarter
+        if constexpr (kMx) {
+            const uint32_t sw = *reinterpret_cast<const uint16_t*>(srow + ((c.k0 + kC * 64) >> 5));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int e = (int)((sw >> (8 * j)) & 0xffu) - 106;
+                e = e < 1 ? 0 : (e > 30 ? 30 : e);
+                S[2 * j] = S[2 * j + 1] = ((uint32_t)e << 10) * 0x00010001u;
+            }
+        } else {
+            const uint32_t sw = *reinterpret_cast<const uint32_t*>(srow + ((c.k0 + kC * 64) >> 4));
+            const uint32_t k16384 = 0x74007400u;         // 2^14 as f16x2
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t b = (((sw >> (8 * j)) & 0x7fu) << 7) * 0x00010001u;       // e4m3 scale * 2^-8 in both halves
+                const __half2 r = __hmul2(*reinterpret_cast<__half2*>(&b), *reinterpret_cast<const __half2*>(&k16384));
+                S[j] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+        }
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t x = raw[i];
+            const __half2 s = *reinterpret_cast<const __half2*>(&S[i >> 1]);
+            uint32_t t0 = ((x << 9) & 0x0e000e00u) | ((x << 12) & 0x80008000u), t1 = ((x << 5) & 0x0e000e00u) | ((x << 8) & 0x80008000u);
+            uint32_t t2 = ((x << 1) & 0x0e000e00u) | ((x << 4) & 0x80008000u), t3 = ((x >> 3) & 0x0e000e00u) | (x & 0x80008000u);
+            const __half2 r0 = __hmul2(*reinterpret_cast<__half2*>(&t0), s), r1 = __hmul2(*reinterpret_cast<__half2*>(&t1), s);
+            const __half2 r2 = __hmul2(*reinterpret_cast<__half2*>(&t2), s), r3 = __hmul2(*reinterpret_cast<__half2*>(&t3), s);
+            v[4 * i] = *reinterpret_cast<const uint32_t*>(&r0); v[4 * i + 1] = *reinterpret_cast<const uint32_t*>(&r1);
+            v[4 * i + 2] = *reinterpret_cast<const uint32_t*>(&r2); v[4 * i + 3] = *reinterpret_cast<const uint32_t*>(&r3);
+        }
+        tc_st32(a_col + kC * 32, v);
+    }
+};
+
 // Q6_K staging.  A block = ql[128] | qh[64] | scales i8[16] | d f16 = 210 bytes and is only 2-byte aligned
 // in memory, while a TMA box must START 16-byte aligned (probed on B200: an unaligned start raises "illegal
 // instruction", tools/probes/tma_align_test.cu).  So the box starts at the block address rounded down to 16
@@ -312,6 +365,8 @@ template <int kQ> struct QuarterOf<B200_GGML_Q4_K, kQ> { using type = Q4KQuarter
 template <int kQ> struct QuarterOf<B200_GGML_Q6_K, kQ> { using type = Q6KQuarter<kQ>; };
 template <int kQ> struct QuarterOf<kTypeM4, kQ> { using type = M4Quarter<kQ>; };
 template <int kQ> struct QuarterOf<kTypeF8, kQ> { using type = F8Quarter<kQ>; };
+template <int kQ> struct QuarterOf<kTypeNV4, kQ> { using type = F4Quarter<kQ, false>; };
+template <int kQ> struct QuarterOf<kTypeMX4, kQ> { using type = F4Quarter<kQ, true>; };
 
 // =================================================================================================
 // One dequant unit for quarter kQ: pull the raw bytes into registers, hand the W stage back to the producer at
@@ -332,7 +387,7 @@ __device__ __forceinline__ void dequant_unit(const uint8_t* blk, int off, uint32
     mbar_wait(a_free_bar, a_free_parity);
     tc_fence_after();
     if (!skip) {
-        if constexpr (kType == kTypeM4 || kType == kTypeF8) Q::compute(raw, mc, a_col); else Q::compute(raw, off, a_col);
+        if constexpr (kType == kTypeM4 || kType == kTypeF8 || is_fp4(kType)) Q::compute(raw, mc, a_col); else Q::compute(raw, off, a_col);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
@@ -414,7 +469,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                     tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), sb * 256, wrow, pol_w);
                     tma_load_2d(smem_base + C::kWOff + s * C::kWBytes + 16384, wm, w_full(s), sb * 256 + 128, wrow, pol_w);
                 } else
-                tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : (kType == kTypeM4 ? sb * 128 : ((sb * 210) & ~15)),
+                tma_load_2d(smem_base + C::kWOff + s * C::kWBytes, wm, w_full(s), kType == B200_GGML_Q4_K ? sb * 144 : (is_4bit_rows(kType) ? sb * 128 : ((sb * 210) & ~15)),
                             wrow, pol_w);
             }
             __syncwarp();
@@ -652,7 +707,7 @@ void launch(const CUtensorMap* wm, const CUtensorMap& xm, const GemmParams& p, c
 
 bool make_w_map(CUtensorMap* wm, const void* w, int n, int nsb, int ggml_type) {
     EncodeTiledFn enc = encode_fn();
-    const bool q4 = ggml_type == B200_GGML_Q4_K, m4 = ggml_type == kTypeM4, f8 = ggml_type == kTypeF8;
+    const bool q4 = ggml_type == B200_GGML_Q4_K, m4 = is_4bit_rows(ggml_type), f8 = ggml_type == kTypeF8;
     // byte tensor [n][nsb * block]; box {144, 128} (Q4_K), {128, 128} (int4; fp8 with the 128-byte swizzle, two per unit) or
     // {240, 128} (Q6_K: 210-byte block + alignment slack)
     const cuuint64_t pitch = (cuuint64_t)nsb * (q4 ? 144 : (m4 ? 128 : (f8 ? 256 : 210)));
@@ -845,6 +900,8 @@ static void wq16_launch(int kind, const void* x_f16, const void* w, const void* 
     for (int i = 0; i < kMaxSeg; ++i) { p.scales_seg[i] = scales; p.zp_seg[i] = zp; }
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     if (kind == kTypeM4) { if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st); }
+    else if (kind == kTypeNV4) { if (mb == 32) launch<32, kTypeNV4>(wm, xm, p, st); else launch<64, kTypeNV4>(wm, xm, p, st); }
+    else if (kind == kTypeMX4) { if (mb == 32) launch<32, kTypeMX4>(wm, xm, p, st); else launch<64, kTypeMX4>(wm, xm, p, st); }
     else { if (mb == 32) launch<32, kTypeF8>(wm, xm, p, st); else launch<64, kTypeF8>(wm, xm, p, st); }
     if (!check_launch(who)) return;
     const int64_t total = (int64_t)m * n;
@@ -919,6 +976,25 @@ void fp8_tc_run(const void* x_f16, const void* w, const float* scale, const void
     launch_pdl(fp8_scale_norm_kernel, dim3(1), dim3(256), 0, st, scale, (int64_t)((n + by - 1) / by) * sk, norm);
     count_launch();
     wq16_launch(kTypeF8, x_f16, w, scale, 0, bx, by, sk, norm, nullptr, bias, out, out_dtype, m, n, k, slabs, st, "fp8_matmul");
+}
+
+// e2m1 weights x fp16 (nvfp4_matmul / mxfp4_matmul); activations fp16 in K8 order (within every aligned group of 8 along k:
+// positions 0..7 hold k = 0,4,1,5,2,6,3,7 -- the order the nibble pairs of a 32-bit word fall out in)
+__global__ void fp4_post_scale_kernel(float* __restrict__ norm, float post) {
+    pdl_wait();
+    pdl_trigger();
+    norm[0] = 1.f; norm[1] = post;
+}
+bool fp4_tc_supported(int m, int n, int k) {
+    if (m < 1 || m > 64 || n < 4 || n % 4 || k < 256 || k % 256) return false;
+    return (int64_t)((n + kTileN - 1) / kTileN + 2) * (k / 256) * sm_count() < ((int64_t)1 << 30);
+}
+void fp4_tc_run(bool mx, const void* x_f16_k8, const void* blocks, const void* scales, float global_scale, const void* bias, void* out, int out_dtype,
+                int m, int n, int k, float* slabs, float* norm, cudaStream_t st) {
+    launch_pdl(fp4_post_scale_kernel, dim3(1), dim3(1), 0, st, norm, 256.f * global_scale);
+    count_launch();
+    wq16_launch(mx ? kTypeMX4 : kTypeNV4, x_f16_k8, blocks, scales, 0, 0, 1, mx ? k / 32 : k / 16, norm, nullptr, bias, out, out_dtype, m, n, k, slabs, st,
+                mx ? "mxfp4_matmul" : "nvfp4_matmul");
 }
 
 // ---- grouped (mixture-of-experts) form ------------------------------------------------------------------------------------------------

@@ -11,6 +11,10 @@ namespace tc {
 constexpr int kTileN = 128;          // weight rows per tile (UMMA M)
 constexpr int kTypeM4 = 1004;        // internal: symmetric int4 (GPTQ) in this library's repacked row-major layout (marlin_4bit_*)
 constexpr int kTypeF8 = 1008;        // internal: e4m3 weights [N,K] with one f32 scale per [by, bx] tile (fp8_matmul)
+constexpr int kTypeNV4 = 1016;       // internal: e2m1 pairs [N,K/2] + e4m3 scale per 16 weights (nvfp4_matmul)
+constexpr int kTypeMX4 = 1032;       // internal: e2m1 pairs [N,K/2] + e8m0 scale per 32 weights (mxfp4_matmul)
+constexpr bool is_fp4(int t) { return t == kTypeNV4 || t == kTypeMX4; }
+constexpr bool is_4bit_rows(int t) { return t == kTypeM4 || is_fp4(t); }      // 128 raw bytes per row and unit
 constexpr int kSB = 256;             // weights per super-block
 constexpr int kDequantWarps = 16;     // 4 TMEM lane quadrants x 4 quarters of a super-block (64 weights per thread per unit)
 constexpr int kThreads = (kDequantWarps + 3) * 32;     // + W producer, X producer, MMA issuer

@@ -75,6 +75,26 @@ def test_nvfp4_and_mxfp4_matmul(dtype, m, n, k):
     assert rel_fro(y, ref) < TOL[dtype], rel_fro(y, ref)
 
 
+@pytest.mark.parametrize("m,n,k", [(32, 1024, 2048), (64, 384, 512), (5, 4096, 256), (33, 132, 768)])
+def test_fp4_on_the_tensor_core_pipeline_full_scale_range(m, n, k):
+    """Decode shapes (m <= 64 per pass, k % 256 == 0) of NVFP4 / MXFP4 run on the tcgen05 dequant-into-TMEM pipeline: e2m1 nibbles are
+    placed as f16 bit patterns (value * 2^-14), the block scale is applied as one HMUL2.  Scales here span the whole e4m3 code range --
+    zero, subnormals, 448 -- and e8m0 exponents from 2^-20 up (the kernel represents 2^-20 .. 2^9 exactly)."""
+    rng = np.random.default_rng(m * 7 + n + k)
+    dtype = torch.float16
+    blocks = F.random_fp4(rng, n, k)
+    x, xf = _x(rng, m, k, dtype)
+    sc = rng.integers(0, 0x7f, (n, k // 16), dtype=np.uint8)          # every non-negative finite e4m3 code, incl. 0 and subnormals
+    g = 0.37
+    y = pkg.LnNvfp4(torch.from_numpy(blocks).to(DEV), torch.from_numpy(sc).to(DEV), g, 1.0, None).forward(x).float().cpu().numpy()
+    ref = F.linear(xf, F.dequant_nvfp4(blocks, sc, g))
+    assert rel_fro(y, ref) < TOL[dtype], rel_fro(y, ref)
+    se = rng.integers(107, 129, (n, k // 32), dtype=np.uint8)          # 2^-20 .. 2^1 (larger scales overflow the f16 OUTPUT)
+    y = pkg.LnMxfp4(torch.from_numpy(blocks).to(DEV), torch.from_numpy(se).to(DEV)).forward(x).float().cpu().numpy()
+    ref = F.linear(xf, F.dequant_mxfp4(blocks, se))
+    assert np.isfinite(y).all() and rel_fro(y, ref) < 2 * TOL[dtype], rel_fro(y, ref)
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_prefill_chunks_dequantise_once_and_use_the_dense_tensor_core_gemm(dtype):
     """m >= 512: weights -> 16 bit once (library scratch) + dense tcgen05 GEMM with the bias in its epilogue, for all three formats.
