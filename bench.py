@@ -538,11 +538,28 @@ def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev)
             attn.forward(q, None, None, None, eng.gpu_cache[l][0], eng.gpu_cache[l][1], meta, out_dtype=torch.float16)
         reps = max(cfg.num_layers, 32)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def run_all():
+            for i in range(reps):
+                k, v = eng.gpu_cache[i % cfg.num_layers]
+                attn.forward(q, None, None, None, k, v, meta, out_dtype=torch.float16)
+
+        # the launches are captured once and replayed: at 50-100 us per launch an eager Python loop would measure the interpreter
+        graph, how = None, "CUDA-graph replay of the launches"
+        try:
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                run_all()
+            graph.replay()                                   # warm replay
+        except Exception as exc:                             # capture unavailable: eager launches (an upper bound on the kernel time)
+            graph, how = None, f"eager launches ({type(exc).__name__})"
         stream.synchronize()
         e0.record(stream)
-        for i in range(reps):
-            k, v = eng.gpu_cache[i % cfg.num_layers]
-            attn.forward(q, None, None, None, k, v, meta, out_dtype=torch.float16)
+        if graph is not None:
+            graph.replay()
+        else:
+            run_all()
         e1.record(stream)
         stream.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -552,7 +569,7 @@ def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev)
     alg = kv_bytes + io_bytes
     return {"kernel": "paged_attention_decode (one layer: split-KV kernel + merge)", "bound": "hbm",
             "achieved": alg / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
-            "ms_per_launch": ms, "ctx": ctx,
+            "ms_per_launch": ms, "ctx": ctx, "timed_as": how,
             # dram__bytes_read + dram__bytes_write of ONE `ncu --set full` capture of this kernel inside this benchmark, parsed
             # from the tracked raw export (profiles/); only quoted for the configuration it was captured on
             **traffic_fields(world, B, esz)}

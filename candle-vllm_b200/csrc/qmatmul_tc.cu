@@ -107,7 +107,8 @@ __device__ __forceinline__ int seg_first_tile(const GemmParams& p, int sg) { ret
 // nibbles are k = 0..31 and high nibbles k = 32..63 of the chunk -- the same nibble geometry as a Q4_K chunk, so the
 // subnormal-placement + HFMA2 trick applies unchanged: w = s*q - 8*s with one per-group scale s
 // (/root/reference/src/backend/gptq.rs:115-178 call site; scales arrive marlin-permuted, linear.rs:341-379).
-struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg, by, sk; const float* norm; const uint32_t* zp; };   // by / sk: fp8 scale-tile rows, scale columns; norm: fp8 range shift; zp: AWQ zero points (marlin layout) or null
+struct M4Ctx { const void* scales; int n_total, group_size, k0, n_idx, bf16, dbg, by, sk; const float* norm; const uint32_t* zp;
+               float pre[4]; int has_pre; };   // int4: {s0, s1, z0, z1} of this thread's quarter, loaded one unit ahead by the caller   // by / sk: fp8 scale-tile rows, scale columns; norm: fp8 range shift; zp: AWQ zero points (marlin layout) or null
 __device__ __forceinline__ int marlin_scale_pos(int n, bool grouped) {
     // inverse of marlin_permute_scales: position of original column n inside its permuted block
     if (grouped) { const int b = n & 63; return (n & ~63) | (8 * (b & 7) + (b >> 3)); }
@@ -140,10 +141,11 @@ struct M4Quarter {
         return (float)((word >> (4 * nib)) & 0xFu);
     }
     static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
-        const float s0 = scale_at(c, c.k0 + kC * 64), s1 = scale_at(c, c.k0 + kC * 64 + 32);
+        const float s0 = c.has_pre ? c.pre[0] : scale_at(c, c.k0 + kC * 64), s1 = c.has_pre ? c.pre[1] : scale_at(c, c.k0 + kC * 64 + 32);
+        const float z0 = c.has_pre ? c.pre[2] : zero_at(c, c.k0 + kC * 64), z1 = c.has_pre ? c.pre[3] : zero_at(c, c.k0 + kC * 64 + 32);
         const bool fast = __all_sync(0xffffffffu, fmaxf(fabsf(s0), fabsf(s1)) * 262144.f <= 65504.f);
         const __half2 s_lo = __float2half2_rn(fast ? s0 * 262144.f : s0), s_hi = __float2half2_rn(fast ? s1 * 262144.f : s1);
-        const __half2 n_lo = __float2half2_rn(-zero_at(c, c.k0 + kC * 64) * s0), n_hi = __float2half2_rn(-zero_at(c, c.k0 + kC * 64 + 32) * s1);
+        const __half2 n_lo = __float2half2_rn(-z0 * s0), n_hi = __float2half2_rn(-z1 * s1);
         uint32_t v[32];
         if (fast) {
 #pragma unroll
@@ -228,7 +230,7 @@ struct F4Quarter {
         const uint8_t* srow = static_cast<const uint8_t*>(c.scales) + (int64_t)c.n_idx * c.sk;      // sk = scale bytes per row
         uint32_t S[4];                                   // block scale * 2^6 as f16x2, per 16 (NVFP4) / 32 (MXFP4) weights of the quarter
         if constexpr (kMx) {
-            const uint32_t sw = *reinterpret_cast<const uint16_t*>(srow + ((c.k0 + kC * 64) >> 5));
+            const uint32_t sw = c.has_pre ? __float_as_uint(c.pre[0]) : (uint32_t)*reinterpret_cast<const uint16_t*>(srow + ((c.k0 + kC * 64) >> 5));
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 int e = (int)((sw >> (8 * j)) & 0xffu) - 106;
@@ -236,7 +238,7 @@ struct F4Quarter {
                 S[2 * j] = S[2 * j + 1] = ((uint32_t)e << 10) * 0x00010001u;
             }
         } else {
-            const uint32_t sw = *reinterpret_cast<const uint32_t*>(srow + ((c.k0 + kC * 64) >> 4));
+            const uint32_t sw = c.has_pre ? __float_as_uint(c.pre[0]) : *reinterpret_cast<const uint32_t*>(srow + ((c.k0 + kC * 64) >> 4));
             const uint32_t k16384 = 0x74007400u;         // 2^14 as f16x2
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -550,10 +552,34 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         int ws = 0, ab = 0;                                // ring positions and phases kept as running state (no div / mod per unit)
         uint32_t wph = 0, aph = 0;
         int tile = (int)tile0;
+        // int4: the group scales / zero points live in global memory (the checkpoint's tensors), two dependent L2 round trips per unit
+        // if loaded on demand -- they are fetched ONE UNIT AHEAD instead (weights: no dependency on the previous kernel)
+        float m4_next[4] = {0.f, 0.f, 8.f, 8.f};
+        auto m4_fetch = [&](int tl, int sbx) {
+            const int sgx = seg_of_tile(p, tl);
+            const int rw = (tl - seg_first_tile(p, sgx)) * kTileN + row, nn = sgx == 0 ? p.n[0] : (sgx == 1 ? p.n[1] : p.n[2]);
+            const M4Ctx c{sgx == 0 ? p.scales_seg[0] : (sgx == 1 ? p.scales_seg[1] : p.scales_seg[2]), nn, p.group_size, sbx * kSB, rw < nn ? rw : 0,
+                          p.scale_bf16, 0, 1, 0, nullptr, sgx == 0 ? p.zp_seg[0] : (sgx == 1 ? p.zp_seg[1] : p.zp_seg[2]), {0.f, 0.f, 0.f, 0.f}, 0};
+            const int kq = sbx * kSB + qt * 64;
+            if constexpr (is_fp4(kType)) {              // the quarter's block-scale bytes (4 e4m3 / 2 e8m0), bit-cast
+                const uint8_t* srow = static_cast<const uint8_t*>(p.scales) + (int64_t)c.n_idx * p.scale_sk;
+                m4_next[0] = __uint_as_float(kType == kTypeMX4 ? (uint32_t)*reinterpret_cast<const uint16_t*>(srow + (kq >> 5))
+                                                               : *reinterpret_cast<const uint32_t*>(srow + (kq >> 4)));
+            } else {
+                m4_next[0] = M4Quarter<0>::scale_at(c, kq); m4_next[1] = M4Quarter<0>::scale_at(c, kq + 32);
+                m4_next[2] = M4Quarter<0>::zero_at(c, kq); m4_next[3] = M4Quarter<0>::zero_at(c, kq + 32);
+            }
+        };
+        constexpr bool kPrefetchScales = kType == kTypeM4 || is_fp4(kType);
+        if constexpr (kPrefetchScales) { if (u0 < u1) m4_fetch(tile, (int)(u0 - (uint32_t)tile * nsb)); }
         for (uint32_t u = u0; u < u1; ++tile) {
             const uint32_t tile_begin = (uint32_t)tile * nsb, tile_end = tile_begin + nsb;
             const uint32_t seg_begin = u, seg_end = tile_end < u1 ? tile_end : u1;
             for (; u < seg_end; ++u, ++it) {
+                float m4_cur[4] = {m4_next[0], m4_next[1], m4_next[2], m4_next[3]};
+                if constexpr (kPrefetchScales) {
+                    if (u + 1 < u1) { if (u + 1 < tile_end) m4_fetch(tile, (int)(u + 1 - tile_begin)); else m4_fetch(tile + 1, 0); }
+                }
                 mbar_wait(w_full(ws), wph);
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 4] = clock64();
                 const uint8_t* blk = smem + C::kWOff + ws * C::kWBytes + (kType == kTypeF8 ? 0 : row * C::kBlk);    // fp8: stage base (swizzled rows)
@@ -566,7 +592,8 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const int mrow = (tile - seg_first_tile(p, msg)) * kTileN + row, mn = msg == 0 ? p.n[0] : (msg == 1 ? p.n[1] : p.n[2]);
                 const M4Ctx mc{msg == 0 ? p.scales_seg[0] : (msg == 1 ? p.scales_seg[1] : p.scales_seg[2]), mn, p.group_size, (int)(u - tile_begin) * kSB,
                                mrow < mn ? mrow : 0, p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm,
-                               msg == 0 ? p.zp_seg[0] : (msg == 1 ? p.zp_seg[1] : p.zp_seg[2])};
+                               msg == 0 ? p.zp_seg[0] : (msg == 1 ? p.zp_seg[1] : p.zp_seg[2]), {m4_cur[0], m4_cur[1], m4_cur[2], m4_cur[3]},
+                               kPrefetchScales ? 1 : 0};
                 switch (qt) {
                     case 0: dequant_unit<kType, 0>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
                     case 1: dequant_unit<kType, 1>(blk, off, a_col, w_empty(ws), a_free(ab), afp, a_ready(ab), lane, skip, mc); break;
