@@ -576,11 +576,14 @@ def attention_roofline(pkg, model, cfg, eng, B, ctx, tables, world, stream, dev)
 
 
 def traffic_fields(world, B, esz):
-    if not (world == 1 and B == 32 and esz == 2):
+    if not (world == 1 and B == 32):
         return {"traffic": None}
-    t, src = ncu_traffic("r02_attention_decode_raw.csv", "paged_attn_decode_kernel")
-    if not t:
-        t, src = ncu_traffic("r01_attention_decode_raw.csv", "paged_attn_decode_kernel")
+    if esz == 1:                                  # FP8 KV
+        t, src = ncu_traffic("r02_attention_decode_fp8_raw.csv", "paged_attn_decode_kernel")
+    else:
+        t, src = ncu_traffic("r02_attention_decode_raw.csv", "paged_attn_decode_kernel")
+        if not t:
+            t, src = ncu_traffic("r01_attention_decode_raw.csv", "paged_attn_decode_kernel")
     return {"traffic": t, "traffic_source": src} if t else {"traffic": None, "traffic_source": "no tracked ncu export found"}
 
 
