@@ -344,6 +344,7 @@ def run_b200(args):
         barrier()
         if rank == 0:
             scale = max(float(np.abs(l).max()) for l in ref_l)
+            tol = 3e-2 if args.config == "dense_bf16" else 5e-3
             errs = [float(np.abs(a - b).max()) / scale for a, b in zip(got_l, ref_l)]
             err = max(errs)
             # a greedy token may differ only on a near-tie inside the logit error
@@ -358,8 +359,11 @@ def run_b200(args):
                       "token_mismatches_beyond_logit_error": flips, "logit_scale": scale,
                       "reference": "TP=1 engine, same seeds, rank 0" + (" (eager, no CUDA graph)" if world == 1 else "")
                                    + "; teacher-forced: every step of both engines consumes the reference's tokens",
-                      "tolerance": "logits within 5e-3 of max|logit| (fp32 reduction order differs between the two engines: "
-                                   "profiles/r02_rounding_floor.md)"}
+                      "tolerance": tol, "within_tolerance": bool(err < tol and flips == 0),
+                      "tolerance_note": ("bf16 activations (relative step 3.9e-3) amplify the fp32 reduction-order difference between the two "
+                                         "engines layer by layer" if args.config == "dense_bf16" else
+                                         "fp16 activations; fp32 reduction order differs between the two engines "
+                                         "(profiles/r02_rounding_floor.md)") + "; unit: fraction of max|logit|"}
             del ref_l
         barrier()
 

@@ -69,7 +69,9 @@ struct Plan {
     static constexpr int kHdr = kBars + kWarps * kStages * 8;                       // int[kWarps][8][8] item headers (the producer cursor runs <= kStages + 2 items ahead)
     static constexpr int kPrefix = kHdr + kWarps * 8 * 8 * 4;                       // int[kMaxSeqs + 1]
     static constexpr int kCtx = kPrefix + (kMaxSeqs + 1) * 4;                       // int[kMaxSeqs]: context lengths (read once from global)
-    static constexpr int kTotal = kCtx + kMaxSeqs * 4;
+    static constexpr int kMail = (kCtx + kMaxSeqs * 4 + 7) / 8 * 8;                             // CTA ticket mailbox: u64[8] tickets + u32[8] acknowledgements
+    static constexpr int kHalf = kMail + 64 + 32 + 16;                              // int[kMaxSeqs + 1]: chunk prefix for the halved chunk size (+ the decision word before it)
+    static constexpr int kTotal = kHalf + (kMaxSeqs + 1) * 4;
     static_assert(kTotal <= 232448, "exceeds the 227 KB shared memory of an SM");
 };
 
@@ -151,7 +153,8 @@ struct DecodeParams {
     float* part_ml;                   // [B*kvh*max_chunks][group][2]  (m in log2 domain, l)
     unsigned int* counter;            // dynamic work queue head (zero on entry; the merge kernel re-zeroes it)
     int num_seqs, num_heads, num_kv_heads, max_blocks, chunk_pages, max_chunks;
-    int static_walk;               // 1 (FP8 cache): walk the item queue statically when the batch is uniform (B200_ATTN_STATIC=0 turns it off)
+    int adaptive_chunks;           // 1: the kernel may halve chunk_pages from the device-side context lengths (B200_ATTN_ADAPTIVE=0: off)
+    int static_walk;               // queue mode: 0 per-warp tickets, 1 CTA tickets (FP8 cache), 2 static walk (B200_ATTN_STATIC overrides)
     float scale_log2;                 // scale * log2(e)
 };
 
@@ -194,21 +197,45 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (threadIdx.x < 8) {
+        reinterpret_cast<unsigned long long*>(smem + PL::kMail)[threadIdx.x] = 0ull;
+        reinterpret_cast<unsigned int*>(smem + PL::kMail + 64)[threadIdx.x] = 0u;
+    }
     pdl_wait();            // context_lens / q / KV written by the previous kernels
     pdl_trigger();
-    // chunk prefix over sequences from the DEVICE-side context lengths
-    const int chunk_tokens = p.chunk_pages * kPage;
-    for (int b = threadIdx.x; b < p.num_seqs; b += kThreads) {
-        const int ctx = (int)p.context_lens[b];
-        ctxs[b] = ctx;
-        prefix[b + 1] = (ctx + chunk_tokens - 1) / chunk_tokens;
+    // Chunk size from the DEVICE-side context lengths: the host proposes p.chunk_pages (pick_chunk_pages, from the table width);
+    // items are whole chunks, so the makespan is rounds x chunk length -- when the proposed size leaves an awkward last round (e.g. 2.16
+    // items per warp = 3 rounds of 16 tiles at ctx 4664 with FP8 KV: 74 us instead of 63), half the size wins.  Every CTA takes the same
+    // decision from the same numbers; CTA 0 publishes it in the workspace header for the merge kernel.
+    int* prefix_half = reinterpret_cast<int*>(smem + PL::kHalf);           // chunk prefix for the halved chunk size
+    int* decision = reinterpret_cast<int*>(smem + PL::kMail + 96);
+    {
+        const int ct0 = p.chunk_pages * kPage, ct1 = (p.chunk_pages > 1 ? p.chunk_pages / 2 : 1) * kPage;
+        for (int b = threadIdx.x; b < p.num_seqs; b += kThreads) {
+            const int ctx = (int)p.context_lens[b];
+            ctxs[b] = ctx;
+            prefix[b + 1] = (ctx + ct0 - 1) / ct0; prefix_half[b + 1] = (ctx + ct1 - 1) / ct1;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        prefix[0] = 0;
-        for (int b = 0; b < p.num_seqs; ++b) prefix[b + 1] += prefix[b];
+        prefix[0] = prefix_half[0] = 0;
+        for (int b = 0; b < p.num_seqs; ++b) { prefix[b + 1] += prefix[b]; prefix_half[b + 1] += prefix_half[b]; }
+        int cp = p.chunk_pages;
+        if (p.chunk_pages > 1 && p.adaptive_chunks) {
+            const int64_t slots = (int64_t)gridDim.x * PL::kWarps;
+            const int64_t r0 = ((int64_t)prefix[p.num_seqs] * p.num_kv_heads + slots - 1) / slots;
+            const int64_t r1 = ((int64_t)prefix_half[p.num_seqs] * p.num_kv_heads + slots - 1) / slots;
+            // cost in tiles: rounds x (tiles per chunk + ~1 tile of per-item overhead: claim, Q fragments, partial write, merge)
+            if (r1 * (p.chunk_pages + 1) < r0 * (2 * p.chunk_pages + 1)) cp = p.chunk_pages / 2;
+        }
+        decision[0] = cp;
+        if (blockIdx.x == 0) p.counter[4] = (unsigned int)cp;
     }
     __syncthreads();
+    const int chunk_pages = decision[0];
+    const int chunk_tokens = chunk_pages * kPage;
+    if (chunk_pages != p.chunk_pages) prefix = prefix_half;
     const int total_items = prefix[p.num_seqs] * p.num_kv_heads;
 
     // Claiming the next item of the global queue is split in two so that neither the atomic's round trip (~1 us) nor the block-table
@@ -218,20 +245,54 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
     int n_claimed = 0;
     unsigned int pend_id = 0;
     bool pending = false;
-    // When every sequence has the same number of chunks (the usual decode batch) the queue is walked STATICALLY: ticket k of this
-    // CTA covers items (blockIdx + k * grid) * kWarps + warp, i.e. the warps of a CTA stream neighbouring kv heads of the same
-    // (sequence, chunk) side by side -- their 128 / 256-byte rows of one token are contiguous in the cache, and requested together
-    // they open one DRAM page once.  Ragged batches keep the dynamic queue (one atomic ticket per warp), which balances them.
-    const bool static_walk = p.static_walk != 0 && prefix[p.num_seqs] == p.num_seqs * prefix[1];
+    // Queue modes.  0: every warp draws its own ticket (one item).  1 (FP8 cache): the CTA draws tickets -- warp 0 does the atomic and
+    // posts the ticket in a shared-memory mailbox, ticket T covers items T * kWarps + warp, so the warps of a CTA stream neighbouring
+    // kv heads of the same (sequence, chunk) side by side: their 128-byte rows of one token are contiguous in the cache and, requested
+    // together, open a DRAM page once (+7 % at 8 kv heads); balancing stays dynamic at CTA granularity.  2: static walk (ticket k of
+    // a CTA = blockIdx + k * grid; uniform batches only; kept for comparison).
+    // Mailbox protocol: slot j % 8 holds {j + 1, T}; a reader acknowledges, and warp 0 re-uses a slot only after all kWarps - 1
+    // readers of its previous ticket have acknowledged.  Warp 0 never waits for a ticket, readers only for warp 0's own progress.
+    const int qmode = p.static_walk == 2 ? (prefix[p.num_seqs] == p.num_seqs * prefix[1] ? 2 : 0) : p.static_walk;
+    unsigned long long* mail = reinterpret_cast<unsigned long long*>(smem + PL::kMail);
+    unsigned int* acks = reinterpret_cast<unsigned int*>(smem + PL::kMail + 64);
     unsigned int n_begun = 0;
     auto claim_begin = [&]() {
-        if (static_walk) pend_id = (blockIdx.x + n_begun * gridDim.x) * PL::kWarps + warp;
-        else if (lane == 0) pend_id = atomicAdd(p.counter, 1u);
+        // the first ticket of every warp / CTA is its own index: no atomic round trip (~1 us) before the first TMA of the launch
+        if (qmode == 2) pend_id = (blockIdx.x + n_begun * gridDim.x) * PL::kWarps + warp;
+        else if (n_begun == 0) pend_id = qmode == 1 ? blockIdx.x : blockIdx.x * PL::kWarps + warp;
+        else if (qmode == 1) {
+            if (warp == 0 && lane == 0) {
+                const unsigned int slot = n_begun & 7;
+                if (n_begun >= 9) {                      // ticket 0 never went through the mailbox
+                    while (*reinterpret_cast<volatile unsigned int*>(&acks[slot]) != (unsigned int)(PL::kWarps - 1)) {}
+                    *reinterpret_cast<volatile unsigned int*>(&acks[slot]) = 0u;
+                    __threadfence_block();
+                }
+                pend_id = gridDim.x + atomicAdd(p.counter, 1u);
+            }
+        } else if (lane == 0) pend_id = gridDim.x * PL::kWarps + atomicAdd(p.counter, 1u);
         ++n_begun;
         pending = true;
     };
     auto claim_finish = [&](bool& valid, int& h, int& ntiles) -> uint32_t {
-        const unsigned int id = __shfl_sync(0xffffffffu, pend_id, 0);
+        unsigned int id = __shfl_sync(0xffffffffu, pend_id, 0);
+        if (qmode == 1 && n_begun == 1) id = id * PL::kWarps + warp;          // ticket 0 = blockIdx, known to every warp
+        else if (qmode == 1) {
+            const unsigned int j = n_begun - 1, slot = j & 7;
+            unsigned int T = id;
+            if (lane == 0) {
+                if (warp == 0) {
+                    *reinterpret_cast<volatile unsigned long long*>(&mail[slot]) = ((unsigned long long)(j + 1) << 32) | T;
+                } else {
+                    unsigned long long v;
+                    do { v = *reinterpret_cast<volatile unsigned long long*>(&mail[slot]); } while ((unsigned int)(v >> 32) != j + 1);
+                    T = (unsigned int)v;
+                    atomicAdd(&acks[slot], 1u);
+                }
+            }
+            T = __shfl_sync(0xffffffffu, T, 0);
+            id = T * PL::kWarps + warp;
+        }
         pending = false;
         int* hd = hdr + (n_claimed & 7) * 8;
         ++n_claimed;
@@ -251,7 +312,7 @@ paged_attn_decode_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_
         ntiles = (ntok + kTile - 1) / kTile;
         const int npages = (ntok + kPage - 1) / kPage;
         if (lane == 0) { hd[0] = 1; hd[1] = lo; hd[2] = h; hd[3] = c; hd[4] = ctx; hd[5] = ntiles; }
-        return lane < npages ? p.block_tables[(int64_t)lo * p.max_blocks + c * p.chunk_pages + lane] : 0u;
+        return lane < npages ? p.block_tables[(int64_t)lo * p.max_blocks + c * chunk_pages + lane] : 0u;
     };
 
     uint64_t policy;
@@ -480,10 +541,11 @@ template <typename T, typename TOut, bool kK4 = false>
 __global__ void __launch_bounds__(kHeadDim)
 paged_attn_merge_kernel(TOut* __restrict__ out, const float* __restrict__ part_o, const float* __restrict__ part_ml,
                         const uint32_t* __restrict__ context_lens, unsigned int* __restrict__ counter, int num_heads,
-                        int num_kv_heads, int group, int chunk_tokens, int max_chunks) {
+                        int num_kv_heads, int group, int max_chunks) {
     pdl_wait();
     pdl_trigger();
     const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    const int chunk_tokens = (int)counter[4] * kPage;        // the chunk size the decode kernel settled on
     if (head == 0 && b == 0 && d == 0) *counter = 0u;        // leave the work queue ready for the next launch
     const int h = head / group, r = head - h * group;
     const int ctx = (int)context_lens[b];
@@ -577,7 +639,7 @@ void launch(const DecodeArgs& a, const CUtensorMap& kmap, const CUtensorMap& vma
     count_launch();
     launch_pdl(paged_attn_merge_kernel<T, TOut, kK4>, dim3(a.num_heads, a.num_seqs), dim3(kHeadDim), 0, st,
                static_cast<TOut*>(a.out), (const float*)p.part_o, (const float*)p.part_ml, a.context_lens, p.counter, (int)a.num_heads,
-               (int)a.num_kv_heads, (int)kGroup, (int)(p.chunk_pages * kPage), (int)p.max_chunks);
+               (int)a.num_kv_heads, (int)kGroup, (int)p.max_chunks);
     count_launch();
 }
 
@@ -626,8 +688,10 @@ void paged_attention_decode_tma(const DecodeArgs& a, cudaStream_t st) {
     p.q = a.q; p.block_tables = a.block_tables; p.context_lens = a.context_lens;
     p.num_seqs = a.num_seqs; p.num_heads = a.num_heads; p.num_kv_heads = a.num_kv_heads; p.max_blocks = a.max_blocks;
     p.chunk_pages = pick_chunk_pages(a.num_seqs, a.num_kv_heads, a.max_blocks);
-    { static const int sw = [] { const char* e = getenv("B200_ATTN_STATIC"); return e ? atoi(e) : 1; }(); p.static_walk = a.fp8 ? sw : 0; }     // measured: +7 % with FP8 KV (128-byte rows), -2 % with 16-bit KV
-    p.max_chunks = (a.max_blocks + p.chunk_pages - 1) / p.chunk_pages;
+    { static const int sw = [] { const char* e = getenv("B200_ATTN_STATIC"); return e ? atoi(e) : 1; }(); p.static_walk = a.fp8 ? sw : 0; }     // queue mode (see the kernel): CTA tickets with FP8 KV (+7 %; -2 % with 16-bit KV, 6 warps)
+    { static const int ad = [] { const char* e = getenv("B200_ATTN_ADAPTIVE"); return e ? atoi(e) : 1; }(); p.adaptive_chunks = ad; }
+    const int min_pages = p.adaptive_chunks && p.chunk_pages > 1 ? p.chunk_pages / 2 : p.chunk_pages;      // the kernel may halve the chunk
+    p.max_chunks = (a.max_blocks + min_pages - 1) / min_pages;
     p.scale_log2 = a.scale * 1.4426950408889634f;
     const size_t n_part = (size_t)a.num_seqs * a.num_kv_heads * p.max_chunks * group;
     const size_t need = n_part * (kHeadDim * 4 + 8) + 256;
