@@ -45,6 +45,8 @@ int wq16_slabs(int n, int k);
 // int4 (GPTQ symmetric / AWQ with zero points; repacked by gptq_repack / awq_repack) x fp16 activations in K4 order
 void marlin_tc(const void* x_f16_k4, const void* w, const void* scales, const void* qzeros /* null: symmetric */, void* out, int out_dtype,
                int m, int n, int k, int group_size, float* slabs, cudaStream_t st);
+// L2 prefetch hint: the weights the NEXT GEMM of this thread's chain will stream (consumed by the next tcgen05 GEMM launch)
+void qmatmul_tc_prefetch_next(int n, const void* const* ptrs, const size_t* bytes);
 // decode-engine form: up to 3 int4 matrices sharing the activations in one launch, f32 output, split tiles red.add into y
 // (accumulate = 0: y zeroed by the caller)
 void marlin_tc_f32_multi(const void* x_f16_k4, int nseg, const void* const* w, const void* const* scales, int scale_bf16, const void* const* qzeros,

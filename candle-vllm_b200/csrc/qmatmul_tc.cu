@@ -96,6 +96,10 @@ struct GemmParams {
     const int* num_items;          // device: number of items of this step
     const uint32_t* row_map;       // sorted position -> output row
     const float* row_scale;        // per OUTPUT row multiplier (top-k routing weight) or null
+    // L2 prefetch of the NEXT GEMM's weights (decode engine): once this CTA's own loads are all issued, its W producer asks the L2 to
+    // fetch its 1 / grid share of up to three tensors -- HBM is idle during the drain / epilogue / next prologue (~3 us per boundary)
+    const char* pf_ptr[3];
+    unsigned int pf_bytes[3];      // 0 = unused; multiples of 16
     long long* trace;              // profiling aid: per-unit clock64 stamps of CTA 0 (B200_GEMM_TRACE)
     int debug;                     // profiling aid (B200_GEMM_DEBUG): 1 = skip MMA issue, 2 = skip dequant, 4 = skip epilogue stores
 };
@@ -477,6 +481,19 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
             __syncwarp();
             if (++sb == (int)nsb) { sb = 0; ++tile; }
         }
+        if (leader) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if (p.pf_bytes[i] == 0) continue;
+                // this CTA's slice, in 4 KB requests
+                const unsigned int per = ((p.pf_bytes[i] / gridDim.x + 4095u) & ~4095u);
+                const unsigned int b0 = per * blockIdx.x;
+                for (unsigned int o = b0; o < b0 + per && o < p.pf_bytes[i]; o += 4096u) {
+                    const unsigned int sz = p.pf_bytes[i] - o < 4096u ? p.pf_bytes[i] - o : 4096u;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr[i] + o), "r"(sz) : "memory");
+                }
+            }
+        }
     } else if (warp == kDequantWarps + 1) {
         // ================================== X PRODUCER (L2 resident) =============================
         pdl_wait();        // activations come from the previous kernel (the weight stream above does not wait: weights are static)
@@ -846,6 +863,22 @@ int qmatmul_tc_slab_count(int64_t n_tiles, int nsb) {
 // slabs_avail = 0: y receives the product (split tiles red.add into it: see qmatmul_tc_needs_zeroed_output).
 // slabs_avail > 0: split tiles store their partial sums to distinct slabs y[sg] + s * slab_stride (plain stores, nothing to
 // pre-zero, bitwise deterministic); returns the number of slabs the consumer has to add up.
+namespace { thread_local const void* t_pf_ptr[3]; thread_local size_t t_pf_bytes[3]; thread_local int t_pf_n = 0; }
+// the weights the NEXT GEMM of the caller's chain will stream: the next qmatmul_tc_multi / marlin_tc_f32_multi launch of this thread asks
+// the L2 to prefetch them from its tail (consumed by that launch)
+void qmatmul_tc_prefetch_next(int n, const void* const* ptrs, const size_t* bytes) {
+    static const bool off = [] { const char* e = getenv("B200_GEMM_PREFETCH"); return e && atoi(e) == 0; }();
+    t_pf_n = 0;
+    if (off) return;
+    for (int i = 0; i < n && i < 3; ++i) {
+        if (!ptrs[i] || ((uintptr_t)ptrs[i] & 15) || bytes[i] < 16 || bytes[i] >= ((size_t)1 << 31)) continue;
+        t_pf_ptr[t_pf_n] = ptrs[i]; t_pf_bytes[t_pf_n] = bytes[i] & ~(size_t)15; ++t_pf_n;
+    }
+}
+static void take_prefetch(GemmParams& p) {
+    for (int i = 0; i < 3; ++i) { p.pf_ptr[i] = i < t_pf_n ? static_cast<const char*>(t_pf_ptr[i]) : nullptr; p.pf_bytes[i] = i < t_pf_n ? (unsigned int)t_pf_bytes[i] : 0u; }
+    t_pf_n = 0;
+}
 int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* const* y, const int* n, int64_t ldy, int m, int k,
                      int ggml_type, int accumulate, int slabs_avail, int64_t slab_stride, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
@@ -877,6 +910,7 @@ int qmatmul_tc_multi(const void* x_f16, int nseg, const void* const* w, float* c
     if ((int64_t)tiles * nsb * sm_count() >= (int64_t)1 << 31) { set_error(kErrUnsupported, "qmatmul: %d tiles x %d super-blocks exceed the 32-bit unit range", tiles, nsb); return 0; }
     p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
     p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
+    take_prefetch(p);
     if (slabs_avail > 0) {
         p.slabs = qmatmul_tc_slab_count(tiles, nsb);
         p.slab_stride = slab_stride;
@@ -987,6 +1021,7 @@ void marlin_tc_f32_multi(const void* x_f16_k4, int nseg, const void* const* w, c
     p.ldy = ldy; p.m = m; p.nsb = nsb; p.n_tiles = tiles; p.accumulate = accumulate;
     p.whole_tiles = use_whole_tiles(tiles) ? 1 : 0;
     p.scales = p.scales_seg[0]; p.zp = p.zp_seg[0]; p.group_size = group_size; p.k = k; p.scale_bf16 = scale_bf16; p.scale_by = 1;
+    take_prefetch(p);
     { static const char* dbg = getenv("B200_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     if (mb == 32) launch<32, kTypeM4>(wm, xm, p, st); else launch<64, kTypeM4>(wm, xm, p, st);
     check_launch("marlin_4bit(f32)");
