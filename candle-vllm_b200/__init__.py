@@ -19,6 +19,6 @@ from .llama import LlamaConfig, GGUFLLaMa, MarlinWeight  # noqa: F401
 from .block_manager import BlockManager, PrefixCache, PrefixCacheConfig, Seq, SeqGroup, AllocStatus  # noqa: F401
 from .gptq import gptq_matmul, marlin_weight_repack, marlin_permute_scales  # noqa: F401
 from .linear import QLinear  # noqa: F401
-from .moe import FusedMoe, topk_softmax, sort_expert_assignments, moe_gemm_gguf  # noqa: F401
+from .moe import FusedMoe, topk_softmax, sort_expert_assignments, moe_gemm_gguf, moe_gemm_fp8  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -25,7 +25,7 @@ SYMBOLS = [
     "qmatmul_workspace_bytes", "qmatmul_f32", "qmatmul_f16act", "qmatmul_slab_count", "qmatmul_f16act_slabs", "b200_llama_peer_inbox_bytes", "b200_llama_set_peer_inboxes", "b200_llama_peer_timeouts", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free",
     "dequantize_f32", "linear_16bit", "fp8_matmul", "nvfp4_matmul", "mxfp4_matmul",
     "concat_and_cache_mla", "mla_paged_decode_workspace_bytes", "mla_paged_attention",
-    "topk_softmax", "sort_expert_assignments", "moe_gemm_workspace_bytes", "moe_gemm_gguf",
+    "topk_softmax", "sort_expert_assignments", "moe_gemm_workspace_bytes", "moe_gemm_gguf", "moe_gemm_fp8_workspace_bytes", "moe_gemm_fp8",
     "rms_norm", "fused_rope_f32", "silu_mul", "add_f32", "cast", "embedding_f32", "argmax_f32", "rope_and_cache",
     "b200_llama_create", "b200_llama_destroy", "b200_llama_set_layer", "b200_llama_set_globals", "b200_llama_set_layer_ex", "b200_llama_set_globals_ex",
     "b200_llama_set_kv_cache", "b200_llama_set_comm", "b200_llama_decode", "b200_llama_decode_resident", "b200_llama_linear_chain", "b200_llama_uses_layer_kernel", "b200_llama_mega_trace",
@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
         L.paged_attention_decode_workspace_bytes.restype = C.c_size_t
         L.qmatmul_workspace_bytes.restype = C.c_size_t
         L.moe_gemm_workspace_bytes.restype = C.c_size_t
+        L.moe_gemm_fp8_workspace_bytes.restype = C.c_size_t
         L.mla_paged_decode_workspace_bytes.restype = C.c_size_t
         L.b200_llama_create.restype = C.c_void_p
         L.b200_llama_peer_inbox_bytes.restype = C.c_size_t

@@ -14,6 +14,10 @@
 // (expert, 128-row weight tile, chunk of <= 32 rows) items: weight tile = UMMA A (dequantised straight into TMEM), the expert's rows =
 // UMMA B through one TMA box, results scattered back to their pair rows with the routing weight folded in.  Nothing on this path
 // synchronises with the host or allocates: the item list is built on the device from this step's routing (graph-capture safe).
+#include <cuda_fp8.h>
+
+#include <type_traits>
+
 #include "moe.cuh"
 #include "qmatmul.cuh"
 
@@ -143,6 +147,57 @@ moe_gather_kernel(const float* __restrict__ x, const uint32_t* __restrict__ sort
     }
 }
 
+// the same from 16-bit activations into fp16 in NATURAL order (moe_gemm_fp8)
+template <typename T>
+__global__ void __launch_bounds__(256)
+moe_gather16_kernel(const T* __restrict__ x, const uint32_t* __restrict__ sorted_pair, __half* __restrict__ xs, int pairs, int k, int per_token, int topk) {
+    pdl_wait();
+    pdl_trigger();
+    const int j = blockIdx.x;
+    __half* dst = xs + (int64_t)j * k;
+    if (j >= pairs) {
+        for (int i = threadIdx.x * 8; i < k; i += blockDim.x * 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint32_t pr = sorted_pair[j];
+    const T* src = x + (int64_t)(per_token ? pr / (uint32_t)topk : pr) * k;
+    for (int i = threadIdx.x * 8; i < k; i += blockDim.x * 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(src + i);
+        if constexpr (std::is_same<T, __half>::value) { *reinterpret_cast<uint4*>(dst + i) = raw; }
+        else {
+            const T* v = reinterpret_cast<const T*>(&raw);
+            __half o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = from_f32<__half>(to_f32(v[q]));
+            *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(o);
+        }
+    }
+}
+
+// shape-generic FP8 fallback: one warp per (pair, output column); exact fp32 decode
+template <typename T>
+__global__ void __launch_bounds__(256)
+moe_gemm_fp8_generic_kernel(const T* __restrict__ x, const uint8_t* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ topk_w,
+                            const uint32_t* __restrict__ sorted_pair, const uint32_t* __restrict__ sorted_expert, float* __restrict__ out, int pairs, int n, int k,
+                            int by, int bx, int per_token, int topk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.y, col = blockIdx.x * 8 + warp;
+    if (j >= pairs || col >= n) return;
+    const uint32_t pr = sorted_pair[j], e = sorted_expert[j];
+    const T* xr = x + (int64_t)(per_token ? pr / (uint32_t)topk : pr) * k;
+    const uint8_t* wr = w + ((int64_t)e * n + col) * k;
+    const int sk = (k + bx - 1) / bx;
+    const float* sr = scale + ((int64_t)e * ((n + by - 1) / by) + col / by) * sk;
+    float acc = 0.f;
+    for (int i = lane; i < k; i += 32) {
+        const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)wr[i], __NV_E4M3);
+        acc += __half2float(__half(h)) * sr[i / bx] * to_f32(xr[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(int64_t)pr * n + col] = acc * (topk_w ? topk_w[pr] : 1.f);
+}
+
 // shape-generic fallback (k not a multiple of 256, Q8_0, ...): one warp per (pair, output column chunk) -- correctness path
 template <int kType>
 __global__ void __launch_bounds__(256)
@@ -237,6 +292,55 @@ void moe_gemm_gguf(const float* x, const void* experts, const float* topk_weight
     else moe_gemm_generic_kernel<B200_GGML_Q8_0><<<grid, 256, 0, st>>>(x, experts, topk_weights, sorted_token_ids, expert_ids, out, num_pairs, n, k, per_token, topk);
     count_launch();
     check_launch("moe_gemm_gguf");
+}
+
+size_t moe_gemm_fp8_workspace_bytes(int32_t num_pairs, int32_t n, int32_t k, int32_t num_experts) {
+    return moe_gemm_workspace_bytes(num_pairs, n, k, num_experts) + ((size_t)num_pairs * (size_t)n * 4 + 255) / 256 * 256 + 256;
+}
+
+// attention_rs::moe::moe_gemm_fp8 (call sites /root/reference/src/openai/models/layers/moe.rs:1447-1473): x [size_m, k] and out [num_pairs, n] of
+// `dtype` (f16 / bf16); experts e4m3 [E, n, k]; scale f32 [E, ceil(n / by), ceil(k / bx)]; the rest as moe_gemm_gguf.
+void moe_gemm_fp8(const void* x, const void* experts, const float* scale, const float* topk_weights, const uint32_t* sorted_token_ids,
+                  const uint32_t* expert_ids, void* out, int32_t num_experts, int32_t topk, int32_t size_m, int32_t num_pairs, int32_t n, int32_t k,
+                  int32_t block_y, int32_t block_x, int32_t dtype, int32_t is_prefill, void* workspace, size_t workspace_bytes, int64_t stream) {
+    (void)is_prefill;
+    if (num_pairs == 0 || n == 0) return;
+    B200_REQUIRE(x && experts && scale && sorted_token_ids && expert_ids && out, kErrBadArg, "moe_gemm_fp8: null pointer");
+    B200_REQUIRE(num_experts >= 1 && num_experts <= 1024 && topk >= 1 && n > 0 && k > 0 && block_y > 0 && block_x > 0, kErrBadArg, "moe_gemm_fp8: bad sizes");
+    B200_REQUIRE(size_m == num_pairs || (int64_t)size_m * topk == num_pairs, kErrBadArg,
+                 "moe_gemm_fp8: x has %d rows, expected %d (one per pair) or %d (one per token)", size_m, num_pairs, num_pairs / topk);
+    B200_REQUIRE(dtype == B200_F16 || dtype == B200_BF16, kErrUnsupported, "moe_gemm_fp8: dtype %d (f16 / bf16)", dtype);
+    B200_REQUIRE(workspace && ((uintptr_t)workspace & 255) == 0 && workspace_bytes >= moe_gemm_fp8_workspace_bytes(num_pairs, n, k, num_experts), kErrBadArg,
+                 "moe_gemm_fp8: workspace of moe_gemm_fp8_workspace_bytes() bytes, 256-byte aligned, required");
+    cudaStream_t st = as_stream(stream);
+    const int per_token = size_m != num_pairs;
+    char* ws = static_cast<char*>(workspace);
+    const size_t xs_bytes = ((size_t)(num_pairs + 32) * (size_t)k * 2 + 255) / 256 * 256;
+    const int max_items = (int)(((size_t)num_pairs / 32 + (size_t)num_experts) * (size_t)((n + 127) / 128));
+    const size_t base = moe_gemm_workspace_bytes(num_pairs, n, k, num_experts);
+    float* y32 = reinterpret_cast<float*>(ws + base);
+    float* norm = reinterpret_cast<float*>(ws + base + ((size_t)num_pairs * (size_t)n * 4 + 255) / 256 * 256);
+    if (qmatmul_tc_moe_fp8_supported(n, k, block_y, block_x) && k % 8 == 0 && (((uintptr_t)x | (uintptr_t)experts) & 15) == 0) {
+        __half* xs = reinterpret_cast<__half*>(ws);
+        MoeItem* items = reinterpret_cast<MoeItem*>(ws + xs_bytes);
+        int* num_items = reinterpret_cast<int*>(items + max_items);
+        if (dtype == B200_BF16) launch_pdl(moe_gather16_kernel<__nv_bfloat16>, dim3(num_pairs + 32), dim3(256), 0, st, (const __nv_bfloat16*)x, sorted_token_ids, xs, (int)num_pairs, (int)k, per_token, (int)topk);
+        else launch_pdl(moe_gather16_kernel<__half>, dim3(num_pairs + 32), dim3(256), 0, st, (const __half*)x, sorted_token_ids, xs, (int)num_pairs, (int)k, per_token, (int)topk);
+        launch_pdl(moe_items_kernel, dim3(1), dim3(256), 0, st, expert_ids, (int)num_pairs, (int)num_experts, (int)n, items, num_items, max_items);
+        count_launch(2);
+        if (!check_launch("moe_gemm_fp8")) return;
+        qmatmul_tc_moe_fp8(xs, num_pairs + 32, experts, scale, num_experts, y32, n, n, k, block_y, block_x, items, num_items, max_items, sorted_token_ids,
+                           topk_weights, norm, st);
+    } else {
+        const dim3 grid(ceil_div(n, 8), num_pairs);
+        if (dtype == B200_BF16)
+            moe_gemm_fp8_generic_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const uint8_t*)experts, scale, topk_weights, sorted_token_ids, expert_ids, y32, num_pairs, n, k, block_y, block_x, per_token, topk);
+        else
+            moe_gemm_fp8_generic_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, (const uint8_t*)experts, scale, topk_weights, sorted_token_ids, expert_ids, y32, num_pairs, n, k, block_y, block_x, per_token, topk);
+        count_launch();
+        if (!check_launch("moe_gemm_fp8")) return;
+    }
+    cast(y32, out, (int64_t)num_pairs * n, B200_F32, dtype, stream);
 }
 
 }  // extern "C"

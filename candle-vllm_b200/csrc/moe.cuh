@@ -18,4 +18,10 @@ bool qmatmul_tc_moe_supported(int n, int k, int ggml_type);
 void qmatmul_tc_moe(const void* xs_f16_k4, int xs_rows, const void* w, int num_experts, float* y, int64_t ldy, int n, int k, int ggml_type,
                     const MoeItem* items, const int* num_items, int max_items, const uint32_t* row_map, const float* row_scale, cudaStream_t st);
 
+// the same with block-scaled e4m3 experts; xs fp16 in natural order; norm: 2 floats of device scratch
+bool qmatmul_tc_moe_fp8_supported(int n, int k, int by, int bx);
+void qmatmul_tc_moe_fp8(const void* xs_f16, int xs_rows, const void* w, const float* scale, int num_experts, float* y, int64_t ldy, int n, int k, int by, int bx,
+                        const MoeItem* items, const int* num_items, int max_items, const uint32_t* row_map, const float* row_scale, float* norm,
+                        cudaStream_t st);
+
 }  // namespace b200

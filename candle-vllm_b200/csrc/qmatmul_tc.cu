@@ -606,9 +606,14 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const bool skip = (p.debug & 2) != 0;
                 // marlin: the scales / zero points of the weight matrix this tile belongs to (constant indices only, see seg_first_tile)
                 const int msg = kType == kTypeM4 ? seg_of_tile(p, tile) : 0;
-                const int mrow = (tile - seg_first_tile(p, msg)) * kTileN + row, mn = msg == 0 ? p.n[0] : (msg == 1 ? p.n[1] : p.n[2]);
+                int mrow = (tile - seg_first_tile(p, msg)) * kTileN + row;
+                const int mn = msg == 0 ? p.n[0] : (msg == 1 ? p.n[1] : p.n[2]);
+                if (moe) {                                 // grouped FP8: the scale row is the row of the STACKED [E * n, k] tensor
+                    const MoeItem mi = p.items[tile];
+                    mrow = mi.n0 + row < mn ? mi.w_row0 + row : 0;
+                } else if (mrow >= mn) mrow = 0;
                 const M4Ctx mc{msg == 0 ? p.scales_seg[0] : (msg == 1 ? p.scales_seg[1] : p.scales_seg[2]), mn, p.group_size, (int)(u - tile_begin) * kSB,
-                               mrow < mn ? mrow : 0, p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm,
+                               mrow, p.scale_bf16, p.debug, p.scale_by, p.scale_sk, p.norm,
                                msg == 0 ? p.zp_seg[0] : (msg == 1 ? p.zp_seg[1] : p.zp_seg[2]), {m4_cur[0], m4_cur[1], m4_cur[2], m4_cur[3]},
                                kPrefetchScales ? 1 : 0};
                 switch (qt) {
@@ -634,6 +639,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 const MoeItem item = p.items[tile];
                 const int n_loc = item.n0 + row;
                 constexpr int kColsPerWarpM = kMB / 4;
+                const float post = (kType == kTypeF8 && p.norm) ? __ldg(p.norm + 1) : 1.f;      // FP8: undo the range shift of the tile scales
 #pragma unroll
                 for (int c0 = 0; c0 < kColsPerWarpM; c0 += 8) {
                     uint32_t acc[8], more[8];
@@ -647,7 +653,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                             if (mi < item.count) {
                                 const uint32_t orow = __ldg(p.row_map + item.x_row0 + mi);
                                 const float sc = p.row_scale ? __ldg(p.row_scale + orow) : 1.f;
-                                p.y[0][(int64_t)orow * p.ldy + n_loc] = (__uint_as_float(acc[i]) + __uint_as_float(more[i])) * sc;
+                                p.y[0][(int64_t)orow * p.ldy + n_loc] = (__uint_as_float(acc[i]) + __uint_as_float(more[i])) * (sc * post);
                             }
                         }
                     }
@@ -1065,6 +1071,40 @@ bool qmatmul_tc_moe_supported(int n, int k, int ggml_type) {
     if (ggml_type == B200_GGML_Q4_K) return true;
     if (ggml_type == B200_GGML_Q6_K) return ((int64_t)(k / 256) * 210) % 16 == 0;
     return false;
+}
+
+// block-scaled FP8 experts (moe_gemm_fp8): w = e4m3 [E * n, k], scale f32 [E * n / by, ceil(k / bx)] (n % by == 0), activations fp16 in
+// NATURAL order; norm = 2 device floats (scratch): the range shift of the scales, computed here
+bool qmatmul_tc_moe_fp8_supported(int n, int k, int by, int bx) { return n >= 1 && k >= 256 && k % 256 == 0 && by >= 1 && n % by == 0 && bx >= 64 && bx % 64 == 0; }
+void qmatmul_tc_moe_fp8(const void* xs_f16, int xs_rows, const void* w, const float* scale, int num_experts, float* y, int64_t ldy, int n, int k, int by, int bx,
+                        const MoeItem* items, const int* num_items, int max_items, const uint32_t* row_map, const float* row_scale, float* norm,
+                        cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) { set_error(kErrCuda, "moe_gemm_fp8: cuTensorMapEncodeTiled unavailable"); return; }
+    if (((uintptr_t)xs_f16 | (uintptr_t)w) & 15) { set_error(kErrBadArg, "moe_gemm_fp8: x and w must be 16-byte aligned"); return; }
+    const int nsb = k / 256, sk = (k + bx - 1) / bx;
+    launch_pdl(fp8_scale_norm_kernel, dim3(1), dim3(256), 0, st, scale, (int64_t)num_experts * (n / by) * sk, norm);
+    count_launch();
+    CUtensorMap wm[kMaxSeg], xm;
+    for (int i = 0; i < kMaxSeg; ++i) if (!make_w_map(&wm[i], w, num_experts * n, nsb, kTypeF8)) return;
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)xs_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+        const cuuint32_t box[2] = {64, 32};
+        const cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(xs_f16), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error(kErrCuda, "moe_gemm_fp8: activation tensor map failed (%d)", (int)r); return; }
+    }
+    if ((int64_t)max_items * nsb * sm_count() >= (int64_t)1 << 31) { set_error(kErrUnsupported, "moe_gemm_fp8: %d items x %d super-blocks exceed the 32-bit unit range", max_items, nsb); return; }
+    GemmParams p{};
+    for (int i = 0; i < kMaxSeg; ++i) { p.y[i] = y; p.n[i] = n; p.tile_end[i] = 0x7fffffff; p.scales_seg[i] = scale; p.zp_seg[i] = nullptr; }
+    p.ldy = ldy; p.m = 32; p.nsb = nsb; p.n_tiles = max_items; p.accumulate = 0; p.whole_tiles = 1;
+    p.items = items; p.num_items = num_items; p.row_map = row_map; p.row_scale = row_scale;
+    p.scales = scale; p.group_size = bx; p.k = k; p.scale_by = by; p.scale_sk = sk; p.norm = norm;
+    launch<32, kTypeF8>(wm, xm, p, st);
+    check_launch("moe_gemm_fp8");
 }
 
 void qmatmul_tc_moe(const void* xs_f16_k4, int xs_rows, const void* w, int num_experts, float* y, int64_t ldy, int n, int k, int ggml_type,

@@ -9,7 +9,7 @@ from typing import Optional, Tuple
 import torch
 
 from ._lib import BackendError, check, lib, require_device
-from .backend import GgmlType, _cuda, _ptr, _stream
+from .backend import DType, GgmlType, _cuda, _ptr, _stream
 
 
 def topk_softmax(router_logits: torch.Tensor, topk: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -59,6 +59,36 @@ def moe_gemm_gguf(xs: torch.Tensor, experts: torch.Tensor, ggml_type: int, shape
                         C.c_int32(xs.shape[0]), C.c_int32(P), C.c_int32(N), C.c_int32(K), C.c_int32(ggml_type), C.c_int32(1 if is_prefill else 0),
                         C.c_void_p(ws.data_ptr() + off), C.c_size_t(need), _stream(xs.device))
     check("moe_gemm_gguf")
+    return out
+
+
+def moe_gemm_fp8(xs: torch.Tensor, experts: torch.Tensor, scale: torch.Tensor, topk_weights: Optional[torch.Tensor], sorted_token_ids: torch.Tensor,
+                 expert_ids: torch.Tensor, topk: int, block_y: int = 128, block_x: int = 128, is_prefill: bool = False) -> torch.Tensor:
+    """attention_rs::moe::moe_gemm_fp8 (moe.rs:1447-1473): xs f16 / bf16 [T or T*k, K]; experts e4m3 (or u8) [E, N, K]; scale f32
+    [E, ceil(N/by), ceil(K/bx)]; -> [T*k, N] in xs' dtype."""
+    _cuda(xs, "xs"); require_device()
+    if experts.dim() != 3 or experts.element_size() != 1:
+        raise BackendError("moe_gemm_fp8: experts must be an 8-bit [E, N, K] tensor")
+    E, N, K = (int(v) for v in experts.shape)
+    if xs.dtype not in (torch.float16, torch.bfloat16) or xs.dim() != 2 or xs.shape[1] != K:
+        raise BackendError(f"moe_gemm_fp8: xs must be f16 / bf16 [rows, {K}]")
+    want = (E, -(-N // block_y), -(-K // block_x))
+    if scale.dtype != torch.float32 or tuple(scale.shape) != want:
+        raise BackendError(f"moe_gemm_fp8: scale must be f32 {want}, got {tuple(scale.shape)} {scale.dtype}")
+    P = sorted_token_ids.numel()
+    out = torch.empty((P, N), dtype=xs.dtype, device=xs.device)
+    L = lib()
+    need = int(L.moe_gemm_fp8_workspace_bytes(C.c_int32(P), C.c_int32(N), C.c_int32(K), C.c_int32(E)))
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=xs.device)
+    off = (-ws.data_ptr()) % 256
+    tw = None if topk_weights is None else topk_weights.reshape(-1).float().contiguous()
+    ex = experts.contiguous().view(torch.uint8)
+    with torch.cuda.device(xs.device):
+        L.moe_gemm_fp8(_ptr(xs.contiguous()), _ptr(ex), _ptr(scale.contiguous()), _ptr(tw), _ptr(sorted_token_ids), _ptr(expert_ids), _ptr(out),
+                       C.c_int32(E), C.c_int32(topk), C.c_int32(xs.shape[0]), C.c_int32(P), C.c_int32(N), C.c_int32(K), C.c_int32(block_y),
+                       C.c_int32(block_x), C.c_int32(DType.F16 if xs.dtype == torch.float16 else DType.BF16), C.c_int32(1 if is_prefill else 0),
+                       C.c_void_p(ws.data_ptr() + off), C.c_size_t(need), _stream(xs.device))
+    check("moe_gemm_fp8")
     return out
 
 

@@ -253,6 +253,17 @@ void moe_gemm_gguf(const float* x, const void* experts, const float* topk_weight
                    float* out, int32_t num_experts, int32_t topk, int32_t size_m, int32_t num_pairs, int32_t n, int32_t k, int32_t ggml_type,
                    int32_t is_prefill, void* workspace, size_t workspace_bytes, int64_t stream);
 
+/* moe_gemm_fp8 -- replaces attention_rs::moe::moe_gemm_fp8 (call sites /root/reference/src/openai/models/layers/moe.rs:1447-1473, block-FP8
+ * experts as in DeepSeek-V3 / Qwen3 FP8 checkpoints): x [size_m, k] and out [num_pairs, n] of `dtype` (B200_F16 / B200_BF16); experts e4m3
+ * [E, n, k]; scale f32 [E, ceil(n / block_y), ceil(k / block_x)] multiplies the weight tile; routing arguments as moe_gemm_gguf.  Weight-only:
+ * activations are rounded to fp16, weights decoded exactly, fp32 accumulation, one rounding to `dtype`.  k % 256 == 0, n % block_y == 0,
+ * block_x % 64 == 0 run grouped on the tcgen05 pipeline; other shapes on a shape-generic kernel.  workspace: moe_gemm_fp8_workspace_bytes(),
+ * 256-byte aligned (required). */
+size_t moe_gemm_fp8_workspace_bytes(int32_t num_pairs, int32_t n, int32_t k, int32_t num_experts);
+void moe_gemm_fp8(const void* x, const void* experts, const float* scale, const float* topk_weights, const uint32_t* sorted_token_ids,
+                  const uint32_t* expert_ids, void* out, int32_t num_experts, int32_t topk, int32_t size_m, int32_t num_pairs, int32_t n, int32_t k,
+                  int32_t block_y, int32_t block_x, int32_t dtype, int32_t is_prefill, void* workspace, size_t workspace_bytes, int64_t stream);
+
 /* ---- K15 / K21: the elementwise ops between the big ones ------------------------------------
  * rms_norm: candle_nn::ops::rms_norm (layers/qrmsnorm.rs:28-31).  out_dtype F32 or F16. */
 void rms_norm(const float* x, const float* weight, void* out, int32_t rows, int32_t n, float eps,

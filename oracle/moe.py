@@ -45,6 +45,23 @@ def moe_gemm(x, stacked, ggml_type, E, n, k, topk_ids_flat, topk, weights_flat=N
     return out.astype(np.float32)
 
 
+def moe_gemm_fp8(x, experts_u8, scale, by, bx, topk_ids_flat, topk, weights_flat=None):
+    """moe.rs:1447-1473 with block-FP8 experts: experts e4m3 bytes [E, n, k], scale f32 [E, ceil(n/by), ceil(k/bx)]."""
+    from . import fp_formats as F
+    P = len(topk_ids_flat)
+    x = np.asarray(x, np.float64)
+    E, n, k = experts_u8.shape
+    per_token = x.shape[0] != P
+    out = np.zeros((P, n), np.float64)
+    for e in np.unique(topk_ids_flat):
+        w = F.dequant_fp8_block(experts_u8[int(e)], scale[int(e)], by, bx).astype(np.float64)
+        for p in np.nonzero(topk_ids_flat == e)[0]:
+            out[p] = w @ x[p // topk if per_token else p]
+            if weights_flat is not None:
+                out[p] *= weights_flat[p]
+    return out.astype(np.float32)
+
+
 def fused_moe(x, gate, ge, ue, de, types, E, H, I, k, norm_topk_prob=True, routed_scaling_factor=None):
     x = np.asarray(x, np.float32)
     w, ids = topk_softmax(x.astype(np.float64) @ np.asarray(gate, np.float64).T, k)

@@ -76,3 +76,32 @@ def test_fused_moe_block_matches_oracle():
     y = blk.forward(t(x)).cpu().numpy()
     ref, (rw, rids) = OM.fused_moe(x, gate, ge, ue, de, (12, 12, 12), E, H, I, k)
     assert y.shape == (T, H) and rel_fro(y, ref) < 2e-3, rel_fro(y, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("E,N,K,T,k,by,bx", [
+    (16, 512, 2048, 16, 4, 128, 128),     # decode batch on block-FP8 experts (DeepSeek-V3 / Qwen3-FP8 block size)
+    (8, 256, 768, 70, 2, 128, 128),       # > 32 rows per expert (several chunks), k = 3 super-blocks
+    (4, 100, 96, 5, 2, 128, 128),         # ragged shapes: shape-generic kernel
+])
+def test_moe_gemm_fp8_matches_oracle(dtype, E, N, K, T, k, by, bx):
+    """moe_gemm_fp8 (moe.rs:1447-1473): block-scaled e4m3 experts, 16-bit activations and outputs.  Grouped tcgen05 path for k % 256 == 0,
+    n % by == 0; tolerance as fp8_matmul (fp16 operands, one rounding of the output)."""
+    from oracle import fp_formats as F
+    rng = np.random.default_rng(E + N + K + T)
+    w = rng.integers(0, 0x7f, (E, N, K), dtype=np.uint8) | (rng.integers(0, 2, (E, N, K), dtype=np.uint8) << 7)
+    w[(w & 0x7f) == 0x7f] = 0x7e                                                  # no NaN codes
+    sc = (rng.uniform(0.5, 2.0, (E, -(-N // by), -(-K // bx))) * 1e-3).astype(np.float32)     # checkpoint-sized scales (~1e-3)
+    ids = np.stack([rng.permutation(E)[:k] for _ in range(T)]).astype(np.int32)
+    tw = rng.uniform(0.05, 0.5, (T, k)).astype(np.float32)
+    x = torch.from_numpy(rng.standard_normal((T, K)).astype(np.float32)).to(DEV).to(dtype)
+    xp = torch.from_numpy(rng.standard_normal((T * k, K)).astype(np.float32)).to(DEV).to(dtype)
+    wt, st = torch.from_numpy(w).to(DEV), torch.from_numpy(sc).to(DEV)
+    e, s = pkg.sort_expert_assignments(torch.from_numpy(ids).to(DEV), E)
+    tol = 1e-3 if dtype == torch.float16 else 4e-3
+    y = pkg.moe_gemm_fp8(x, wt, st, None, s, e, k, by, bx).float().cpu().numpy()
+    ref = OM.moe_gemm_fp8(x.float().cpu().numpy(), w, sc, by, bx, ids.reshape(-1), k)
+    assert y.shape == (T * k, N) and np.isfinite(y).all() and rel_fro(y, ref) < tol, rel_fro(y, ref)
+    y = pkg.moe_gemm_fp8(xp, wt, st, torch.from_numpy(tw).to(DEV), s, e, k, by, bx).float().cpu().numpy()
+    ref = OM.moe_gemm_fp8(xp.float().cpu().numpy(), w, sc, by, bx, ids.reshape(-1), k, tw.reshape(-1))
+    assert rel_fro(y, ref) < tol, rel_fro(y, ref)
