@@ -119,17 +119,23 @@ def cpu_sample_setup(batch: int, ctx: int):
     one_layer()                                                    # warm the team and the page tables (not counted)
 
     def step():
-        """one bounded sample -> seconds for a FULL decode step (scaled): two full decoder layers + a lm_head row slice"""
+        """one decode step of the whole model, nothing extrapolated: 32 decoder-layer passes (one layer's weights and KV reused -- 123 MB +
+        1 GB per pass, far beyond the CPU caches) + the Q6_K lm_head over all `V` rows in slices of `rows`.  Returns seconds."""
         assert keep
-        t_layer = 0.5 * (one_layer() + one_layer())
+        t_layers = sum(one_layer() for _ in range(32))
         t0 = time.perf_counter()
-        cpu_ref.qmatmul_q8k(xh, w6, 14, rows, H)
+        done = 0
+        while done < V:
+            r = min(rows, V - done)
+            cpu_ref.qmatmul_q8k(xh, w6[:r * (H // 256) * 210], 14, r, H)
+            done += r
         t_head = time.perf_counter() - t0
-        return 32 * t_layer + t_head * (V / rows), t_layer, t_head
+        return t_layers + t_head, t_layers / 32, t_head
 
     info = dict(cores=cpu_ref.num_threads(), kind="port",
-                sample=f"per step: 2 of 32 decoder layers (batch {batch}, ctx {ctx}, Q4_K x Q8_K int dot + f32 paged "
-                       f"attention) + {rows}/{V} Q6_K lm_head rows, scaled to the full model; {n_thr} threads = "
+                sample=f"per step: all 32 decoder layers (batch {batch}, ctx {ctx}, Q4_K x Q8_K int dot + f32 paged attention; the "
+                       f"weights and KV of one layer are reused for every pass) + the full {V}-row Q6_K lm_head -- a complete decode step, "
+                       f"nothing scaled; {n_thr} threads = "
                        f"{'half the ' + str(avail) + ' schedulable logical CPUs' if avail >= 16 else 'all schedulable CPUs'}; mean over samples")
     return step, info
 
@@ -146,26 +152,44 @@ def cpu_decode_sample(batch: int, ctx: int, budget_s: float):
     return batch / mean, mean, info
 
 
+def timed_window(args):
+    """context lengths (including the decoded token) of the K timed steps: identical for both arms"""
+    ctx0 = args.ctx + args.parity_steps
+    return ctx0 + 1 + args.warmup + 1, ctx0 + 1 + args.warmup + args.steps
+
+
+def workload_config(args, world: int, layers: int = 32) -> dict:
+    """`config` of the JSON line -- the SAME dict from `--impl reference` and from the GPU arm (same workload, same window)."""
+    first, last = timed_window(args)
+    name = {"q4k": "Llama-3-8B Q4_K (lm_head Q6_K)", "dense_bf16": "Llama-3-8B BF16 (dense)",
+            "gptq_fp8kv": "Llama-3-8B GPTQ int4 g128 (Marlin-prepared; lm_head Q6_K)"}[args.config]
+    kv = args.kv or {"q4k": "bf16", "dense_bf16": "bf16", "gptq_fp8kv": "fp8"}[args.config]
+    return {"workload": f"{name} decode, batch {args.batch}, ctx {first}->{last} of 4096->5120, block_size 64, {kv} paged KV, "
+                        f"random non-contiguous block tables",
+            "parallelism": f"tp{world}", "global_batch": args.batch, "layers": layers,
+            "l2_policy": "inputs larger than L2 (KV 17+ GB and weights 4.4 GB streamed per step; 126 MB L2)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (C port; the Rust reference cannot be built here)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step, info = cpu_sample_setup(args.batch, args.ctx)
+    step, info = cpu_sample_setup(args.batch, timed_window(args)[0])       # the first context of the timed window
     vals, t_begin = [], time.perf_counter()
     for i in range(args.warmup + args.steps):
         t_step, _, _ = step()
         if i >= args.warmup or (time.perf_counter() - t_begin) > 60:
             vals.append((args.batch / t_step, t_step))
-        if vals and (time.perf_counter() - t_begin) > 150:       # keep the whole run within a few minutes
+        if vals and (time.perf_counter() - t_begin) > 170:       # keep the whole run within a few minutes (the line reports how many steps ran)
             break
     ms = statistics.mean(v[1] for v in vals) * 1e3                  # same statistic as the cpu_baseline leg: mean seconds per step
     tps = args.batch / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "q4_k weights x q8_k activations (int8 dot), f32 attention", "data": "synthetic",
-            "config": {"workload": f"Llama-3-8B Q4_K decode, batch {args.batch}, ctx {args.ctx}, block_size 64, bf16 paged KV",
-                       "note": "CPU arm runs on host cores only; each step is a bounded sample scaled to the full model"},
+            "config": workload_config(args, args.gpus),
+            "note": "CPU arm (host cores only, rank 0): every step is a complete decode step of the same workload (one layer's weights / KV reused across the 32 layer passes)",
             "cpu_baseline": {"value": tps, "unit": UNIT, **info},
             "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -387,17 +411,20 @@ def run_b200(args):
         return ms_total / K, sampler.stop(), model.kernel_launches() - l0, (ctx0 + 1 + W + 1, ctx0 + 1 + W + K)
 
     ms_step, clocks, launches, (ctx_first, ctx_last) = resident_leg(args.ctx + PS)
+    assert (ctx_first, ctx_last) == timed_window(args)
     value = B / (ms_step * 1e-3)
     # the metric is quoted over ctx 4096 -> 5120 (mean 4608): the same leg centred on the mean context
     mid0 = max(args.ctx, 4608 - (W + K) // 2 - 1)
     ms_mid, clocks_mid, _, (mid_first, mid_last) = resident_leg(mid0)
 
     # ---- (2) end to end through the host API -------------------------------------------------------
-    cur = mid_last + 1
+    # over the SAME context window as `value` (ctx_first -> ctx_last), so that the two numbers differ by the host path only
+    n_warm = min(W, 3)
+    cur = ctx_first - n_warm
     nxt = model.read_next_tokens(B)
     h2d = B * (8 + 8 + 8 + 4) + B * blocks_per_seq * 4
     d2h = B * 4
-    for _ in range(min(W, 3)):
+    for _ in range(n_warm):
         prep = pkg.prepare_decode(np.full(B, cur), nxt, tables_np, bs)
         nxt, _ = model.decode(prep); cur += 1
     barrier()
@@ -439,10 +466,8 @@ def run_b200(args):
     line = {"metric": conf["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": conf["dtype"], "data": "synthetic",
-            "config": {"workload": f"{conf['name']} decode, batch {B}, ctx {ctx_first}->{ctx_last} of 4096->5120, "
-                                   f"block_size {bs}, {args.kv} paged KV, random non-contiguous block tables",
-                       "parallelism": f"tp{world}" + ("" if world == 1 else (" (fused all-reduce + add + norm over NVLink peer memory)" if peer_ar else " (NCCL all-reduce)")), "global_batch": B, "layers": cfg.num_layers,
-                       "l2_policy": "inputs larger than L2 (KV 17+ GB and weights 4.4 GB streamed per step; 126 MB L2)"},
+            "config": workload_config(args, world, cfg.num_layers),
+            "all_reduce": None if world == 1 else ("fused all-reduce + add + norm over NVLink peer memory" if peer_ar else "NCCL all-reduce"),
             "value_mean_ctx": {"value": B / (ms_mid * 1e-3), "unit": UNIT, "ms_per_step": ms_mid, "ctx": f"{mid_first}->{mid_last}",
                                "note": "same leg centred on the metric's mean context 4608 (attention bytes +12 % over ctx 4096)",
                                "clocks": clocks_mid},
@@ -455,7 +480,7 @@ def run_b200(args):
     if cfg.num_layers != 32:
         line["invalid"] = "debug run with fewer layers"
     if not args.no_cpu_baseline and world == 1 and args.config == "q4k":      # the CPU arm is the reference's GGUF/GGML path
-        tps, t_step, info = cpu_decode_sample(B, args.ctx, args.cpu_seconds)
+        tps, t_step, info = cpu_decode_sample(B, timed_window(args)[0], args.cpu_seconds)
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, **info}
     print(json.dumps(line), flush=True)
     if world > 1:
