@@ -122,9 +122,12 @@ __device__ __forceinline__ int marlin_scale_pos(int n, bool grouped) {
 template <int kC>
 struct M4Quarter {
     static constexpr int kRaw = 8;
-    static __device__ __forceinline__ void load(const uint8_t* blk, int, uint32_t (&raw)[kRaw]) {
-        const uint4 qa = *reinterpret_cast<const uint4*>(blk + kC * 32);
-        const uint4 qb = *reinterpret_cast<const uint4*>(blk + kC * 32 + 16);
+    // the unit's 128 rows x 128 bytes land with the 128-byte TMA swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)): the threads of
+    // a quarter-warp read 8 different bank groups.  [Unswizzled, every lane of a warp hit the same 4 banks -- 8-way conflicts on both
+    // LDS.128 of every unit, which alone cost as much as a whole Q4_K unit.]
+    static __device__ __forceinline__ void load(const uint8_t* blk, int r7, uint32_t (&raw)[kRaw]) {
+        const uint4 qa = *reinterpret_cast<const uint4*>(blk + (((2 * kC) ^ r7) << 4));
+        const uint4 qb = *reinterpret_cast<const uint4*>(blk + (((2 * kC + 1) ^ r7) << 4));
         raw[0] = qa.x; raw[1] = qa.y; raw[2] = qa.z; raw[3] = qa.w; raw[4] = qb.x; raw[5] = qb.y; raw[6] = qb.z; raw[7] = qb.w;
     }
     static __device__ __forceinline__ float scale_at(const M4Ctx& c, int k) {
@@ -225,9 +228,12 @@ struct F8Quarter {
 template <int kC, bool kMx>
 struct F4Quarter {
     static constexpr int kRaw = 8;
-    static __device__ __forceinline__ void load(const uint8_t* blk, int, uint32_t (&raw)[kRaw]) {
-        const uint4 qa = *reinterpret_cast<const uint4*>(blk + kC * 32);
-        const uint4 qb = *reinterpret_cast<const uint4*>(blk + kC * 32 + 16);
+    // the unit's 128 rows x 128 bytes land with the 128-byte TMA swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)): the threads of
+    // a quarter-warp read 8 different bank groups.  [Unswizzled, every lane of a warp hit the same 4 banks -- 8-way conflicts on both
+    // LDS.128 of every unit, which alone cost as much as a whole Q4_K unit.]
+    static __device__ __forceinline__ void load(const uint8_t* blk, int r7, uint32_t (&raw)[kRaw]) {
+        const uint4 qa = *reinterpret_cast<const uint4*>(blk + (((2 * kC) ^ r7) << 4));
+        const uint4 qb = *reinterpret_cast<const uint4*>(blk + (((2 * kC + 1) ^ r7) << 4));
         raw[0] = qa.x; raw[1] = qa.y; raw[2] = qa.z; raw[3] = qa.w; raw[4] = qb.x; raw[5] = qb.y; raw[6] = qb.z; raw[7] = qb.w;
     }
     static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
@@ -601,7 +607,8 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) p.trace[it * 8 + 4] = clock64();
                 const uint8_t* blk = smem + C::kWOff + ws * C::kWBytes + (kType == kTypeF8 ? 0 : row * C::kBlk);    // fp8: stage base (swizzled rows)
                 const uint32_t a_col = tmem + kColA + ab * 128 + lane_addr;
-                const int off = kType == kTypeF8 ? row : (kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15));   // Q6_K: block offset in its window
+                // fp8: row (stage-relative addressing); 4-bit rows: swizzle key; Q6_K: block offset in its window
+                const int off = kType == kTypeF8 ? row : (is_4bit_rows(kType) ? (row & 7) : (kType == B200_GGML_Q4_K ? 0 : (((int)(u - tile_begin) * 210) & 15)));
                 const uint32_t afp = aph ^ 1;
                 const bool skip = (p.debug & 2) != 0;
                 // marlin: the scales / zero points of the weight matrix this tile belongs to (constant indices only, see seg_first_tile)
@@ -766,7 +773,7 @@ bool make_w_map(CUtensorMap* wm, const void* w, int n, int nsb, int ggml_type) {
     const cuuint32_t box[2] = {(cuuint32_t)(q4 ? 144 : ((m4 || f8) ? 128 : 240)), (cuuint32_t)kTileN};
     const cuuint32_t es[2] = {1, 1};
     const CUresult r = enc(wm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           f8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           (f8 || m4) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error(kErrCuda, "qmatmul: weight tensor map failed (%d)", (int)r); return false; }
     return true;
