@@ -130,26 +130,39 @@ struct M4Quarter {
         const uint4 qb = *reinterpret_cast<const uint4*>(blk + (((2 * kC + 1) ^ r7) << 4));
         raw[0] = qa.x; raw[1] = qa.y; raw[2] = qa.z; raw[3] = qa.w; raw[4] = qb.x; raw[5] = qb.y; raw[6] = qb.z; raw[7] = qb.w;
     }
-    static __device__ __forceinline__ float scale_at(const M4Ctx& c, int k) {
+    // raw fetches (no arithmetic on the loaded value: issued one unit ahead, the consumer converts them when it needs them)
+    static __device__ __forceinline__ uint32_t scale_bits_at(const M4Ctx& c, int k) {
         const bool grouped = c.group_size > 0;
         const int g = grouped ? k / c.group_size : 0;
         const int64_t idx = (int64_t)g * c.n_total + marlin_scale_pos(c.n_idx, grouped);
-        return c.bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(c.scales)[idx]) : __half2float(static_cast<const __half*>(c.scales)[idx]);
+        return static_cast<const unsigned short*>(c.scales)[idx];
     }
+    static __device__ __forceinline__ float scale_from_bits(const M4Ctx& c, uint32_t bits) {
+        return c.bf16 ? __uint_as_float(bits << 16) : __half2float(__ushort_as_half((unsigned short)bits));
+    }
+    static __device__ __forceinline__ float scale_at(const M4Ctx& c, int k) { return scale_from_bits(c, scale_bits_at(c, k)); }
     // zero point of column n_idx in group g: symmetric GPTQ = 8; AWQ = nibble of the packed [G, N/8] tensor in the layout the
     // reference's converter writes (examples/convert_awq_marlin.py:75-113: scale_perm inside 64-column blocks, then the
     // [0,2,4,6,1,3,5,7] interleave inside 8): column b of a block sits in word (b & 7), nibble inv_interleave[b >> 3]
-    static __device__ __forceinline__ float zero_at(const M4Ctx& c, int k) {
-        if (!c.zp) return 8.f;
+    static __device__ __forceinline__ uint32_t zero_word_at(const M4Ctx& c, int k) {
+        if (!c.zp) return 0u;
         const int g = c.group_size > 0 ? k / c.group_size : 0;
         const int b = c.n_idx & 63;
-        const uint32_t word = c.zp[(int64_t)g * (c.n_total >> 3) + ((c.n_idx >> 6) << 3) + (b & 7)];
+        return c.zp[(int64_t)g * (c.n_total >> 3) + ((c.n_idx >> 6) << 3) + (b & 7)];
+    }
+    static __device__ __forceinline__ float zero_from_word(const M4Ctx& c, uint32_t word) {
+        if (!c.zp) return 8.f;
+        const int b = c.n_idx & 63;
         const int nib = (0x73625140u >> (4 * (b >> 3))) & 7;          // inverse of [0,2,4,6,1,3,5,7]: 0,4,1,5,2,6,3,7
         return (float)((word >> (4 * nib)) & 0xFu);
     }
+    static __device__ __forceinline__ float zero_at(const M4Ctx& c, int k) { return zero_from_word(c, zero_word_at(c, k)); }
     static __device__ __forceinline__ void compute(const uint32_t (&raw)[kRaw], const M4Ctx& c, uint32_t a_col) {
-        const float s0 = c.has_pre ? c.pre[0] : scale_at(c, c.k0 + kC * 64), s1 = c.has_pre ? c.pre[1] : scale_at(c, c.k0 + kC * 64 + 32);
-        const float z0 = c.has_pre ? c.pre[2] : zero_at(c, c.k0 + kC * 64), z1 = c.has_pre ? c.pre[3] : zero_at(c, c.k0 + kC * 64 + 32);
+        // c.pre: the raw scale bits / zero-point words of this quarter, fetched one unit ahead (bit-cast floats)
+        const float s0 = c.has_pre ? scale_from_bits(c, __float_as_uint(c.pre[0])) : scale_at(c, c.k0 + kC * 64);
+        const float s1 = c.has_pre ? scale_from_bits(c, __float_as_uint(c.pre[1])) : scale_at(c, c.k0 + kC * 64 + 32);
+        const float z0 = c.has_pre ? zero_from_word(c, __float_as_uint(c.pre[2])) : zero_at(c, c.k0 + kC * 64);
+        const float z1 = c.has_pre ? zero_from_word(c, __float_as_uint(c.pre[3])) : zero_at(c, c.k0 + kC * 64 + 32);
         const bool fast = __all_sync(0xffffffffu, fmaxf(fabsf(s0), fabsf(s1)) * 262144.f <= 65504.f);
         const __half2 s_lo = __float2half2_rn(fast ? s0 * 262144.f : s0), s_hi = __float2half2_rn(fast ? s1 * 262144.f : s1);
         const __half2 n_lo = __float2half2_rn(-z0 * s0), n_hi = __float2half2_rn(-z1 * s1);
@@ -577,7 +590,7 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
         int tile = (int)tile0;
         // int4: the group scales / zero points live in global memory (the checkpoint's tensors), two dependent L2 round trips per unit
         // if loaded on demand -- they are fetched ONE UNIT AHEAD instead (weights: no dependency on the previous kernel)
-        float m4_next[4] = {0.f, 0.f, 8.f, 8.f};
+        float m4_next[4] = {0.f, 0.f, 0.f, 0.f};
         auto m4_fetch = [&](int tl, int sbx) {
             const int sgx = seg_of_tile(p, tl);
             const int rw = (tl - seg_first_tile(p, sgx)) * kTileN + row, nn = sgx == 0 ? p.n[0] : (sgx == 1 ? p.n[1] : p.n[2]);
@@ -589,8 +602,8 @@ qmatmul_tc_kernel(const __grid_constant__ CUtensorMap wmap0, const __grid_consta
                 m4_next[0] = __uint_as_float(kType == kTypeMX4 ? (uint32_t)*reinterpret_cast<const uint16_t*>(srow + (kq >> 5))
                                                                : *reinterpret_cast<const uint32_t*>(srow + (kq >> 4)));
             } else {
-                m4_next[0] = M4Quarter<0>::scale_at(c, kq); m4_next[1] = M4Quarter<0>::scale_at(c, kq + 32);
-                m4_next[2] = M4Quarter<0>::zero_at(c, kq); m4_next[3] = M4Quarter<0>::zero_at(c, kq + 32);
+                m4_next[0] = __uint_as_float(M4Quarter<0>::scale_bits_at(c, kq)); m4_next[1] = __uint_as_float(M4Quarter<0>::scale_bits_at(c, kq + 32));
+                m4_next[2] = __uint_as_float(M4Quarter<0>::zero_word_at(c, kq)); m4_next[3] = __uint_as_float(M4Quarter<0>::zero_word_at(c, kq + 32));
             }
         };
         constexpr bool kPrefetchScales = kType == kTypeM4 || is_fp4(kType);
