@@ -43,6 +43,29 @@ def kv_head_shard(num_kv_heads: int, rank: int, world: int) -> Tuple[int, int]:
     return 1, rank // (world // num_kv_heads)      # replicate each head over world/kvh ranks
 
 
+def allocate_mla_cache(num_layers: int, num_blocks: int, block_size: int, kv_lora_rank: int, qk_rope_head_dim: int,
+                       dtype: torch.dtype = torch.bfloat16, device="cuda") -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    """MLA models (cache_engine.rs:172-185): per layer the compressed KV ``[nb, bs, 1, kv_lora_rank]`` and the rope keys
+    ``[nb, bs, 1, qk_rope_head_dim]`` -- what ``mla.concat_and_cache_mla`` writes and ``mla.mla_paged_decode`` reads."""
+    return [(torch.zeros((num_blocks, block_size, 1, kv_lora_rank), dtype=dtype, device=device),
+             torch.zeros((num_blocks, block_size, 1, qk_rope_head_dim), dtype=dtype, device=device)) for _ in range(num_layers)]
+
+
+def turboquant_layer_shapes(mode: str, num_blocks: int, block_size: int, num_kv_heads: int, head_dim: int, num_shards: int = 1) -> Dict[str, tuple]:
+    """STORAGE shapes of the TurboQuant KV cache (cache_engine.rs:401-482); ``mode`` in {"turbo8", "turbo4", "turbo3"}.  Only the
+    allocation is visible in the reference -- the transform (WHT + absmax quantisation) lives in attention-rs -- so this backend
+    offers the shapes for sizing and block bookkeeping, and no kernels."""
+    if mode not in ("turbo8", "turbo4", "turbo3"):
+        raise BackendError(f"unknown TurboQuant mode {mode!r}")
+    kvh = max(num_kv_heads // max(num_shards, 1), 1)
+    shapes = {"v_absmax": (num_blocks, block_size, kvh), "v_quant": (num_blocks, block_size, kvh, head_dim // 2)}
+    if mode == "turbo4":
+        shapes.update(k_absmax=(num_blocks, block_size, kvh), k_quant=(num_blocks, block_size, kvh, head_dim // 2))
+    elif mode == "turbo3":
+        shapes.update(k_absmax=(num_blocks, block_size, kvh), k_quant=(num_blocks, block_size, kvh, (head_dim * 3 + 7) // 8))
+    return shapes            # turbo8: K stays in the regular FP8 cache (no k_* tensors), as upstream
+
+
 class CacheEngine:
     def __init__(self, num_layers: int, num_kv_heads: int, head_dim: int, cache_config: CacheConfig,
                  dtype: torch.dtype = torch.bfloat16, device="cuda", num_shards: int = 1,

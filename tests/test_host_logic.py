@@ -120,3 +120,20 @@ def test_flashinfer_csr_matches_the_reference_construction():
     assert csr["indices"].tolist() == [3, 5, 7, 1, 9, 0, 2]
     assert csr["last_len"].tolist() == [1, 64, 1, 2, 0]
     assert csr["kv_len"].tolist() == [1, 64, 65, 130, 0]
+
+
+def test_mla_and_turboquant_storage_shapes_follow_the_reference():
+    """cache_engine.rs:172-185 (MLA) and :401-482 (TurboQuant storage; shapes only -- the algorithm is not in the reference tree)."""
+    import torch
+    from candle_vllm_b200.cache_engine import allocate_mla_cache, turboquant_layer_shapes
+    c = allocate_mla_cache(2, 5, 64, 512, 64, dtype=torch.bfloat16, device="cpu")
+    assert len(c) == 2 and c[0][0].shape == (5, 64, 1, 512) and c[0][1].shape == (5, 64, 1, 64) and c[1][0].dtype == torch.bfloat16
+    s4 = turboquant_layer_shapes("turbo4", 10, 64, 8, 128, num_shards=2)
+    assert s4 == {"v_absmax": (10, 64, 4), "v_quant": (10, 64, 4, 64), "k_absmax": (10, 64, 4), "k_quant": (10, 64, 4, 64)}
+    s3 = turboquant_layer_shapes("turbo3", 10, 64, 8, 128)
+    assert s3["k_quant"] == (10, 64, 8, 48) and s3["v_quant"] == (10, 64, 8, 64)
+    assert set(turboquant_layer_shapes("turbo8", 1, 64, 8, 128)) == {"v_absmax", "v_quant"}
+    import pytest
+    from candle_vllm_b200 import BackendError
+    with pytest.raises(BackendError):
+        turboquant_layer_shapes("turbo5", 1, 64, 8, 128)
