@@ -48,3 +48,14 @@ def test_e4m3_bits_moved_down_by_one_is_the_value_times_2_pow_minus_8():
     y = b << 8                                                          # the byte in the high half of a 16-bit lane
     f16_bits = ((y >> 1) & 0x3f80) | (y & 0x8000)
     assert np.array_equal(_f16(f16_bits) * 2.0 ** 8, F.e4m3_to_f32(b.astype(np.uint8)).astype(np.float64))
+
+
+def test_ggml_nibble_and_6bit_subnormal_placements():
+    """Q4_K / int4: a nibble at f16 mantissa bits 6..9 is q * 2^-18; Q6_K: a 6-bit value at bits 4..9 is q * 2^-20 (both f16 subnormals):
+    one HFMA2 with (scale * 2^18 | 2^20, offset) then yields scale * q + offset with a single rounding."""
+    q4 = np.arange(16, dtype=np.uint16)
+    assert np.array_equal(_f16(q4 << 6) * 2.0 ** 18, q4.astype(np.float64))
+    q6 = np.arange(64, dtype=np.uint16)
+    assert np.array_equal(_f16(q6 << 4) * 2.0 ** 20, q6.astype(np.float64))
+    # the exact fallback: (1024 + q) as f16 via the 0x6400 magic, minus 1024
+    assert np.array_equal(_f16(q4 | 0x6400) - 1024.0, q4.astype(np.float64))
